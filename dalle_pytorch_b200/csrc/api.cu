@@ -1,0 +1,231 @@
+// C ABI of libdalle_b200.so (include/dalle_b200.h): argument validation and dispatch to the kernels.
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace db200 {
+
+std::string& last_error_slot() {
+  static thread_local std::string s;
+  return s;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_slot() = buf;
+  return code;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// kernels (other translation units)
+int ln_shift_fwd_launch(const db200_ln_shift_fwd_params& P, cudaStream_t st);
+int ln_shift_bwd_launch(const db200_ln_shift_bwd_params& P, cudaStream_t st);
+int scale_bwd_launch(const db200_scale_bwd_params& P, cudaStream_t st);
+int colsum_launch(const void* x, int dtype, int rows, int cols, float* out, cudaStream_t st);
+int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st);
+int axpby_launch(const float* a, const float* b, float alpha, float* y, int64_t count, cudaStream_t st);
+int gemm_simt_launch(const db200_gemm_params& p, cudaStream_t st);
+bool gemm_tcgen05_supported(const db200_gemm_params& p, const char** why);
+int gemm_tcgen05_launch(const db200_gemm_params& p, cudaStream_t st);
+int attn_fwd_simt_launch(const db200_attn_fwd_params& p, cudaStream_t st);
+int attn_bwd_simt_launch(const db200_attn_bwd_params& p, cudaStream_t st);
+bool attn_mma_supported(const db200_attn_fwd_params& p);
+int attn_fwd_mma_launch(const db200_attn_fwd_params& p, cudaStream_t st);
+int attn_bwd_mma_launch(const db200_attn_bwd_params& p, cudaStream_t st);
+
+static bool dtype_ok(int d) { return d == DB200_F32 || d == DB200_BF16; }
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// DALLE_B200_GEMM=simt|tcgen05 and DALLE_B200_ATTN=simt|mma override the AUTO choice (debugging / A-B timing)
+static int env_choice(const char* name, const char* a, const char* b) {
+  const char* v = getenv(name);
+  if (!v) return 0;
+  if (!strcmp(v, a)) return 1;
+  if (!strcmp(v, b)) return 2;
+  return 0;
+}
+
+}  // namespace db200
+
+using namespace db200;
+
+extern "C" {
+
+int dalle_b200_version(void) { return DALLE_B200_VERSION; }
+
+const char* dalle_b200_last_error(void) { return last_error_slot().c_str(); }
+
+int dalle_b200_device_ok(int dev) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+  return prop.major == 10 ? 1 : 0;
+}
+
+int dalle_b200_abi_sizes(int* out, int capacity) {
+  const int sizes[6] = {(int)sizeof(db200_ln_shift_fwd_params), (int)sizeof(db200_ln_shift_bwd_params), (int)sizeof(db200_gemm_params),
+                        (int)sizeof(db200_attn_fwd_params),     (int)sizeof(db200_attn_bwd_params),     (int)sizeof(db200_scale_bwd_params)};
+  for (int i = 0; i < 6 && i < capacity; ++i) out[i] = sizes[i];
+  return 6;
+}
+
+int dalle_b200_ln_shift_fwd(const db200_ln_shift_fwd_params* p, void* stream) {
+  DB200_CHECK_ARG(p != nullptr, "ln_shift_fwd: null params");
+  DB200_CHECK_ARG(p->batch >= 0 && p->n >= 0 && p->d > 0, "ln_shift_fwd: bad shape b=%d n=%d d=%d", p->batch, p->n, p->d);
+  DB200_CHECK_ARG(dtype_ok(p->out_dtype), "ln_shift_fwd: bad dtype %d", p->out_dtype);
+  DB200_CHECK_ARG(p->d % (p->do_shift ? 16 : 4) == 0, "ln_shift_fwd: d=%d must be a multiple of %d", p->d, p->do_shift ? 16 : 4);
+  DB200_CHECK_ARG(p->x && p->out, "ln_shift_fwd: null tensor");
+  DB200_CHECK_ARG(aligned16(p->x) && aligned16(p->out), "ln_shift_fwd: tensors must be 16-byte aligned");
+  if (p->do_ln) DB200_CHECK_ARG(p->gamma && p->beta && p->mean && p->rstd, "ln_shift_fwd: LayerNorm needs gamma/beta/mean/rstd");
+  if (p->do_shift) {
+    DB200_CHECK_ARG(p->fmap > 0 && p->text_len > 0, "ln_shift_fwd: shift needs text_len/fmap");
+    DB200_CHECK_ARG(p->n >= p->text_len, "ln_shift_fwd: n=%d < text_len=%d is the no-shift case (transformer.py:160)", p->n, p->text_len);
+    DB200_CHECK_ARG(p->n <= p->text_len + p->fmap * p->fmap, "ln_shift_fwd: n=%d exceeds text_len + fmap^2", p->n);
+  }
+  return ln_shift_fwd_launch(*p, (cudaStream_t)stream);
+}
+
+int dalle_b200_ln_shift_bwd(const db200_ln_shift_bwd_params* p, void* stream) {
+  DB200_CHECK_ARG(p != nullptr, "ln_shift_bwd: null params");
+  DB200_CHECK_ARG(p->batch >= 0 && p->n >= 0 && p->d > 0, "ln_shift_bwd: bad shape");
+  DB200_CHECK_ARG(dtype_ok(p->dout_dtype), "ln_shift_bwd: bad dtype %d", p->dout_dtype);
+  DB200_CHECK_ARG(p->d % (p->do_shift ? 16 : 4) == 0, "ln_shift_bwd: d=%d alignment", p->d);
+  DB200_CHECK_ARG(p->d_out && p->dx, "ln_shift_bwd: null tensor");
+  if (p->do_ln) DB200_CHECK_ARG(p->x && p->mean && p->rstd && p->gamma && p->dgamma && p->dbeta, "ln_shift_bwd: LayerNorm needs x/mean/rstd/gamma/dgamma/dbeta");
+  if (p->do_shift) DB200_CHECK_ARG(p->fmap > 0 && p->n >= p->text_len && p->n <= p->text_len + p->fmap * p->fmap, "ln_shift_bwd: bad shift geometry");
+  return ln_shift_bwd_launch(*p, (cudaStream_t)stream);
+}
+
+int dalle_b200_gemm(const db200_gemm_params* p, void* stream) {
+  DB200_CHECK_ARG(p != nullptr, "gemm: null params");
+  DB200_CHECK_ARG(p->M >= 0 && p->N > 0 && p->K > 0, "gemm: bad shape M=%d N=%d K=%d", p->M, p->N, p->K);
+  DB200_CHECK_ARG(dtype_ok(p->dtype), "gemm: bad dtype %d", p->dtype);
+  DB200_CHECK_ARG(p->A && p->B, "gemm: null operand");
+  DB200_CHECK_ARG((p->N & 1) == 0, "gemm: N=%d must be even (epilogues work on column pairs)", p->N);
+  switch (p->epilogue) {
+    case DB200_EPI_STORE:
+      DB200_CHECK_ARG(p->C && dtype_ok(p->c_dtype) && (p->ldc & 1) == 0, "gemm/STORE: bad C");
+      break;
+    case DB200_EPI_QKV:
+      DB200_CHECK_ARG(p->q && p->k && p->v, "gemm/QKV: null q/k/v");
+      DB200_CHECK_ARG(p->heads > 0 && p->dim_head > 0 && (p->dim_head & 1) == 0 && p->N == 3 * p->heads * p->dim_head,
+                      "gemm/QKV: N=%d != 3*heads*dim_head (%d*%d)", p->N, p->heads, p->dim_head);
+      DB200_CHECK_ARG(p->seq_n > 0 && p->M % p->seq_n == 0, "gemm/QKV: M=%d not a multiple of seq_n=%d", p->M, p->seq_n);
+      DB200_CHECK_ARG((p->cos_t == nullptr) == (p->sin_t == nullptr), "gemm/QKV: cos/sin tables must come together");
+      break;
+    case DB200_EPI_RESID:
+      DB200_CHECK_ARG(p->out != nullptr, "gemm/RESID: null out");
+      break;
+    case DB200_EPI_GEGLU:
+      DB200_CHECK_ARG(p->h_out && p->hidden > 0 && p->N == 2 * p->hidden && (p->hidden & 1) == 0, "gemm/GEGLU: N must equal 2*hidden");
+      break;
+    case DB200_EPI_GEGLU_BWD:
+      DB200_CHECK_ARG(p->u_in && p->du_out && p->hidden == p->N, "gemm/GEGLU_BWD: N must equal hidden");
+      break;
+    default:
+      return set_error(DB200_ERR_BAD_ARG, "gemm: unknown epilogue %d", p->epilogue);
+  }
+  if (p->M == 0) return DB200_OK;
+  int backend = p->backend;
+  if (backend == DB200_GEMM_AUTO) {
+    const int env = env_choice("DALLE_B200_GEMM", "simt", "tcgen05");
+    if (env == 1) backend = DB200_GEMM_SIMT;
+    else {
+      const char* why = nullptr;
+      backend = gemm_tcgen05_supported(*p, &why) ? DB200_GEMM_TCGEN05 : DB200_GEMM_SIMT;
+    }
+  }
+  if (backend == DB200_GEMM_TCGEN05) {
+    const char* why = "";
+    if (!gemm_tcgen05_supported(*p, &why)) return set_error(DB200_ERR_UNSUPPORTED, "gemm: tcgen05 backend cannot run this problem: %s", why);
+    return gemm_tcgen05_launch(*p, (cudaStream_t)stream);
+  }
+  return gemm_simt_launch(*p, (cudaStream_t)stream);
+}
+
+int dalle_b200_gemm_select(const db200_gemm_params* p) {
+  if (!p) return DB200_GEMM_SIMT;
+  if (p->backend != DB200_GEMM_AUTO) return p->backend;
+  if (env_choice("DALLE_B200_GEMM", "simt", "tcgen05") == 1) return DB200_GEMM_SIMT;
+  const char* why = nullptr;
+  return gemm_tcgen05_supported(*p, &why) ? DB200_GEMM_TCGEN05 : DB200_GEMM_SIMT;
+}
+
+static int check_attn(const db200_attn_fwd_params& f, const char* who) {
+  DB200_CHECK_ARG(f.batch >= 0 && f.heads > 0 && f.n_q >= 0 && f.n_k >= f.n_q, "%s: bad shape", who);
+  if (f.dim_head != 64) return set_error(DB200_ERR_UNSUPPORTED, "%s: dim_head=%d, kernels are specialised for 64", who, f.dim_head);
+  DB200_CHECK_ARG(dtype_ok(f.dtype), "%s: bad dtype", who);
+  DB200_CHECK_ARG(f.q && f.k && f.v && f.out && f.lse, "%s: null tensor", who);
+  DB200_CHECK_ARG(f.pattern >= DB200_ATTN_FULL && f.pattern <= DB200_ATTN_STATIC, "%s: bad pattern %d", who, f.pattern);
+  if (f.pattern == DB200_ATTN_STATIC) DB200_CHECK_ARG(f.static_mask && f.static_ld >= f.n_k, "%s: STATIC needs static_mask", who);
+  if (f.pattern == DB200_ATTN_AXIAL_ROW || f.pattern == DB200_ATTN_AXIAL_COL || f.pattern == DB200_ATTN_CONV_LIKE)
+    DB200_CHECK_ARG(f.fmap > 0 && f.text_len > 0, "%s: sparse pattern needs text_len / fmap", who);
+  if (f.pattern == DB200_ATTN_CONV_LIKE) DB200_CHECK_ARG(f.kernel_size > 0 && (f.kernel_size & 1) && f.dilation > 0, "%s: conv_like kernel_size must be odd", who);
+  return DB200_OK;
+}
+
+int dalle_b200_attn_fwd(const db200_attn_fwd_params* p, void* stream) {
+  DB200_CHECK_ARG(p != nullptr, "attn_fwd: null params");
+  const int rc = check_attn(*p, "attn_fwd");
+  if (rc) return rc;
+  if (p->batch == 0 || p->n_q == 0) return DB200_OK;
+  const int env = env_choice("DALLE_B200_ATTN", "simt", "mma");
+  if (env != 1 && attn_mma_supported(*p)) return attn_fwd_mma_launch(*p, (cudaStream_t)stream);
+  return attn_fwd_simt_launch(*p, (cudaStream_t)stream);
+}
+
+int dalle_b200_attn_bwd(const db200_attn_bwd_params* p, void* stream) {
+  DB200_CHECK_ARG(p != nullptr, "attn_bwd: null params");
+  const int rc = check_attn(p->f, "attn_bwd");
+  if (rc) return rc;
+  DB200_CHECK_ARG(p->f.n_q == p->f.n_k, "attn_bwd: training only (n_q == n_k)");
+  DB200_CHECK_ARG(p->d_out && p->delta && p->dqkv, "attn_bwd: null tensor");
+  DB200_CHECK_ARG((p->cos_t == nullptr) == (p->sin_t == nullptr), "attn_bwd: cos/sin tables must come together");
+  if (p->f.batch == 0 || p->f.n_q == 0) return DB200_OK;
+  const int env = env_choice("DALLE_B200_ATTN", "simt", "mma");
+  if (env != 1 && attn_mma_supported(p->f)) return attn_bwd_mma_launch(*p, (cudaStream_t)stream);
+  return attn_bwd_simt_launch(*p, (cudaStream_t)stream);
+}
+
+int dalle_b200_scale_bwd(const db200_scale_bwd_params* p, void* stream) {
+  DB200_CHECK_ARG(p != nullptr, "scale_bwd: null params");
+  DB200_CHECK_ARG(p->rows >= 0 && p->d > 0 && (p->d & 1) == 0, "scale_bwd: bad shape");
+  DB200_CHECK_ARG(dtype_ok(p->dtype) && p->d_out && p->dy, "scale_bwd: bad args");
+  return scale_bwd_launch(*p, (cudaStream_t)stream);
+}
+
+int dalle_b200_colsum(const void* x, int dtype, int rows, int cols, float* out, void* stream) {
+  DB200_CHECK_ARG(x && out && rows >= 0 && cols > 0 && (cols & 1) == 0 && dtype_ok(dtype), "colsum: bad args");
+  return colsum_launch(x, dtype, rows, cols, out, (cudaStream_t)stream);
+}
+
+int dalle_b200_cast_bf16(const float* src, void* dst, int64_t count, void* stream) {
+  DB200_CHECK_ARG(src && dst && count >= 0, "cast_bf16: bad args");
+  DB200_CHECK_ARG(aligned16(src) && (reinterpret_cast<uintptr_t>(dst) & 7) == 0, "cast_bf16: alignment");
+  return cast_bf16_launch(src, dst, count, (cudaStream_t)stream);
+}
+
+int dalle_b200_axpby(const float* a, const float* b, float alpha, float* y, int64_t count, void* stream) {
+  DB200_CHECK_ARG(a && b && y && count >= 0, "axpby: bad args");
+  DB200_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(y), "axpby: alignment");
+  return axpby_launch(a, b, alpha, y, count, (cudaStream_t)stream);
+}
+
+}  // extern "C"

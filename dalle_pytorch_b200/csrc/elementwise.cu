@@ -1,0 +1,320 @@
+// HBM-bound glue kernels of the DALL-E block: LayerNorm + token-shift (forward and backward), LayerScale /
+// residual backward, column sums, casts.  Each is one pass over its tensor with 16-byte accesses.
+#include "common.cuh"
+
+namespace db200 {
+
+namespace {
+
+constexpr int LN_THREADS = 128;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();                         // protect `red` against the previous use
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  const int nw = blockDim.x >> 5;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
+}
+
+// Where does channel c of the (LayerNorm-ed) token at position p end up after PreShiftToken?
+// transformer.py:165-186: text tokens shift their first half to p+1; image token (r,c) sends its first
+// quarter to the token below (r+1,c) and its second quarter to the right neighbour (r,c+1); -1 = dropped.
+__device__ __forceinline__ int shift_dest(int p, int c, int n, int d, int text_len, int fmap, int do_shift) {
+  if (!do_shift || c >= (d >> 1)) return p;
+  if (p < text_len) return (p + 1 < text_len) ? p + 1 : -1;
+  const int q = p - text_len;
+  const int r = q / fmap, cc = q - r * fmap;
+  if (c < (d >> 2)) return (r + 1 < fmap && p + fmap < n) ? p + fmap : -1;
+  return (cc + 1 < fmap && p + 1 < n) ? p + 1 : -1;
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(LN_THREADS) ln_shift_fwd_kernel(db200_ln_shift_fwd_params P) {
+  extern __shared__ float row[];
+  __shared__ float red[LN_THREADS / 32];
+  const int r = blockIdx.x;
+  const int n = P.n, d = P.d;
+  const int b = r / n, p = r - b * n;
+  const float* xr = P.x + (long long)r * d;
+  float s = 0.f;
+  for (int c = threadIdx.x * 4; c < d; c += LN_THREADS * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    *reinterpret_cast<float4*>(row + c) = v;
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (P.do_ln) {
+    mean = block_sum(s, red) / d;
+    float q = 0.f;
+    for (int c = threadIdx.x * 4; c < d; c += LN_THREADS * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(row + c);
+      const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+      q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+    const float var = block_sum(q, red) / d;
+    rstd = 1.0f / sqrtf(var + P.eps);
+    if (threadIdx.x == 0) { P.mean[r] = mean; P.rstd[r] = rstd; }
+  }
+  TO* out = reinterpret_cast<TO*>(P.out);
+  const long long brow = (long long)b * n;
+  for (int c = threadIdx.x * 4; c < d; c += LN_THREADS * 4) {
+    float4 v = *reinterpret_cast<const float4*>(row + c);
+    if (P.do_ln) {
+      const float4 g = *reinterpret_cast<const float4*>(P.gamma + c);
+      const float4 be = *reinterpret_cast<const float4*>(P.beta + c);
+      v.x = (v.x - mean) * rstd * g.x + be.x;
+      v.y = (v.y - mean) * rstd * g.y + be.y;
+      v.z = (v.z - mean) * rstd * g.z + be.z;
+      v.w = (v.w - mean) * rstd * g.w + be.w;
+    }
+    const int dest = shift_dest(p, c, n, d, P.text_len, P.fmap, P.do_shift);
+    if (dest >= 0) {
+      TO* o = out + (brow + dest) * d + c;
+      store2<TO>(o, v.x, v.y);
+      store2<TO>(o + 2, v.z, v.w);
+    }
+    if (P.do_shift && c < (d >> 1)) {
+      // positions that receive nothing get zeros (F.pad in transformer.py:172,178-179)
+      bool zero;
+      if (p < P.text_len) zero = (p == 0);
+      else {
+        const int q = p - P.text_len;
+        const int rr = q / P.fmap, cc = q - rr * P.fmap;
+        zero = (c < (d >> 2)) ? (rr == 0) : (cc == 0);
+      }
+      if (zero) {
+        TO* o = out + (brow + p) * d + c;
+        store2<TO>(o, 0.f, 0.f);
+        store2<TO>(o + 2, 0.f, 0.f);
+      }
+    }
+  }
+}
+
+template <typename TI>
+__global__ void __launch_bounds__(LN_THREADS) ln_shift_bwd_kernel(db200_ln_shift_bwd_params P) {
+  extern __shared__ float sm[];
+  __shared__ float red[LN_THREADS / 32];
+  const int n = P.n, d = P.d;
+  float* dy = sm;             // [d] gradient w.r.t. the LN output of this row (after un-shifting)
+  float* xh = sm + d;         // [d] x_hat
+  float* accg = sm + 2 * d;   // [d] dgamma partial
+  float* accb = sm + 3 * d;   // [d] dbeta partial
+  for (int c = threadIdx.x; c < d; c += LN_THREADS) { accg[c] = 0.f; accb[c] = 0.f; }
+  const TI* dA = reinterpret_cast<const TI*>(P.d_out);
+  const int rows = P.batch * n;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int b = r / n, p = r - b * n;
+    const long long brow = (long long)b * n;
+    const float* xr = P.x + (long long)r * d;
+    float mean = 0.f, rstd = 1.f;
+    if (P.do_ln) { mean = P.mean[r]; rstd = P.rstd[r]; }
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = threadIdx.x * 4; c < d; c += LN_THREADS * 4) {
+      const int src = shift_dest(p, c, n, d, P.text_len, P.fmap, P.do_shift);
+      float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+      if (src >= 0) {
+        const TI* gp = dA + (brow + src) * d + c;
+        const float2 a = load2<TI>(gp), bb = load2<TI>(gp + 2);
+        g0 = a.x; g1 = a.y; g2 = bb.x; g3 = bb.y;
+      }
+      if (P.do_ln) {
+        const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+        const float4 ga = *reinterpret_cast<const float4*>(P.gamma + c);
+        const float h0 = (xv.x - mean) * rstd, h1 = (xv.y - mean) * rstd, h2 = (xv.z - mean) * rstd, h3 = (xv.w - mean) * rstd;
+        accg[c] += g0 * h0; accg[c + 1] += g1 * h1; accg[c + 2] += g2 * h2; accg[c + 3] += g3 * h3;
+        accb[c] += g0; accb[c + 1] += g1; accb[c + 2] += g2; accb[c + 3] += g3;
+        g0 *= ga.x; g1 *= ga.y; g2 *= ga.z; g3 *= ga.w;
+        s1 += (g0 + g1) + (g2 + g3);
+        s2 += (g0 * h0 + g1 * h1) + (g2 * h2 + g3 * h3);
+        *reinterpret_cast<float4*>(xh + c) = make_float4(h0, h1, h2, h3);
+      }
+      *reinterpret_cast<float4*>(dy + c) = make_float4(g0, g1, g2, g3);
+    }
+    float m1 = 0.f, m2 = 0.f;
+    if (P.do_ln) {
+      m1 = block_sum(s1, red) / d;
+      m2 = block_sum(s2, red) / d;
+    }
+    float* dxr = P.dx + (long long)r * d;
+    const float* dr = P.dres ? P.dres + (long long)r * d : nullptr;
+    for (int c = threadIdx.x * 4; c < d; c += LN_THREADS * 4) {
+      float4 g = *reinterpret_cast<const float4*>(dy + c);
+      if (P.do_ln) {
+        const float4 h = *reinterpret_cast<const float4*>(xh + c);
+        g.x = rstd * (g.x - m1 - h.x * m2);
+        g.y = rstd * (g.y - m1 - h.y * m2);
+        g.z = rstd * (g.z - m1 - h.z * m2);
+        g.w = rstd * (g.w - m1 - h.w * m2);
+      }
+      if (dr) {
+        const float4 e = *reinterpret_cast<const float4*>(dr + c);
+        g.x += e.x; g.y += e.y; g.z += e.z; g.w += e.w;
+      }
+      *reinterpret_cast<float4*>(dxr + c) = g;
+    }
+    // each thread only ever touches its own channels of dy/xh/accg/accb -> no barrier needed between rows
+  }
+  if (P.do_ln && P.dgamma) {
+    // same thread<->channel ownership as above
+    for (int c = threadIdx.x * 4; c < d; c += LN_THREADS * 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(P.dgamma + c + j, accg[c + j]);
+        atomicAdd(P.dbeta + c + j, accb[c + j]);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scale_bwd_kernel(db200_scale_bwd_params P) {
+  extern __shared__ float sm[];
+  const int d = P.d;
+  float* accs = sm;       // [d]
+  float* accb = sm + d;   // [d]
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
+  // ownership: thread t owns channel pairs c = 2*t + k*2*blockDim
+  const T* y = reinterpret_cast<const T*>(P.y);
+  T* dy = reinterpret_cast<T*>(P.dy);
+  for (int r = blockIdx.x; r < P.rows; r += gridDim.x) {
+    const long long off = (long long)r * d;
+    for (int c = threadIdx.x * 2; c < d; c += blockDim.x * 2) {
+      const float2 g = *reinterpret_cast<const float2*>(P.d_out + off + c);
+      float s0 = P.sign, s1 = P.sign;
+      if (P.scale) { s0 *= P.scale[c]; s1 *= P.scale[c + 1]; }
+      const float o0 = s0 * g.x, o1 = s1 * g.y;
+      store2<T>(dy + off + c, o0, o1);
+      // dbias accumulates exactly what the GEMMs will consume (the rounded value in bf16 mode is within tolerance;
+      // keep the unrounded fp32 one for accuracy)
+      accb[c] += o0; accb[c + 1] += o1;
+      if (P.dscale && y) {
+        const float2 yy = load2<T>(y + off + c);
+        accs[c] += P.sign * g.x * yy.x; accs[c + 1] += P.sign * g.y * yy.y;
+      }
+    }
+  }
+  for (int c = threadIdx.x * 2; c < d; c += blockDim.x * 2) {
+    if (P.dscale) { atomicAdd(P.dscale + c, accs[c]); atomicAdd(P.dscale + c + 1, accs[c + 1]); }
+    if (P.dbias) { atomicAdd(P.dbias + c, accb[c]); atomicAdd(P.dbias + c + 1, accb[c + 1]); }
+  }
+}
+
+constexpr int CS_ROWS = 512;
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int rows, int cols, float* __restrict__ out) {
+  __shared__ float red[8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + tx) * 2;
+  const int r0 = blockIdx.y * CS_ROWS;
+  const int r1 = min(rows, r0 + CS_ROWS);
+  float a0 = 0.f, a1 = 0.f;
+  if (c < cols) {
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const float2 v = load2<T>(x + (long long)r * cols + c);
+      a0 += v.x; a1 += v.y;
+    }
+  }
+  red[ty][tx * 2] = a0; red[ty][tx * 2 + 1] = a1;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s0 += red[i][tx * 2]; s1 += red[i][tx * 2 + 1]; }
+    atomicAdd(out + c, s0);
+    atomicAdd(out + c + 1, s1);
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long count) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < count; i += stride) {
+    if (i + 3 < count) {
+      const float4 v = *reinterpret_cast<const float4*>(src + i);
+      *reinterpret_cast<__nv_bfloat162*>(dst + i) = __floats2bfloat162_rn(v.x, v.y);
+      *reinterpret_cast<__nv_bfloat162*>(dst + i + 2) = __floats2bfloat162_rn(v.z, v.w);
+    } else {
+      for (long long j = i; j < count; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+    }
+  }
+}
+
+__global__ void axpby_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha, float* __restrict__ y,
+                             long long count) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < count; i += stride) {
+    if (i + 3 < count) {
+      const float4 u = *reinterpret_cast<const float4*>(a + i);
+      const float4 v = *reinterpret_cast<const float4*>(b + i);
+      *reinterpret_cast<float4*>(y + i) = make_float4(u.x + alpha * v.x, u.y + alpha * v.y, u.z + alpha * v.z, u.w + alpha * v.w);
+    } else {
+      for (long long j = i; j < count; ++j) y[j] = a[j] + alpha * b[j];
+    }
+  }
+}
+
+}  // namespace
+
+int ln_shift_fwd_launch(const db200_ln_shift_fwd_params& P, cudaStream_t st) {
+  const int rows = P.batch * P.n;
+  if (rows == 0) return DB200_OK;
+  const size_t smem = (size_t)P.d * sizeof(float);
+  if (P.out_dtype == DB200_F32) ln_shift_fwd_kernel<float><<<rows, LN_THREADS, smem, st>>>(P);
+  else ln_shift_fwd_kernel<__nv_bfloat16><<<rows, LN_THREADS, smem, st>>>(P);
+  DB200_LAUNCH_OK("ln_shift_fwd_kernel");
+  return DB200_OK;
+}
+
+int ln_shift_bwd_launch(const db200_ln_shift_bwd_params& P, cudaStream_t st) {
+  const int rows = P.batch * P.n;
+  if (rows == 0) return DB200_OK;
+  const size_t smem = (size_t)4 * P.d * sizeof(float);
+  const int grid = rows < sm_count() * 8 ? rows : sm_count() * 8;
+  if (P.dout_dtype == DB200_F32) ln_shift_bwd_kernel<float><<<grid, LN_THREADS, smem, st>>>(P);
+  else ln_shift_bwd_kernel<__nv_bfloat16><<<grid, LN_THREADS, smem, st>>>(P);
+  DB200_LAUNCH_OK("ln_shift_bwd_kernel");
+  return DB200_OK;
+}
+
+int scale_bwd_launch(const db200_scale_bwd_params& P, cudaStream_t st) {
+  if (P.rows == 0) return DB200_OK;
+  const size_t smem = (size_t)2 * P.d * sizeof(float);
+  const int grid = P.rows < sm_count() * 4 ? P.rows : sm_count() * 4;
+  if (P.dtype == DB200_F32) scale_bwd_kernel<float><<<grid, 256, smem, st>>>(P);
+  else scale_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(P);
+  DB200_LAUNCH_OK("scale_bwd_kernel");
+  return DB200_OK;
+}
+
+int colsum_launch(const void* x, int dtype, int rows, int cols, float* out, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return DB200_OK;
+  dim3 grid(ceil_div(cols, 64), ceil_div(rows, CS_ROWS));
+  if (dtype == DB200_F32) colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), rows, cols, out);
+  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, out);
+  DB200_LAUNCH_OK("colsum_kernel");
+  return DB200_OK;
+}
+
+int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st) {
+  if (count == 0) return DB200_OK;
+  int64_t blocks = ceil_div64(count, 256 * 4);
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  cast_bf16_kernel<<<(int)blocks, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), count);
+  DB200_LAUNCH_OK("cast_bf16_kernel");
+  return DB200_OK;
+}
+
+int axpby_launch(const float* a, const float* b, float alpha, float* y, int64_t count, cudaStream_t st) {
+  if (count == 0) return DB200_OK;
+  int64_t blocks = ceil_div64(count, 256 * 4);
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  axpby_kernel<<<(int)blocks, 256, 0, st>>>(a, b, alpha, y, count);
+  DB200_LAUNCH_OK("axpby_kernel");
+  return DB200_OK;
+}
+
+}  // namespace db200

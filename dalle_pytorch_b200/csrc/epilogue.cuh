@@ -1,0 +1,241 @@
+// Fused GEMM epilogues shared by the SIMT (fp32) and tcgen05 (bf16) GEMM kernels.
+// Each function consumes one PAIR of adjacent accumulator columns (n even) of one output row m, which is
+// the natural granule for the rotary pair rotation and for packed bf16x2 stores.
+#pragma once
+#include "common.cuh"
+
+namespace db200 {
+
+struct EpiArgs {
+  int M, N;
+  // STORE
+  void* C; long long ldc; int c_is_f32; const float* bias;
+  // QKV
+  void* q; void* k; void* v; const float* cos_t; const float* sin_t;
+  int seq_n, heads, dim_head, pos_offset; float q_scale;
+  // RESID
+  const float* resid; const float* scale; float sign; void* y_out; float* out;
+  // GEGLU / GEGLU_BWD
+  void* u_out; void* h_out; int hidden; const void* u_in; void* du_out;
+};
+
+inline EpiArgs make_epi_args(const db200_gemm_params& p) {
+  EpiArgs e;
+  e.M = p.M; e.N = p.N;
+  e.C = p.C; e.ldc = p.ldc; e.c_is_f32 = (p.c_dtype == DB200_F32); e.bias = p.bias;
+  e.q = p.q; e.k = p.k; e.v = p.v; e.cos_t = p.cos_t; e.sin_t = p.sin_t;
+  e.seq_n = p.seq_n; e.heads = p.heads; e.dim_head = p.dim_head; e.pos_offset = p.pos_offset; e.q_scale = p.q_scale;
+  e.resid = p.resid; e.scale = p.scale; e.sign = p.sign; e.y_out = p.y_out; e.out = p.out;
+  e.u_out = p.u_out; e.h_out = p.h_out; e.hidden = p.hidden; e.u_in = p.u_in; e.du_out = p.du_out;
+  return e;
+}
+
+// EPI_STORE ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void epi_store_pair(const EpiArgs& e, int m, int n, float v0, float v1) {
+  if (e.bias) { v0 += e.bias[n]; v1 += e.bias[n + 1]; }
+  const long long off = (long long)m * e.ldc + n;
+  if (e.c_is_f32) store2<float>(reinterpret_cast<float*>(e.C) + off, v0, v1);
+  else            store2<T>(reinterpret_cast<T*>(e.C) + off, v0, v1);
+}
+
+// EPI_QKV: 'b n (h d) -> b h n d', rotary on q,k,v (interleaved pairs), q *= dh^-0.5 -------------------
+// (attention.py:63-69 ; rotary_embedding_torch.apply_rotary_emb: t*cos + rotate_half(t)*sin)
+template <typename T>
+__device__ __forceinline__ void epi_qkv_pair(const EpiArgs& e, int m, int n, float v0, float v1) {
+  const int inner = e.heads * e.dim_head;
+  const int which = n / inner;
+  const int rem = n - which * inner;
+  const int head = rem / e.dim_head;
+  const int d = rem - head * e.dim_head;           // even
+  const int b = m / e.seq_n;
+  const int p = m - b * e.seq_n;
+  if (e.cos_t) {
+    const int ti = (p + e.pos_offset) * (e.dim_head >> 1) + (d >> 1);
+    const float c = e.cos_t[ti], s = e.sin_t[ti];
+    const float r0 = v0 * c + (-v1) * s;
+    const float r1 = v1 * c + v0 * s;
+    v0 = r0; v1 = r1;
+  }
+  if (which == 0) { v0 *= e.q_scale; v1 *= e.q_scale; }
+  T* base = reinterpret_cast<T*>(which == 0 ? e.q : (which == 1 ? e.k : e.v));
+  const long long off = (((long long)b * e.heads + head) * e.seq_n + p) * e.dim_head + d;
+  store2<T>(base + off, v0, v1);
+}
+
+// EPI_RESID: out = resid + sign*scale*(acc+bias) ; optionally keep y = acc+bias for the LayerScale grad ----
+template <typename T>
+__device__ __forceinline__ void epi_resid_pair(const EpiArgs& e, int m, int n, float v0, float v1) {
+  if (e.bias) { v0 += e.bias[n]; v1 += e.bias[n + 1]; }
+  const long long off = (long long)m * e.N + n;
+  if (e.y_out) store2<T>(reinterpret_cast<T*>(e.y_out) + off, v0, v1);
+  float s0 = e.sign, s1 = e.sign;
+  if (e.scale) { s0 *= e.scale[n]; s1 *= e.scale[n + 1]; }
+  float r0 = 0.f, r1 = 0.f;
+  if (e.resid) { const float2 r = *reinterpret_cast<const float2*>(e.resid + off); r0 = r.x; r1 = r.y; }
+  *reinterpret_cast<float2*>(e.out + off) = make_float2(r0 + s0 * v0, r1 + s1 * v1);
+}
+
+// EPI_GEGLU: j indexes the hidden dim; a = acc[:, j], g = acc[:, hidden + j] -------------------------------
+template <typename T>
+__device__ __forceinline__ void epi_geglu_pair(const EpiArgs& e, int m, int j, float a0, float a1, float g0, float g1) {
+  if (e.bias) {
+    a0 += e.bias[j]; a1 += e.bias[j + 1];
+    g0 += e.bias[e.hidden + j]; g1 += e.bias[e.hidden + j + 1];
+  }
+  if (e.u_out) {
+    T* u = reinterpret_cast<T*>(e.u_out) + (long long)m * (2 * e.hidden);
+    store2<T>(u + j, a0, a1);
+    store2<T>(u + e.hidden + j, g0, g1);
+  }
+  T* h = reinterpret_cast<T*>(e.h_out) + (long long)m * e.hidden;
+  store2<T>(h + j, a0 * gelu_erf(g0), a1 * gelu_erf(g1));
+}
+
+// EPI_GEGLU_BWD: acc = dh[m, j..j+1] --------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void epi_geglu_bwd_pair(const EpiArgs& e, int m, int j, float d0, float d1) {
+  const T* u = reinterpret_cast<const T*>(e.u_in) + (long long)m * (2 * e.hidden);
+  const float2 a = load2<T>(u + j);
+  const float2 g = load2<T>(u + e.hidden + j);
+  T* du = reinterpret_cast<T*>(e.du_out) + (long long)m * (2 * e.hidden);
+  store2<T>(du + j, d0 * gelu_erf(g.x), d1 * gelu_erf(g.y));
+  store2<T>(du + e.hidden + j, d0 * a.x * gelu_erf_grad(g.x), d1 * a.y * gelu_erf_grad(g.y));
+}
+
+template <int EPI, typename T>
+__device__ __forceinline__ void epi_pair(const EpiArgs& e, int m, int n, float v0, float v1) {
+  if constexpr (EPI == DB200_EPI_STORE) epi_store_pair<T>(e, m, n, v0, v1);
+  else if constexpr (EPI == DB200_EPI_QKV) epi_qkv_pair<T>(e, m, n, v0, v1);
+  else if constexpr (EPI == DB200_EPI_RESID) epi_resid_pair<T>(e, m, n, v0, v1);
+  else if constexpr (EPI == DB200_EPI_GEGLU_BWD) epi_geglu_bwd_pair<T>(e, m, n, v0, v1);
+}
+
+
+// =====================================================================================================
+// 8-column granules (one 16-byte bf16 store per output tensor) for the tcgen05 epilogue, where a thread
+// owns one accumulator row and walks along N.  v[8] are columns n .. n+7 (n % 8 == 0) of row m.
+// =====================================================================================================
+template <typename T> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+    uint4 u;
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.z));
+    const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.w));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+};
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
+template <int EPI, typename T>
+__device__ __forceinline__ void epi_vec8(const EpiArgs& e, int m, int n, float* v) {
+  if constexpr (EPI == DB200_EPI_STORE) {
+    if (e.bias) {
+      float bb[8]; Vec8<float>::load(e.bias + n, bb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += bb[i];
+    }
+    const long long off = (long long)m * e.ldc + n;
+    if (e.c_is_f32) Vec8<float>::store(reinterpret_cast<float*>(e.C) + off, v);
+    else Vec8<T>::store(reinterpret_cast<T*>(e.C) + off, v);
+  } else if constexpr (EPI == DB200_EPI_QKV) {
+    const int inner = e.heads * e.dim_head;
+    const int which = n / inner;
+    const int rem = n - which * inner;
+    const int head = rem / e.dim_head;
+    const int d = rem - head * e.dim_head;          // multiple of 8
+    const int b = m / e.seq_n;
+    const int p = m - b * e.seq_n;
+    if (e.cos_t) {
+      const int ti = (p + e.pos_offset) * (e.dim_head >> 1) + (d >> 1);
+      const float4 c = *reinterpret_cast<const float4*>(e.cos_t + ti);
+      const float4 s = *reinterpret_cast<const float4*>(e.sin_t + ti);
+      const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x0 = v[2 * i], x1 = v[2 * i + 1];
+        v[2 * i] = x0 * cc[i] + (-x1) * ss[i];
+        v[2 * i + 1] = x1 * cc[i] + x0 * ss[i];
+      }
+    }
+    if (which == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= e.q_scale;
+    }
+    T* base = reinterpret_cast<T*>(which == 0 ? e.q : (which == 1 ? e.k : e.v));
+    Vec8<T>::store(base + (((long long)b * e.heads + head) * e.seq_n + p) * e.dim_head + d, v);
+  } else if constexpr (EPI == DB200_EPI_RESID) {
+    if (e.bias) {
+      float bb[8]; Vec8<float>::load(e.bias + n, bb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += bb[i];
+    }
+    const long long off = (long long)m * e.N + n;
+    if (e.y_out) Vec8<T>::store(reinterpret_cast<T*>(e.y_out) + off, v);
+    float sc[8], rr[8];
+    if (e.scale) Vec8<float>::load(e.scale + n, sc);
+    if (e.resid) Vec8<float>::load(e.resid + off, rr);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float s = e.scale ? e.sign * sc[i] : e.sign;
+      const float r = e.resid ? rr[i] : 0.f;
+      v[i] = r + s * v[i];
+    }
+    Vec8<float>::store(e.out + off, v);
+  } else if constexpr (EPI == DB200_EPI_GEGLU_BWD) {
+    const T* u = reinterpret_cast<const T*>(e.u_in) + (long long)m * (2 * e.hidden);
+    float a[8], g[8], da[8], dg[8];
+    Vec8<T>::load(u + n, a);
+    Vec8<T>::load(u + e.hidden + n, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      da[i] = v[i] * gelu_erf(g[i]);
+      dg[i] = v[i] * a[i] * gelu_erf_grad(g[i]);
+    }
+    T* du = reinterpret_cast<T*>(e.du_out) + (long long)m * (2 * e.hidden);
+    Vec8<T>::store(du + n, da);
+    Vec8<T>::store(du + e.hidden + n, dg);
+  }
+}
+
+// GEGLU forward: a[8], g[8] are hidden indices j .. j+7 of row m
+template <typename T>
+__device__ __forceinline__ void epi_geglu_vec8(const EpiArgs& e, int m, int j, float* a, float* g) {
+  if (e.bias) {
+    float ba[8], bg[8];
+    Vec8<float>::load(e.bias + j, ba);
+    Vec8<float>::load(e.bias + e.hidden + j, bg);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] += ba[i]; g[i] += bg[i]; }
+  }
+  if (e.u_out) {
+    T* u = reinterpret_cast<T*>(e.u_out) + (long long)m * (2 * e.hidden);
+    Vec8<T>::store(u + j, a);
+    Vec8<T>::store(u + e.hidden + j, g);
+  }
+  float h[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h[i] = a[i] * gelu_erf(g[i]);
+  Vec8<T>::store(reinterpret_cast<T*>(e.h_out) + (long long)m * e.hidden + j, h);
+}
+
+}  // namespace db200

@@ -1,0 +1,459 @@
+// bf16 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands staged by TMA
+// into 128B-swizzled shared memory, warp-specialised producer / MMA-issuer / epilogue roles, persistent CTAs
+// (one per SM) with a double-buffered TMEM accumulator so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+//   warp 0      : TMA producer   (one elected lane; cp.async.bulk.tensor -> smem ring, mbarrier complete_tx)
+//   warp 1      : MMA issuer     (one elected lane; tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16;
+//                                 tcgen05.commit releases smem stages / publishes the accumulator)
+//   warps 2..5  : epilogue       (tcgen05.ld 32x32b: thread = accumulator row; fused epilogues of epilogue.cuh,
+//                                 16-byte global stores)
+//
+// All three GEMM shapes of training map onto the same kernel through the operand "major" flags:
+//   forward : A K-major (activations [M,K]),  B K-major (weight [N,K])
+//   dgrad   : A K-major (dY [M,K=out]),       B MN-major (weight [out,in] read as B(n=in, k=out))
+//   wgrad   : A MN-major (dY [rows, out]),    B MN-major (X [rows, in])     -> C = dW [out, in] fp32
+// (UMMA shared-memory descriptors support both majors for bf16; MN-major tiles are loaded as 64x64 boxes.)
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace db200 {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr int BOX_MN_BYTES = 64 * BLOCK_K * 2;         // one 64(mn) x 64(k) MN-major box = 8 KB
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// ---- mbarrier ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// A pipeline bug must surface as a launch failure, never as a hung GPU: trap after ~2 s of spinning.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("dalle_b200 gemm_tcgen05: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+
+// ---- TMA ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// ---- tcgen05 ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor (SWIZZLE_128B, sm_100 "version 1"):
+//   bits [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
+//   bits [46,48) = 1 | [61,64) layout type (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int BLOCK_N>
+struct SmemLayout {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual 1 KB alignment slack
+};
+
+template <int BLOCK_N, int EPI, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, EpiArgs e) {
+  using L = SmemLayout<BLOCK_N>;
+  constexpr int STAGES = L::STAGES;
+  constexpr int B_STAGE_BYTES = L::B_STAGE_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;                 // double-buffered fp32 accumulator (power of two >= 32)
+  static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+  static_assert(EPI != DB200_EPI_GEGLU || (BLOCK_N == 256 && !B_MN), "GEGLU pairs the two 128-column halves of a 256 tile");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  const uint32_t full_bar = smem_u32(bars);                    // [STAGES]
+  const uint32_t empty_bar = smem_u32(bars + STAGES);          // [STAGES]
+  const uint32_t tfull_bar = smem_u32(bars + 2 * STAGES);      // [2]
+  const uint32_t tempty_bar = smem_u32(bars + 2 * STAGES + 2); // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % num_m) * BLOCK_M;
+        const int n0 = (tile / num_m) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          const uint32_t fb = full_bar + 8 * s;
+          mbar_expect_tx(fb, L::STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem_a + s * A_STAGE_BYTES);
+          const uint32_t sb = smem_u32(smem_b + s * B_STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmA, fb, k0, m0);                                   // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(sa + c * BOX_MN_BYTES, &tmA, fb, m0 + c * 64, k0);   // box {64 m, 64 k}
+          }
+          if constexpr (!B_MN) {
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 128; ++c) {
+              int row = n0 + c * 128;
+              if constexpr (EPI == DB200_EPI_GEGLU) row = (c == 0) ? (n0 >> 1) : e.hidden + (n0 >> 1);
+              tma_load_2d(sb + c * (128 * BLOCK_K * 2), &tmB, fb, k0, row);      // box {64 k, 128 n}
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 64; ++c) tma_load_2d(sb + c * BOX_MN_BYTES, &tmB, fb, n0 + c * 64, k0);   // box {64 n, 64 k}
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major bit15, b_major bit16,
+      // N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u) |
+                             (static_cast<uint32_t>(BLOCK_N >> 3) << 17) | (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
+      // K-major  : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (1).      k-step = 32 B
+      // MN-major : 64-wide mn chunks 8 KB apart (LBO), 8-k-row groups 1024 B apart (SBO). k-step = 16 rows * 128 B
+      constexpr uint32_t A_LBO = A_MN ? BOX_MN_BYTES : 16, B_LBO = B_MN ? BOX_MN_BYTES : 16;
+      constexpr uint32_t A_KSTEP = A_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      constexpr uint32_t B_KSTEP = B_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      int s = 0; uint32_t ph = 0;
+      int as = 0; uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar + 8 * as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * s, ph);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES), A_LBO, 1024);
+          const uint64_t db = make_smem_desc(smem_u32(smem_b + s * B_STAGE_BYTES), B_LBO, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(tmem_c, da + static_cast<uint64_t>(k * A_KSTEP), db + static_cast<uint64_t>(k * B_KSTEP), idesc, (kb | k) != 0);
+          umma_commit(empty_bar + 8 * s);                    // smem stage free once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar + 8 * as);   // accumulator complete
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue (warps 2..5) ================================
+    const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    int as = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % num_m) * BLOCK_M;
+      const int n0 = (tile / num_m) * BLOCK_N;
+      const int m = m0 + row;
+      mbar_wait(tfull_bar + 8 * as, aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
+      if constexpr (EPI == DB200_EPI_GEGLU) {
+#pragma unroll 1
+        for (int ch = 0; ch < 128 / 32; ++ch) {
+          uint32_t ra[32], rg[32];
+          tmem_ld32(taddr + ch * 32, ra);
+          tmem_ld32(taddr + 128 + ch * 32, rg);
+          tmem_ld_wait();
+          const int j0 = (n0 >> 1) + ch * 32;
+          if (m < M) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              const int j = j0 + o * 8;
+              if (j < e.hidden) {
+                float a[8], g[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(ra[o * 8 + i]); g[i] = __uint_as_float(rg[o * 8 + i]); }
+                epi_geglu_vec8<__nv_bfloat16>(e, m, j, a, g);
+              }
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(taddr + ch * 32, r);
+          tmem_ld_wait();
+          if (m < M) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              const int n = n0 + ch * 32 + o * 8;
+              if (n < N) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[o * 8 + i]);
+                epi_vec8<EPI, __nv_bfloat16>(e, m, n, v);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar + 8 * as);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, outer stride `ld` elements
+int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(DB200_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(DB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu)", (int)r,
+                                          (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+  return DB200_OK;
+}
+
+template <int BLOCK_N, int EPI, bool A_MN, bool B_MN>
+int launch_cfg(const db200_gemm_params& p, cudaStream_t st) {
+  using L = SmemLayout<BLOCK_N>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!A_MN) rc = make_map(&tmA, p.A, p.K, p.M, p.lda, BLOCK_K, BLOCK_M);
+  else rc = make_map(&tmA, p.A, p.M, p.K, p.lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!B_MN) rc = make_map(&tmB, p.B, p.K, p.N, p.ldb, BLOCK_K, 128);
+  else rc = make_map(&tmB, p.B, p.N, p.K, p.ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI, A_MN, B_MN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_done = true;
+  }
+  const int num_tiles = ceil_div(p.M, BLOCK_M) * ceil_div(p.N, BLOCK_N);
+  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  const EpiArgs e = make_epi_args(p);
+  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(tmA, tmB, p.M, p.N, p.K, e);
+  DB200_LAUNCH_OK("gemm_tcgen05_kernel");
+  return DB200_OK;
+}
+
+template <int EPI, bool A_MN, bool B_MN>
+int launch_bn(const db200_gemm_params& p, cudaStream_t st) {
+  if constexpr (EPI == DB200_EPI_GEGLU) {
+    return launch_cfg<256, EPI, A_MN, B_MN>(p, st);
+  } else {
+    // 128x256 tiles halve the smem traffic per MMA; fall back to 128x128 when N is small or when the wider tile would
+    // leave most SMs idle
+    const long long tiles256 = (long long)ceil_div(p.M, BLOCK_M) * ceil_div(p.N, 256);
+    if (p.N >= 256 && (p.N % 256 == 0 || p.N > 1024) && tiles256 >= sm_count() / 2) return launch_cfg<256, EPI, A_MN, B_MN>(p, st);
+    return launch_cfg<128, EPI, A_MN, B_MN>(p, st);
+  }
+}
+
+bool device_is_sm100() {
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  if (cached[dev] == 0) {
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cached[dev] = (major == 10) ? 1 : -1;
+  }
+  return cached[dev] == 1;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+bool gemm_tcgen05_supported(const db200_gemm_params& p, const char** why) {
+  const char* w = nullptr;
+  if (p.dtype != DB200_BF16) w = "operands are not bf16";
+  else if (!device_is_sm100()) w = "device is not sm_100";
+  else if (!al16(p.A) || !al16(p.B)) w = "A/B not 16-byte aligned";
+  else if (p.lda % 8 || p.ldb % 8) w = "leading dimensions must be multiples of 8 elements";
+  else if (p.K % 8 || p.N % 8) w = "K and N must be multiples of 8";
+  else if (p.a_mn_major && p.M % 8) w = "M-major A needs M % 8 == 0";
+  else if (p.a_mn_major && !p.b_mn_major && p.epilogue != DB200_EPI_STORE) w = "M-major A x K-major B only with the STORE epilogue";
+  else {
+    switch (p.epilogue) {
+      case DB200_EPI_STORE:
+        if (!al16(p.C) || p.ldc % 8 || (p.bias && !al16(p.bias))) w = "C/bias alignment";
+        break;
+      case DB200_EPI_QKV:
+        if (p.a_mn_major || p.b_mn_major) w = "QKV epilogue is forward-only (K-major operands)";
+        else if (p.dim_head % 8 || !al16(p.q) || !al16(p.k) || !al16(p.v) || (p.cos_t && (!al16(p.cos_t) || !al16(p.sin_t) || p.dim_head % 16)))
+          w = "q/k/v/rotary alignment";
+        break;
+      case DB200_EPI_RESID:
+        if (p.a_mn_major || p.b_mn_major) w = "RESID epilogue is forward-only";
+        else if (!al16(p.out) || (p.resid && !al16(p.resid)) || (p.scale && !al16(p.scale)) || (p.bias && !al16(p.bias)) || (p.y_out && !al16(p.y_out)))
+          w = "RESID tensor alignment";
+        break;
+      case DB200_EPI_GEGLU:
+        if (p.a_mn_major || p.b_mn_major) w = "GEGLU epilogue is forward-only";
+        else if (p.hidden % 128) w = "GEGLU needs hidden % 128 == 0";
+        else if (!al16(p.h_out) || (p.u_out && !al16(p.u_out)) || (p.bias && !al16(p.bias))) w = "GEGLU tensor alignment";
+        break;
+      case DB200_EPI_GEGLU_BWD:
+        if (p.a_mn_major) w = "GEGLU_BWD expects K-major A";
+        else if (!al16(p.u_in) || !al16(p.du_out) || p.hidden % 8) w = "GEGLU_BWD tensor alignment";
+        break;
+      default: w = "unknown epilogue";
+    }
+  }
+  if (why) *why = w ? w : "";
+  return w == nullptr;
+}
+
+int gemm_tcgen05_launch(const db200_gemm_params& p, cudaStream_t st) {
+  const bool a = p.a_mn_major != 0, b = p.b_mn_major != 0;
+  switch (p.epilogue) {
+    case DB200_EPI_STORE:
+      if (!a && !b) return launch_bn<DB200_EPI_STORE, false, false>(p, st);
+      if (!a && b) return launch_bn<DB200_EPI_STORE, false, true>(p, st);
+      if (a && b) return launch_bn<DB200_EPI_STORE, true, true>(p, st);
+      return launch_bn<DB200_EPI_STORE, true, false>(p, st);
+    case DB200_EPI_QKV: return launch_bn<DB200_EPI_QKV, false, false>(p, st);
+    case DB200_EPI_RESID: return launch_bn<DB200_EPI_RESID, false, false>(p, st);
+    case DB200_EPI_GEGLU: return launch_bn<DB200_EPI_GEGLU, false, false>(p, st);
+    case DB200_EPI_GEGLU_BWD:
+      if (!b) return launch_bn<DB200_EPI_GEGLU_BWD, false, false>(p, st);
+      return launch_bn<DB200_EPI_GEGLU_BWD, false, true>(p, st);
+    default: break;
+  }
+  return set_error(DB200_ERR_BAD_ARG, "gemm_tcgen05: unsupported epilogue/major combination");
+}
+
+}  // namespace db200

@@ -1,0 +1,219 @@
+"""Fused sub-layers of the DALL-E transformer block, as sequences of libdalle_b200 kernels.
+
+One attention sub-layer  = LayerScale(PreNorm(PreShiftToken(Attention*)))   (reference transformer.py:279-292)
+One feed-forward sub-layer = LayerScale(PreNorm(PreShiftToken(FeedForward)))
+
+    out = resid + sign * scale * F( Shift( LN(x_in) ) )
+
+`x_in` and `resid` are separate so that the same code serves the sequential executor (x_in is resid,
+reversible.py:139-140) and the reversible one (y1 = x1 + f(x2), reversible.py:64-66).  Forward and backward are
+plain functions over tensors (`*_forward` returns a context tuple, `*_backward` consumes it); thin
+torch.autograd.Function wrappers expose them to autograd, and the reversible executor calls them directly to
+recompute activations block by block.
+
+Kernel sequence, attention sub-layer (bf16 mode: every GEMM is the tcgen05 kernel):
+  fwd  ln_shift_fwd -> gemm[QKV: rotary+scale+head split] -> attn_fwd -> gemm[RESID: bias+LayerScale+residual]
+  bwd  scale_bwd -> gemm dgrad(to_out) , gemm wgrad(to_out) -> attn_bwd -> gemm dgrad(to_qkv), gemm wgrad(to_qkv)
+       -> ln_shift_bwd (adds the residual-branch gradient)
+feed-forward sub-layer:
+  fwd  ln_shift_fwd -> gemm[GEGLU: bias + a*gelu(g)] -> gemm[RESID]
+  bwd  scale_bwd -> gemm dgrad(net.3)[GEGLU_BWD] , gemm wgrad(net.3) -> colsum (b1) -> gemm dgrad(net.0), gemm wgrad(net.0)
+       -> ln_shift_bwd
+"""
+import torch
+
+from . import ops
+
+
+class SublayerGeom:
+    """Static description of a sub-layer (everything that is not a tensor)."""
+
+    def __init__(self, *, dtype, text_len=0, fmap=0, do_ln=True, do_shift=False, heads=0, dim_head=64, attn_spec=None,
+                 q_scale=None, eps=1e-5):
+        self.dtype = dtype
+        self.text_len, self.fmap = text_len, fmap
+        self.do_ln, self.do_shift = do_ln, do_shift
+        self.heads, self.dim_head = heads, dim_head
+        self.attn_spec = attn_spec
+        self.q_scale = q_scale if q_scale is not None else dim_head ** -0.5
+        self.eps = eps
+
+    def shift_active(self, n):
+        # transformer.py:160-161: sequences shorter than the text length are not shifted
+        return self.do_shift and n >= self.text_len
+
+
+def _w(weight, dtype):
+    """Weights are stored in fp32 (reference checkpoints); bf16 mode casts them once per use with the cast kernel."""
+    weight = weight.detach()
+    if dtype == torch.float32:
+        return weight.contiguous()
+    return ops.cast_bf16(weight.contiguous())
+
+
+# =====================================================================================================
+# attention sub-layer
+# =====================================================================================================
+def attn_sublayer_forward(g: SublayerGeom, x_in, resid, ln_w, ln_b, w_qkv, w_out, b_out, scale, sign, cos_t, sin_t,
+                          key_mask=None, save=True):
+    b, n, d = x_in.shape
+    x_in = x_in.contiguous()
+    shift = g.shift_active(n)
+    a1, mean, rstd = ops.ln_shift_fwd(x_in, ln_w, ln_b, g.dtype, g.text_len, g.fmap, do_ln=g.do_ln, do_shift=shift, eps=g.eps)
+    wq, wo = _w(w_qkv, g.dtype), _w(w_out, g.dtype)
+    q, k, v = ops.gemm_qkv(a1, wq, b, n, g.heads, g.dim_head, cos_t, sin_t, g.q_scale)
+    o, lse = ops.attn_fwd(g.attn_spec, q, k, v, key_mask)
+    keep_y = save and scale is not None
+    out, y = ops.gemm_resid(o.view(b * n, -1), wo, b_out, None if resid is None else resid.contiguous().view(b * n, d),
+                            None if scale is None else scale.detach().reshape(-1).contiguous(), sign, keep_y=keep_y)
+    out = out.view(b, n, d)
+    ctx = None
+    if save:
+        ctx = (x_in, mean, rstd, a1, wq, wo, q, k, v, o, lse, y, shift)
+    return out, ctx
+
+
+def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t, sin_t, key_mask=None, dres=None):
+    """d_out: gradient w.r.t. `out` [b,n,d] fp32.  Returns (dx_in, dln_w, dln_b, dw_qkv, dw_out, db_out, dscale).
+    `dres` (optional, fp32) is added to dx_in inside the LayerNorm-backward kernel (sequential executor: the residual
+    branch gradient, which equals d_out)."""
+    x_in, mean, rstd, a1, wq, wo, q, k, v, o, lse, y, shift = ctx
+    b, n, d = x_in.shape
+    M = b * n
+    d_out = d_out.contiguous().view(M, d)
+    sc = None if scale is None else scale.detach().reshape(-1).contiguous()
+    dy, dscale, db_out = ops.scale_bwd(d_out, y, sc, sign, g.dtype)
+    d_o = ops.gemm_store(dy, wo, a_mn=False, b_mn=True)                                   # [M, inner]
+    dw_out = ops.gemm_store(dy, o.view(M, -1), a_mn=True, b_mn=True, out_dtype=torch.float32)   # [d, inner]
+    dqkv = ops.attn_bwd(g.attn_spec, q, k, v, o, lse, d_o.view(b, n, -1), cos_t, sin_t, g.q_scale, key_mask)
+    da1 = ops.gemm_store(dqkv, wq, a_mn=False, b_mn=True)                                 # [M, d]
+    dw_qkv = ops.gemm_store(dqkv, a1, a_mn=True, b_mn=True, out_dtype=torch.float32)      # [3*inner, d]
+    dln_w = dln_b = None
+    if g.do_ln:
+        dln_w = torch.zeros(d, device=x_in.device, dtype=torch.float32)
+        dln_b = torch.zeros(d, device=x_in.device, dtype=torch.float32)
+    dx = ops.ln_shift_bwd(da1, x_in, mean, rstd, ln_w, None if dres is None else dres.contiguous(), g.text_len, g.fmap,
+                          do_ln=g.do_ln, do_shift=shift, dgamma=dln_w, dbeta=dln_b)
+    if dscale is not None:
+        dscale = dscale.view_as(scale)
+    return dx, dln_w, dln_b, dw_qkv, dw_out, db_out, dscale
+
+
+# =====================================================================================================
+# feed-forward sub-layer
+# =====================================================================================================
+def ff_sublayer_forward(g: SublayerGeom, x_in, resid, ln_w, ln_b, w1, b1, w2, b2, scale, sign, save=True):
+    b, n, d = x_in.shape
+    x_in = x_in.contiguous()
+    shift = g.shift_active(n)
+    a2, mean, rstd = ops.ln_shift_fwd(x_in, ln_w, ln_b, g.dtype, g.text_len, g.fmap, do_ln=g.do_ln, do_shift=shift, eps=g.eps)
+    w1c, w2c = _w(w1, g.dtype), _w(w2, g.dtype)
+    h, u = ops.gemm_geglu(a2, w1c, b1, keep_u=save)
+    keep_y = save and scale is not None
+    out, y = ops.gemm_resid(h, w2c, b2, None if resid is None else resid.contiguous().view(b * n, d),
+                            None if scale is None else scale.detach().reshape(-1).contiguous(), sign, keep_y=keep_y)
+    out = out.view(b, n, d)
+    ctx = None
+    if save:
+        ctx = (x_in, mean, rstd, a2, w1c, w2c, u, h, y, shift)
+    return out, ctx
+
+
+def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=None):
+    """Returns (dx_in, dln_w, dln_b, dw1, db1, dw2, db2, dscale)."""
+    x_in, mean, rstd, a2, w1c, w2c, u, h, y, shift = ctx
+    b, n, d = x_in.shape
+    M = b * n
+    d_out = d_out.contiguous().view(M, d)
+    sc = None if scale is None else scale.detach().reshape(-1).contiguous()
+    dy, dscale, db2 = ops.scale_bwd(d_out, y, sc, sign, g.dtype)
+    du = ops.gemm_geglu_bwd(dy, w2c, u)                                                   # [M, 2H]
+    dw2 = ops.gemm_store(dy, h, a_mn=True, b_mn=True, out_dtype=torch.float32)            # [d, H]
+    db1 = ops.colsum(du)
+    da2 = ops.gemm_store(du, w1c, a_mn=False, b_mn=True)                                  # [M, d]
+    dw1 = ops.gemm_store(du, a2, a_mn=True, b_mn=True, out_dtype=torch.float32)           # [2H, d]
+    dln_w = dln_b = None
+    if g.do_ln:
+        dln_w = torch.zeros(d, device=x_in.device, dtype=torch.float32)
+        dln_b = torch.zeros(d, device=x_in.device, dtype=torch.float32)
+    dx = ops.ln_shift_bwd(da2, x_in, mean, rstd, ln_w, None if dres is None else dres.contiguous(), g.text_len, g.fmap,
+                          do_ln=g.do_ln, do_shift=shift, dgamma=dln_w, dbeta=dln_b)
+    if dscale is not None:
+        dscale = dscale.view_as(scale)
+    return dx, dln_w, dln_b, dw1, db1, dw2, db2, dscale
+
+
+# =====================================================================================================
+# autograd wrappers
+# =====================================================================================================
+class AttnSublayerFn(torch.autograd.Function):
+    """out = resid + sign*scale*Attn(Shift(LN(x_in))).  If `resid_is_input`, resid := x_in and the residual-branch
+    gradient is fused into the LayerNorm backward kernel."""
+
+    @staticmethod
+    def forward(ctx, g, resid_is_input, sign, cos_t, sin_t, key_mask, x_in, resid, ln_w, ln_b, w_qkv, w_out, b_out, scale):
+        r = x_in if resid_is_input else resid
+        need = torch.is_grad_enabled()
+        out, saved = attn_sublayer_forward(g, x_in, r, ln_w, ln_b, w_qkv, w_out, b_out, scale, sign, cos_t, sin_t, key_mask,
+                                           save=True)
+        ctx.g, ctx.resid_is_input, ctx.sign = g, resid_is_input, sign
+        ctx.cos_t, ctx.sin_t, ctx.key_mask = cos_t, sin_t, key_mask
+        ctx.saved = saved
+        ctx.ln_w, ctx.scale = ln_w, scale
+        ctx.has_resid = resid is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        g = ctx.g
+        d_out = d_out.contiguous()
+        dres = d_out if ctx.resid_is_input else None
+        dx, dln_w, dln_b, dw_qkv, dw_out, db_out, dscale = attn_sublayer_backward(
+            g, ctx.saved, d_out, ctx.ln_w, ctx.scale, ctx.sign, ctx.cos_t, ctx.sin_t, ctx.key_mask, dres=dres)
+        ctx.saved = None
+        d_resid = d_out if (ctx.has_resid and not ctx.resid_is_input) else None
+        return (None, None, None, None, None, None, dx, d_resid, dln_w, dln_b, dw_qkv, dw_out, db_out, dscale)
+
+
+class FFSublayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, resid_is_input, sign, x_in, resid, ln_w, ln_b, w1, b1, w2, b2, scale):
+        r = x_in if resid_is_input else resid
+        out, saved = ff_sublayer_forward(g, x_in, r, ln_w, ln_b, w1, b1, w2, b2, scale, sign, save=True)
+        ctx.g, ctx.resid_is_input, ctx.sign = g, resid_is_input, sign
+        ctx.saved = saved
+        ctx.ln_w, ctx.scale = ln_w, scale
+        ctx.has_resid = resid is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        d_out = d_out.contiguous()
+        dres = d_out if ctx.resid_is_input else None
+        dx, dln_w, dln_b, dw1, db1, dw2, db2, dscale = ff_sublayer_backward(ctx.g, ctx.saved, d_out, ctx.ln_w, ctx.scale, ctx.sign,
+                                                                              dres=dres)
+        ctx.saved = None
+        d_resid = d_out if (ctx.has_resid and not ctx.resid_is_input) else None
+        return (None, None, None, dx, d_resid, dln_w, dln_b, dw1, db1, dw2, db2, dscale)
+
+
+class LayerNormFn(torch.autograd.Function):
+    """Plain LayerNorm on the ln_shift kernels (used for sandwich norm, transformer.py:96,102)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        shp = x.shape
+        x3 = x.contiguous().view(1, -1, shp[-1]).float()
+        out, mean, rstd = ops.ln_shift_fwd(x3, w, b, torch.float32, 0, 1, do_ln=True, do_shift=False, eps=eps)
+        ctx.save_for_backward(x3, mean, rstd, w)
+        return out.view(shp)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x3, mean, rstd, w = ctx.saved_tensors
+        d = x3.shape[-1]
+        dw = torch.zeros(d, device=x3.device, dtype=torch.float32)
+        db = torch.zeros(d, device=x3.device, dtype=torch.float32)
+        dx = ops.ln_shift_bwd(d_out.contiguous().view(-1, d).float(), x3, mean, rstd, w, None, 0, 1, do_ln=True, do_shift=False,
+                              dgamma=dw, dbeta=db)
+        return dx.view(d_out.shape), dw, db, None

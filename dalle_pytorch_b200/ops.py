@@ -1,0 +1,287 @@
+"""Thin torch-tensor wrappers over the C ABI (include/dalle_b200.h).  No arithmetic happens in Python:
+each function fills a POD struct with device pointers and enqueues the kernel on the current CUDA stream.
+Tensors are allocated by torch (the library never owns memory)."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (F32, BF16, EPI_STORE, EPI_QKV, EPI_RESID, EPI_GEGLU, EPI_GEGLU_BWD, GEMM_AUTO,
+                   ATTN_FULL, ATTN_AXIAL_ROW, ATTN_AXIAL_COL, ATTN_CONV_LIKE, ATTN_STATIC)
+
+_launch_count = 0          # kernels-launching ABI calls (bench.py reports it as gpu_launches)
+
+
+def launches():
+    return _launch_count
+
+
+def _count(n=1):
+    global _launch_count
+    _launch_count += n
+
+
+def dt_code(dtype):
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f'unsupported compute dtype {dtype}')
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda, 'libdalle_b200 operates on CUDA tensors only (no CPU fallback)'
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _c(t):
+    assert t.is_contiguous(), 'expected a contiguous tensor'
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+def ln_shift_fwd(x, gamma, beta, out_dtype, text_len, fmap, do_ln=True, do_shift=True, eps=1e-5):
+    """x [b,n,d] fp32 -> (out [b*n,d] out_dtype, mean [b*n], rstd [b*n])"""
+    b, n, d = x.shape
+    _c(x)
+    assert x.dtype == torch.float32
+    out = torch.empty(b * n, d, device=x.device, dtype=out_dtype)
+    mean = torch.empty(b * n, device=x.device, dtype=torch.float32) if do_ln else None
+    rstd = torch.empty(b * n, device=x.device, dtype=torch.float32) if do_ln else None
+    P = _lib.LnShiftFwdParams(batch=b, n=n, d=d, text_len=text_len, fmap=fmap, do_ln=int(do_ln), do_shift=int(do_shift),
+                              out_dtype=dt_code(out_dtype), eps=eps, x=_p(x), gamma=_p(gamma), beta=_p(beta), out=_p(out),
+                              mean=_p(mean), rstd=_p(rstd))
+    _lib.check(_lib.lib().dalle_b200_ln_shift_fwd(ctypes.byref(P), _stream()), 'ln_shift_fwd')
+    _count()
+    return out, mean, rstd
+
+
+def ln_shift_bwd(d_out, x, mean, rstd, gamma, dres, text_len, fmap, do_ln=True, do_shift=True, dgamma=None, dbeta=None):
+    """-> dx [b,n,d] fp32 ; dgamma/dbeta accumulated in place (must be zero-initialised by the caller)"""
+    b, n, d = x.shape
+    dx = torch.empty_like(x)
+    P = _lib.LnShiftBwdParams(batch=b, n=n, d=d, text_len=text_len, fmap=fmap, do_ln=int(do_ln), do_shift=int(do_shift),
+                              dout_dtype=dt_code(d_out.dtype), d_out=_p(_c(d_out)), x=_p(_c(x)), mean=_p(mean), rstd=_p(rstd),
+                              gamma=_p(gamma), dres=_p(dres), dx=_p(dx), dgamma=_p(dgamma), dbeta=_p(dbeta))
+    _lib.check(_lib.lib().dalle_b200_ln_shift_bwd(ctypes.byref(P), _stream()), 'ln_shift_bwd')
+    _count()
+    return dx
+
+
+_gemm_events = None      # list of (start, end, flops, backend, shape-key) while gemm_timing is on
+
+
+def gemm_timing(enable):
+    """bench.py: bracket every GEMM launch with CUDA events on the launching stream.  gemm_timing(True) starts
+    collecting; gemm_timing(False) synchronises and returns {'tcgen05': {flops, ms, launches}, 'simt': {...},
+    'by_shape': {key: {ms, tflops, launches}}}."""
+    global _gemm_events
+    if enable:
+        _gemm_events = []
+        return None
+    ev, _gemm_events = _gemm_events or [], None
+    torch.cuda.synchronize()
+    out = {'tcgen05': {'flops': 0.0, 'ms': 0.0, 'launches': 0}, 'simt': {'flops': 0.0, 'ms': 0.0, 'launches': 0}, 'by_shape': {}}
+    for s, e, flops, backend, key in ev:
+        ms = s.elapsed_time(e)
+        fam = out['tcgen05' if backend == _lib.GEMM_TCGEN05 else 'simt']
+        fam['flops'] += flops
+        fam['ms'] += ms
+        fam['launches'] += 1
+        b = out['by_shape'].setdefault(key, {'ms': 0.0, 'flops': 0.0, 'launches': 0})
+        b['ms'] += ms
+        b['flops'] += flops
+        b['launches'] += 1
+    for b in out['by_shape'].values():
+        b['tflops'] = b['flops'] / (b['ms'] * 1e-3) / 1e12 if b['ms'] > 0 else 0.0
+        b['ms_per_launch'] = b['ms'] / b['launches']
+        del b['flops']
+    return out
+
+
+_EPI_NAMES = {EPI_STORE: 'store', EPI_QKV: 'qkv', EPI_RESID: 'resid', EPI_GEGLU: 'geglu', EPI_GEGLU_BWD: 'geglu_bwd'}
+
+
+def _gemm(P):
+    if _gemm_events is None:
+        _lib.check(_lib.lib().dalle_b200_gemm(ctypes.byref(P), _stream()), 'gemm')
+        _count()
+        return
+    backend = _lib.lib().dalle_b200_gemm_select(ctypes.byref(P))
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    _lib.check(_lib.lib().dalle_b200_gemm(ctypes.byref(P), _stream()), 'gemm')
+    e.record()
+    _count()
+    key = f"{_EPI_NAMES.get(P.epilogue, '?')}:{'M' if P.a_mn_major else 'K'}{'N' if P.b_mn_major else 'K'}:{P.M}x{P.N}x{P.K}"
+    _gemm_events.append((s, e, 2.0 * P.M * P.N * P.K, backend, key))
+
+
+def _base(M, N, K, A, lda, a_mn, B, ldb, b_mn, epilogue, backend=GEMM_AUTO):
+    assert A.dtype == B.dtype
+    return _lib.GemmParams(M=M, N=N, K=K, dtype=dt_code(A.dtype), backend=backend, A=_p(A), lda=lda, a_mn_major=int(a_mn),
+                           B=_p(B), ldb=ldb, b_mn_major=int(b_mn), epilogue=epilogue)
+
+
+def gemm_store(A, B, a_mn=False, b_mn=False, out_dtype=None, bias=None, backend=GEMM_AUTO):
+    """acc[M,N] = sum_k A(m,k) B(n,k).  A: [M,K] (a_mn=False) or [K,M] (a_mn=True); B: [N,K] or [K,N]."""
+    _c(A), _c(B)
+    if a_mn:
+        K, M = A.shape
+    else:
+        M, K = A.shape
+    if b_mn:
+        Kb, N = B.shape
+    else:
+        N, Kb = B.shape
+    assert K == Kb, (A.shape, B.shape, a_mn, b_mn)
+    out_dtype = out_dtype or A.dtype
+    C = torch.empty(M, N, device=A.device, dtype=out_dtype)
+    P = _base(M, N, K, A, A.shape[1], a_mn, B, B.shape[1], b_mn, EPI_STORE, backend)
+    P.C, P.ldc, P.c_dtype, P.bias = _p(C), N, dt_code(out_dtype), _p(bias)
+    _gemm(P)
+    return C
+
+
+def gemm_qkv(A, W, batch, seq_n, heads, dim_head, cos_t, sin_t, q_scale, pos_offset=0, backend=GEMM_AUTO):
+    """A [batch*seq_n, d], W [3*heads*dim_head, d] -> q,k,v [batch, heads, seq_n, dim_head] (rotary + q scale fused)"""
+    _c(A), _c(W)
+    M, K = A.shape
+    N = W.shape[0]
+    qkv = torch.empty(3, batch, heads, seq_n, dim_head, device=A.device, dtype=A.dtype)
+    P = _base(M, N, K, A, K, False, W, K, False, EPI_QKV, backend)
+    P.q, P.k, P.v = _p(qkv[0]), _p(qkv[1]), _p(qkv[2])
+    P.cos_t, P.sin_t = _p(cos_t), _p(sin_t)
+    P.seq_n, P.heads, P.dim_head, P.pos_offset, P.q_scale = seq_n, heads, dim_head, pos_offset, q_scale
+    _gemm(P)
+    return qkv[0], qkv[1], qkv[2]
+
+
+def gemm_resid(A, W, bias, resid, scale, sign=1.0, keep_y=False, backend=GEMM_AUTO):
+    """out[M,N] fp32 = resid + sign*scale*(A W^T + bias); optionally also returns y = A W^T + bias (A.dtype)"""
+    _c(A), _c(W)
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty(M, N, device=A.device, dtype=torch.float32)
+    y = torch.empty(M, N, device=A.device, dtype=A.dtype) if keep_y else None
+    P = _base(M, N, K, A, K, False, W, K, False, EPI_RESID, backend)
+    P.bias, P.resid, P.scale, P.sign, P.y_out, P.out = _p(bias), _p(resid), _p(scale), sign, _p(y), _p(out)
+    _gemm(P)
+    return out, y
+
+
+def gemm_geglu(A, W1, b1, keep_u=True, backend=GEMM_AUTO):
+    """A [M,d], W1 [2H,d], b1 [2H] -> (h [M,H], u [M,2H] or None)"""
+    _c(A), _c(W1)
+    M, K = A.shape
+    N = W1.shape[0]
+    H = N // 2
+    h = torch.empty(M, H, device=A.device, dtype=A.dtype)
+    u = torch.empty(M, N, device=A.device, dtype=A.dtype) if keep_u else None
+    P = _base(M, N, K, A, K, False, W1, K, False, EPI_GEGLU, backend)
+    P.bias, P.u_out, P.h_out, P.hidden = _p(b1), _p(u), _p(h), H
+    _gemm(P)
+    return h, u
+
+
+def gemm_geglu_bwd(dy, W2, u, backend=GEMM_AUTO):
+    """dy [M,d], W2 [d,H] (read N-major), u [M,2H] -> du [M,2H]"""
+    _c(dy), _c(W2), _c(u)
+    M, K = dy.shape
+    H = W2.shape[1]
+    du = torch.empty_like(u)
+    P = _base(M, H, K, dy, K, False, W2, H, True, EPI_GEGLU_BWD, backend)
+    P.u_in, P.du_out, P.hidden = _p(u), _p(du), H
+    _gemm(P)
+    return du
+
+
+# ------------------------------------------------------------------------------------------------
+class AttnSpec:
+    """Geometry + pattern of one attention layer (maps the reference's attention classes onto db200_attn_pattern)."""
+
+    def __init__(self, pattern=ATTN_FULL, causal=True, stable=False, text_len=0, fmap=0, kernel_size=0, dilation=1,
+                 static_mask=None):
+        self.pattern, self.causal, self.stable = pattern, causal, stable
+        self.text_len, self.fmap, self.kernel_size, self.dilation = text_len, fmap, kernel_size, dilation
+        self.static_mask = static_mask      # uint8 [n, n] on device or None
+
+
+def _attn_params(spec, q, k, v, out, lse, key_mask):
+    b, h, n_q, dh = q.shape
+    n_k = k.shape[2]
+    sm = spec.static_mask
+    return _lib.AttnFwdParams(batch=b, heads=h, n_q=n_q, n_k=n_k, dim_head=dh, dtype=dt_code(q.dtype), pattern=spec.pattern,
+                              causal=int(spec.causal), stable=int(spec.stable), text_len=spec.text_len, fmap=spec.fmap,
+                              kernel_size=spec.kernel_size, dilation=spec.dilation, key_mask=_p(key_mask),
+                              static_mask=_p(sm), static_ld=(sm.shape[1] if sm is not None else 0),
+                              q=_p(_c(q)), k=_p(_c(k)), v=_p(_c(v)), out=_p(out), lse=_p(lse))
+
+
+def attn_fwd(spec, q, k, v, key_mask=None):
+    """q [b,h,n_q,64], k,v [b,h,n_k,64] -> out [b,n_q,h*64], lse [b,h,n_q]"""
+    b, h, n_q, dh = q.shape
+    out = torch.empty(b, n_q, h * dh, device=q.device, dtype=q.dtype)
+    lse = torch.empty(b, h, n_q, device=q.device, dtype=torch.float32)
+    P = _attn_params(spec, q, k, v, out, lse, key_mask)
+    _lib.check(_lib.lib().dalle_b200_attn_fwd(ctypes.byref(P), _stream()), 'attn_fwd')
+    _count()
+    return out, lse
+
+
+def attn_bwd(spec, q, k, v, out, lse, d_out, cos_t, sin_t, q_scale, key_mask=None):
+    """-> dqkv [b*n, 3*h*64] : gradient w.r.t. the to_qkv output (rotary adjoint and q scale folded in)"""
+    b, h, n, dh = q.shape
+    dqkv = torch.empty(b * n, 3 * h * dh, device=q.device, dtype=q.dtype)
+    delta = torch.empty(b, h, n, device=q.device, dtype=torch.float32)
+    P = _lib.AttnBwdParams(f=_attn_params(spec, q, k, v, out, lse, key_mask), d_out=_p(_c(d_out)), cos_t=_p(cos_t), sin_t=_p(sin_t),
+                           q_scale=q_scale, delta=_p(delta), dqkv=_p(dqkv))
+    _lib.check(_lib.lib().dalle_b200_attn_bwd(ctypes.byref(P), _stream()), 'attn_bwd')
+    _count(3)
+    return dqkv
+
+
+# ------------------------------------------------------------------------------------------------
+def scale_bwd(d_out, y, scale, sign, dtype, want_dscale=True, want_dbias=True):
+    """d_out [M,d] fp32 -> dy [M,d] dtype, dscale [d] fp32 | None, dbias [d] fp32 | None"""
+    M, d = d_out.shape
+    dy = torch.empty(M, d, device=d_out.device, dtype=dtype)
+    dscale = torch.zeros(d, device=d_out.device, dtype=torch.float32) if (want_dscale and scale is not None) else None
+    dbias = torch.zeros(d, device=d_out.device, dtype=torch.float32) if want_dbias else None
+    P = _lib.ScaleBwdParams(rows=M, d=d, dtype=dt_code(dtype), sign=sign, d_out=_p(_c(d_out)), y=_p(y), scale=_p(scale), dy=_p(dy),
+                            dscale=_p(dscale), dbias=_p(dbias))
+    _lib.check(_lib.lib().dalle_b200_scale_bwd(ctypes.byref(P), _stream()), 'scale_bwd')
+    _count()
+    return dy, dscale, dbias
+
+
+def colsum(x):
+    rows, cols = x.shape
+    out = torch.zeros(cols, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().dalle_b200_colsum(_p(_c(x)), dt_code(x.dtype), rows, cols, _p(out), _stream()), 'colsum')
+    _count()
+    return out
+
+
+def cast_bf16(src):
+    src = _c(src)
+    assert src.dtype == torch.float32
+    dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().dalle_b200_cast_bf16(_p(src), _p(dst), src.numel(), _stream()), 'cast_bf16')
+    _count()
+    return dst
+
+
+def axpby(a, b, alpha):
+    """a + alpha * b over fp32 tensors of equal shape"""
+    _c(a), _c(b)
+    y = torch.empty_like(a)
+    _lib.check(_lib.lib().dalle_b200_axpby(_p(a), _p(b), alpha, _p(y), a.numel(), _stream()), 'axpby')
+    _count()
+    return y

@@ -1,0 +1,210 @@
+/*
+ * dalle_b200.h — C ABI of libdalle_b200.so, the B200 (sm_100a) hot path of the DALL-E transformer block.
+ *
+ * This is the drop-in boundary.  Every entry point replaces an op sequence that the
+ * reference (lucidrains/DALLE-pytorch, /root/reference/dalle_pytorch/) evaluates with aten calls; the
+ * reference file:line each one stands in for is cited next to its declaration.  The host side
+ * (dalle_pytorch_b200/*.py) mirrors the reference's module API and calls these functions through ctypes.
+ *
+ * Conventions
+ *   - plain C: POD parameter structs of raw DEVICE pointers, sizes and flags; no torch types.
+ *   - the library never allocates, frees or retains device memory; the caller owns every buffer.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it.
+ *   - return 0 on success, a negative db200_status on failure; dalle_b200_last_error() returns a
+ *     thread-local message.  No exceptions cross the ABI and nothing aborts.
+ *   - re-entrant: forward is called from the Python thread, backward from autograd's device thread.
+ *   - dtype: DB200_F32 computes and stores in fp32 (parity mode, tolerance rtol 1e-3 / atol 1e-5 against
+ *     the reference CPU path); DB200_BF16 stores activations/weights in bf16 with fp32 accumulation
+ *     (speed mode: tcgen05 tensor-core GEMMs).  The residual stream, LayerNorm statistics, softmax
+ *     statistics and all parameter gradients are always fp32.
+ */
+#ifndef DALLE_B200_H
+#define DALLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DALLE_B200_VERSION 100
+
+typedef enum {
+  DB200_OK = 0,
+  DB200_ERR_BAD_ARG = -1,      /* shape / pointer / flag combination not supported */
+  DB200_ERR_UNSUPPORTED = -2,  /* valid request the kernels do not implement (e.g. dim_head != 64) */
+  DB200_ERR_CUDA = -3,         /* CUDA runtime / driver error at launch */
+  DB200_ERR_NO_DEVICE = -4     /* no sm_100 device / driver entry point missing */
+} db200_status;
+
+typedef enum { DB200_F32 = 0, DB200_BF16 = 1 } db200_dtype;
+
+/* attention sparsity pattern = allowed(query i, key j) predicate evaluated inside the kernels */
+typedef enum {
+  DB200_ATTN_FULL = 0,      /* Attention                    attention.py:39-99   (causal triu or none)        */
+  DB200_ATTN_AXIAL_ROW = 1, /* SparseAxialCausalAttention   attention.py:225-335 axis=0                       */
+  DB200_ATTN_AXIAL_COL = 2, /*                              axis=1                                             */
+  DB200_ATTN_CONV_LIKE = 3, /* SparseConvCausalAttention    attention.py:103-221                              */
+  DB200_ATTN_STATIC = 4     /* Attention(static_mask=...)   attention.py:89-90 ; transformer.py:333-350       */
+} db200_attn_pattern;
+
+typedef enum {
+  DB200_EPI_STORE = 0,     /* C = acc (+bias)                                       nn.Linear                  */
+  DB200_EPI_QKV = 1,       /* head split + rotary(q,k,v) + q*scale                  attention.py:63-69,263-269 */
+  DB200_EPI_RESID = 2,     /* out = resid + sign*scale*(acc+bias)                   attention.py:97 / transformer.py:118,88 ; reversible.py:139-140 */
+  DB200_EPI_GEGLU = 3,     /* h = (a+ba) * gelu_erf(g+bg), also stores u=[a|g]      transformer.py:106-109,115 */
+  DB200_EPI_GEGLU_BWD = 4  /* du = [dh*gelu(g) | dh*a*gelu'(g)]                     autograd of the above      */
+} db200_epilogue;
+
+typedef enum { DB200_GEMM_AUTO = 0, DB200_GEMM_SIMT = 1, DB200_GEMM_TCGEN05 = 2 } db200_gemm_backend;
+
+int dalle_b200_version(void);
+const char* dalle_b200_last_error(void);
+/* 1 if device `dev` is an sm_100 part on which the tcgen05/TMA kernels can run, else 0 */
+int dalle_b200_device_ok(int dev);
+/* sizeof() of the parameter structs in declaration order (ln_shift_fwd, ln_shift_bwd, gemm, attn_fwd, attn_bwd,
+ * scale_bwd) so that a foreign-language binding can verify its struct layout at load time; returns the count */
+int dalle_b200_abi_sizes(int* out, int capacity);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm (+ token shift) producing the GEMM A operand.
+ * Replaces PreNorm.norm + PreShiftToken.forward: transformer.py:100, 155-186 (training branch).
+ * x [rows = batch*n, d] fp32 (residual stream) -> out [rows, d] (dtype), mean/rstd [rows] fp32 saved
+ * for backward.  do_ln=0: plain copy/cast; do_shift=0: no shift (shift_tokens=False or n < text_len).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int batch, n, d;
+  int text_len, fmap;       /* text_len = text_seq_len + 1 (<bos>), fmap = image_fmap_size */
+  int do_ln, do_shift;
+  int out_dtype;
+  float eps;
+  const float* x;
+  const float* gamma;
+  const float* beta;
+  void* out;
+  float* mean;
+  float* rstd;
+} db200_ln_shift_fwd_params;
+int dalle_b200_ln_shift_fwd(const db200_ln_shift_fwd_params* p, void* stream);
+
+/* backward of the above: dx = dres + LN_bwd(unshift(d_out)); dgamma/dbeta are ACCUMULATED (+=) */
+typedef struct {
+  int batch, n, d;
+  int text_len, fmap;
+  int do_ln, do_shift;
+  int dout_dtype;
+  const void* d_out;        /* [rows, d] gradient w.r.t. the shifted LN output (dtype) */
+  const float* x;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  const float* dres;        /* optional fp32 [rows, d] added to the result (the residual branch) */
+  float* dx;                /* [rows, d] fp32 */
+  float* dgamma;            /* [d] fp32, += */
+  float* dbeta;             /* [d] fp32, += */
+} db200_ln_shift_bwd_params;
+int dalle_b200_ln_shift_bwd(const db200_ln_shift_bwd_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM with fused epilogue:  acc[M,N] = sum_k A(m,k) * B(n,k)
+ *   a_mn_major = 0: A(m,k) = A[m*lda + k] (K-major)      1: A(m,k) = A[k*lda + m] (M-major)
+ *   b_mn_major = 0: B(n,k) = B[n*ldb + k] (K-major)      1: B(n,k) = B[k*ldb + n] (N-major)
+ * forward  Linear  : A = activations (K-major), B = weight [out,in] (K-major)      attention.py:63,97 transformer.py:114,118
+ * dgrad            : A = dY (K-major), B = weight [out,in] read as (N=in, K=out) (N-major)
+ * wgrad            : A = dY^T (M-major), B = X^T (N-major), C = dW [out,in] fp32
+ * dtype selects fp32 (SIMT FFMA) or bf16 (tcgen05.mma kind::f16, TMA-fed) operands; accumulation fp32.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int M, N, K;
+  int dtype;                /* operand dtype of A and B */
+  int backend;              /* db200_gemm_backend */
+  const void* A; int64_t lda; int a_mn_major;
+  const void* B; int64_t ldb; int b_mn_major;
+  int epilogue;             /* db200_epilogue */
+  /* STORE */
+  void* C; int64_t ldc; int c_dtype; const float* bias;   /* bias [N] fp32 optional */
+  /* QKV: N = 3*heads*dim_head; rows m = b*seq_n + p */
+  void* q; void* k; void* v;                 /* [batch, heads, seq_n, dim_head] (dtype)                  */
+  const float* cos_t; const float* sin_t;    /* [n_pos, dim_head/2] fp32, (1,0) on pass-through pairs; NULL = no rotary */
+  int seq_n, heads, dim_head, pos_offset;
+  float q_scale;
+  /* RESID: out[m,n] = resid[m,n] + sign*scale[n]*(acc + bias[n]); y_out (dtype, optional) keeps acc+bias */
+  const float* resid; const float* scale; float sign; void* y_out; float* out;
+  /* GEGLU: N = 2*hidden; bias [2*hidden]; u_out [M, 2*hidden] (dtype, optional), h_out [M, hidden] (dtype) */
+  void* u_out; void* h_out; int hidden;
+  /* GEGLU_BWD: N = hidden; acc = dh; u_in [M, 2*hidden]; du_out [M, 2*hidden] (dtype) */
+  const void* u_in; void* du_out;
+} db200_gemm_params;
+int dalle_b200_gemm(const db200_gemm_params* p, void* stream);
+/* which backend dalle_b200_gemm would run for *p (DB200_GEMM_SIMT or DB200_GEMM_TCGEN05); no launch */
+int dalle_b200_gemm_select(const db200_gemm_params* p);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused attention (flash-style, never materialises [n,n]) for every pattern of the reference.
+ * q [batch, heads, n_q, 64], k,v [batch, heads, n_k, 64] with rotary and q-scale already applied (EPI_QKV);
+ * queries are the LAST n_q positions of the n_k keys (n_q == n_k in training; n_q < n_k for cached decoding,
+ * attention.py:71-76).
+ * out [batch, n_q, heads*64] (merged heads, A operand of to_out), lse [batch, heads, n_q] fp32.
+ * Replaces attention.py:78-96 and :271-331 (+ :147-207 for conv_like).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int batch, heads, n_q, n_k, dim_head;
+  int dtype;
+  int pattern;              /* db200_attn_pattern */
+  int causal;               /* FULL / STATIC only: apply j <= i (attention.py:84-87) */
+  int stable;               /* stable_softmax (attention.py:27-30); alpha = 2^10 is an exact rescale, see DESIGN.md */
+  int text_len, fmap;
+  int kernel_size, dilation;            /* CONV_LIKE */
+  const uint8_t* key_mask;  /* optional [batch, n_k] 1 = keep (attention.py:80-83) */
+  const uint8_t* static_mask; int64_t static_ld;   /* STATIC: [n, static_ld] 1 = allowed */
+  const void* q; const void* k; const void* v;
+  void* out;
+  float* lse;
+} db200_attn_fwd_params;
+int dalle_b200_attn_fwd(const db200_attn_fwd_params* p, void* stream);
+
+/* backward: d_out [batch, n, heads*64] (dtype) -> dqkv [batch*n, 3*heads*64] (dtype) = gradient w.r.t. the
+ * to_qkv output, i.e. with the inverse rotary rotation and the q-scale folded in (attention.py:63-69 adjoint).
+ * delta [batch, heads, n] fp32 is workspace.  Training only (n_q == n_k). */
+typedef struct {
+  db200_attn_fwd_params f;  /* same geometry / q,k,v / out / lse as the forward call */
+  const void* d_out;
+  const float* cos_t; const float* sin_t; float q_scale;  /* as in EPI_QKV; NULL tables = no rotary */
+  float* delta;
+  void* dqkv;
+} db200_attn_bwd_params;
+int dalle_b200_attn_bwd(const db200_attn_bwd_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerScale / residual backward glue (transformer.py:88 adjoint + bias grad of the last Linear):
+ *   dy[m,c]   = sign * scale[c] * d_out[m,c]          (dtype)  -> A operand of dgrad / wgrad
+ *   dscale[c] += sum_m sign * d_out[m,c] * y[m,c]
+ *   dbias[c]  += sum_m dy[m,c]
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int rows, d;
+  int dtype;
+  float sign;
+  const float* d_out;
+  const void* y;            /* [rows,d] (dtype) saved by EPI_RESID; may be NULL when scale is NULL */
+  const float* scale;       /* NULL = 1 */
+  void* dy;
+  float* dscale;            /* optional, += */
+  float* dbias;             /* optional, += */
+} db200_scale_bwd_params;
+int dalle_b200_scale_bwd(const db200_scale_bwd_params* p, void* stream);
+
+/* column sums: out[c] += sum_m x[m,c]  (bias gradient of net.0, transformer.py:114) */
+int dalle_b200_colsum(const void* x, int dtype, int rows, int cols, float* out, void* stream);
+
+/* fp32 -> bf16 cast of `count` elements (weights are kept in fp32 and cast once per step) */
+int dalle_b200_cast_bf16(const float* src, void* dst, int64_t count, void* stream);
+
+/* y = a + alpha*b over fp32 (reversible stream arithmetic, reversible.py:83,86,96,99) */
+int dalle_b200_axpby(const float* a, const float* b, float alpha, float* y, int64_t count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DALLE_B200_H */

@@ -1,0 +1,114 @@
+"""CPU-side checks (run with -m "not gpu"): the C-ABI library loads and exports every symbol the header declares,
+ctypes struct layouts match the C structs, and the host logic of the package (module tree / state-dict keys, rotary
+table, static masks, token-shift restatement, argument routing) agrees with the oracle / reference."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import dalle_pytorch_b200 as D
+from dalle_pytorch_b200 import _lib
+from dalle_pytorch_b200.attention import rotary_tables
+from dalle_pytorch_b200.transformer import PreShiftToken, build_rotary_angle_table
+from dalle_pytorch_b200.reversible import route_args
+from dalle_oracle import OracleConfig, make_state_dict, rotary_angle_table, token_shift, allowed_mask
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_header_symbols():
+    lib = _lib.lib()
+    assert lib.dalle_b200_version() == 100
+    hdr = open(os.path.join(ROOT, 'include', 'dalle_b200.h')).read()
+    declared = set(re.findall(r'\b(dalle_b200_[a-z0-9_]+)\s*\(', hdr))
+    assert declared == set(_lib.EXPORTED), declared ^ set(_lib.EXPORTED)
+    for name in declared:
+        assert hasattr(lib, name), f'{name} not exported by libdalle_b200.so'
+
+
+def test_struct_layouts_match_c():
+    lib = _lib.lib()
+    sizes = (ctypes.c_int * 8)()
+    n = lib.dalle_b200_abi_sizes(sizes, 8)
+    assert n == len(_lib._STRUCTS)
+    for i, st in enumerate(_lib._STRUCTS):
+        assert ctypes.sizeof(st) == sizes[i], st.__name__
+
+
+def test_bad_arguments_are_rejected_without_a_gpu():
+    lib = _lib.lib()
+    P = _lib.GemmParams(M=4, N=3, K=8, dtype=0, epilogue=0)     # odd N, null operands
+    rc = lib.dalle_b200_gemm(ctypes.byref(P), None)
+    assert rc == -1 and b'null operand' in lib.dalle_b200_last_error()
+    A = _lib.AttnFwdParams(batch=1, heads=1, n_q=4, n_k=4, dim_head=32)
+    rc = lib.dalle_b200_attn_fwd(ctypes.byref(A), None)
+    assert rc == -2 and b'dim_head' in lib.dalle_b200_last_error()
+
+
+@pytest.mark.parametrize('kw', [dict(), dict(reversible=True), dict(shift_tokens=False), dict(sandwich_norm=True),
+                                dict(attn_types=('full', 'axial_row', 'axial_col', 'conv_like'), depth=4)])
+def test_state_dict_keys_match_reference_format(kw):
+    base = dict(dim=64, depth=2, heads=2, text_seq_len=8, fmap=4, num_text_tokens=50, num_image_tokens=32)
+    base.update(kw)
+    cfg = OracleConfig(**base)
+    sd = make_state_dict(cfg)       # keys asserted equal to the live reference's in oracle/make_golden.py
+    m = D.DALLE(dim=cfg.dim, vae=D.TokenVAE(image_size=8 * cfg.fmap, num_layers=3, num_tokens=cfg.num_image_tokens),
+                num_text_tokens=cfg.num_text_tokens, text_seq_len=cfg.text_seq_len, depth=cfg.depth, heads=cfg.heads,
+                reversible=cfg.reversible, attn_types=cfg.attn_types, sandwich_norm=cfg.sandwich_norm, shift_tokens=cfg.shift_tokens)
+    own = m.state_dict()
+    assert set(own) == set(sd)
+    for k in own:
+        assert own[k].shape == sd[k].shape, k
+    assert torch.equal(own['transformer.pos_emb'], sd['transformer.pos_emb'])
+    m.load_state_dict(sd)
+
+
+def test_rotary_table_and_cos_sin():
+    for T, fm in ((9, 4), (65, 8), (257, 32)):
+        assert torch.equal(build_rotary_angle_table(T, fm, 64)[0], rotary_angle_table(T, fm, 64))
+    ang = build_rotary_angle_table(9, 4, 64)
+    cos, sin = rotary_tables(ang, 64)
+    assert cos.shape == (25, 32)
+    assert torch.allclose(cos[:, :30], ang[0, :, 0::2].double().cos().float()) and torch.all(cos[:, 30:] == 1)
+    assert torch.all(sin[:, 30:] == 0)
+
+
+def test_token_shift_restatement_matches_oracle():
+    ps = PreShiftToken(lambda x, **kw: x, image_size=4, seq_len=24)
+    for n in (24, 20, 9):
+        x = torch.randn(2, n, 32)
+        assert torch.equal(ps(x), token_shift(x, 9, 4))
+    x = torch.randn(2, 5, 32)
+    assert torch.equal(ps(x), x)
+
+
+def test_static_masks_match_predicate():
+    t = D.Transformer(dim=64, depth=1, seq_len=24, heads=2, image_fmap_size=4)
+    caus = torch.ones(24, 24).tril().bool()
+    for kind in ('axial_row', 'axial_col'):
+        assert torch.equal(t._get_attention_mask(kind) & caus, allowed_mask(kind, 24, 24, 9, 4))
+
+
+def test_route_args():
+    r = route_args({'mask': ((True, False),) * 2, 'cache': ((True, True),) * 2}, dict(mask=1, cache=2, other=3), 2)
+    assert r == [({'mask': 1, 'cache': 2}, {'cache': 2})] * 2
+
+
+def test_plan_resolves_fused_sublayers():
+    t = D.Transformer(dim=64, depth=2, seq_len=24, heads=2, image_fmap_size=4, shift_tokens=True,
+                      attn_types=('axial_row', 'conv_like'))
+    x = torch.zeros(1, 24, 64)
+    f0, g0 = t.layers.layers[0]
+    p = f0.plan(x, rotary_pos_emb=t.pos_emb)
+    assert p.kind == 'attn' and p.geom.do_shift and p.geom.text_len == 9 and p.geom.attn_spec.pattern == _lib.ATTN_AXIAL_ROW
+    assert g0.plan(x).kind == 'ff'
+    assert t.layers.layers[1][0].plan(x).geom.attn_spec.pattern == _lib.ATTN_CONV_LIKE
+    assert f0.plan(x, cache={}) is None           # inference cache -> module-by-module path
+
+
+def test_ops_refuse_cpu_tensors():
+    from dalle_pytorch_b200 import ops
+    with pytest.raises(AssertionError):
+        ops.colsum(torch.zeros(4, 4))

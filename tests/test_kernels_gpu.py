@@ -1,0 +1,253 @@
+"""Kernel-level checks on the GPU, through the C ABI (dalle_pytorch_b200.ops): every kernel against a plain
+torch fp32 evaluation of the same op on the same seeded inputs.  fp32 mode: rtol 1e-3 / atol 1e-5
+(north_star).  bf16 mode: inputs are rounded to bf16 first, tolerance 2e-2 relative to the tensor scale."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import report
+from dalle_oracle import allowed_mask, token_shift, rotary_angle_table, apply_rotary
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-3, 1e-5
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def ops():
+    from dalle_pytorch_b200 import ops as o
+    return o
+
+
+def bf16_tol(want):
+    return dict(rtol=2e-2, atol=2e-2 * float(want.abs().max()) + 1e-6)
+
+
+# ---- LayerNorm + token shift ------------------------------------------------------------------------------
+@pytest.mark.parametrize('n', [24, 19, 9, 5])
+@pytest.mark.parametrize('do_shift', [True, False])
+def test_ln_shift_fwd_bwd(n, do_shift):
+    o = ops()
+    torch.manual_seed(0)
+    b, d, T, fm = 2, 64, 9, 4
+    shift = do_shift and n >= T
+    x = torch.randn(b, n, d, device=dev()) * 2 + 0.5
+    w = torch.randn(d, device=dev()) * 0.2 + 1
+    bias = torch.randn(d, device=dev()) * 0.2
+    out, mean, rstd = o.ln_shift_fwd(x, w, bias, torch.float32, T, fm, do_ln=True, do_shift=shift)
+    xr = x.detach().cpu().requires_grad_()
+    wr, br = w.cpu().requires_grad_(), bias.cpu().requires_grad_()
+    y = F.layer_norm(xr, (d,), wr, br, 1e-5)
+    if shift:
+        y = token_shift(y, T, fm)
+    report('ln_shift_fwd', out.view(b, n, d), y, RTOL, ATOL)
+    gy = torch.randn(b, n, d)
+    dres = torch.randn(b, n, d)
+    y.backward(gy)
+    dg = torch.zeros(d, device=dev()); db = torch.zeros(d, device=dev())
+    dx = o.ln_shift_bwd(gy.to(dev()).view(b * n, d).contiguous(), x, mean, rstd, w, dres.to(dev()), T, fm, do_ln=True, do_shift=shift,
+                        dgamma=dg, dbeta=db)
+    report('ln_shift_bwd dx', dx, xr.grad + dres, RTOL, 1e-5)
+    report('ln_shift_bwd dgamma', dg, wr.grad, RTOL, 1e-4)
+    report('ln_shift_bwd dbeta', db, br.grad, RTOL, 1e-4)
+
+
+def test_ln_shift_full_size_property():
+    """C2 geometry (n=1280, d=1024): un-shifted output rows are plain LayerNorm; shifted halves equal neighbours."""
+    o = ops()
+    torch.manual_seed(1)
+    b, n, d, T, fm = 2, 1280, 1024, 257, 32
+    x = torch.randn(b, n, d, device=dev())
+    w = torch.ones(d, device=dev()); bias = torch.zeros(d, device=dev())
+    out, _, _ = o.ln_shift_fwd(x, w, bias, torch.float32, T, fm)
+    out = out.view(b, n, d)
+    ln = F.layer_norm(x, (d,))
+    report('pass-through half', out[..., d // 2:], ln[..., d // 2:], RTOL, ATOL)
+    report('text shift', out[:, 1:T, :d // 2], ln[:, :T - 1, :d // 2], RTOL, ATOL)
+    report('image top', out[:, T + fm:, :d // 4], ln[:, T:n - fm, :d // 4], RTOL, ATOL)
+    assert out[:, 0, :d // 2].abs().max() == 0 and out[:, T:T + fm, :d // 4].abs().max() == 0
+    assert out[:, T::fm, d // 4:d // 2].abs().max() == 0
+
+
+# ---- GEMM + epilogues ---------------------------------------------------------------------------------------
+def _mk(shape, dtype, scale=1.0):
+    return (torch.randn(*shape, device=dev()) * scale).to(dtype)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('a_mn,b_mn', [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize('M,N,K', [(96, 64, 72), (257, 192, 128), (130, 320, 264)])
+def test_gemm_store_all_majors(dtype, a_mn, b_mn, M, N, K):
+    o = ops()
+    torch.manual_seed(2)
+    A = _mk((K, M) if a_mn else (M, K), dtype)
+    B = _mk((K, N) if b_mn else (N, K), dtype)
+    bias = torch.randn(N, device=dev())
+    want = (A.float().t() if a_mn else A.float()) @ (B.float() if b_mn else B.float().t()) + bias
+    got = o.gemm_store(A, B, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, bias=bias)
+    tol = dict(rtol=RTOL, atol=1e-4) if dtype == torch.float32 else dict(rtol=1e-3, atol=1e-3 * math.sqrt(K))
+    report(f'gemm_store {dtype} a_mn={a_mn} b_mn={b_mn}', got, want, **tol)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_gemm_qkv_epilogue(dtype):
+    o = ops()
+    torch.manual_seed(3)
+    b, n, d, h, dh = 2, 24, 64, 2, 64
+    A = _mk((b * n, d), dtype)
+    W = _mk((3 * h * dh, d), dtype, d ** -0.5)
+    ang = rotary_angle_table(9, 4, dh)
+    from dalle_pytorch_b200.attention import rotary_tables
+    cos_t, sin_t = rotary_tables(ang.to(dev()), dh)
+    q, k, v = o.gemm_qkv(A, W, b, n, h, dh, cos_t, sin_t, dh ** -0.5)
+    qkv = (A.float() @ W.float().t()).cpu().view(b, n, 3, h, dh).permute(2, 0, 3, 1, 4)
+    wq, wk, wv = (apply_rotary(ang, qkv[i]) for i in range(3))
+    tol = dict(rtol=RTOL, atol=ATOL) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    report('q', q, wq * dh ** -0.5, **tol)
+    report('k', k, wk, **tol)
+    report('v', v, wv, **tol)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_gemm_resid_geglu_epilogues(dtype):
+    o = ops()
+    torch.manual_seed(4)
+    M, d, H = 200, 64, 256
+    A = _mk((M, d), dtype)
+    W1 = _mk((2 * H, d), dtype, d ** -0.5)
+    b1 = torch.randn(2 * H, device=dev()) * 0.1
+    h, u = o.gemm_geglu(A, W1, b1)
+    uw = A.float() @ W1.float().t() + b1
+    hw = uw[:, :H] * F.gelu(uw[:, H:])
+    tol = dict(rtol=RTOL, atol=ATOL) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    report('geglu u', u, uw, **tol)
+    report('geglu h', h, hw, **tol)
+    W2 = _mk((d, H), dtype, H ** -0.5)
+    b2 = torch.randn(d, device=dev()) * 0.1
+    resid = torch.randn(M, d, device=dev())
+    scale = torch.rand(d, device=dev()) + 0.5
+    out, y = o.gemm_resid(h, W2, b2, resid, scale, sign=-1.0, keep_y=True)
+    yw = h.float() @ W2.float().t() + b2
+    report('resid y', y, yw, **tol)
+    report('resid out', out, resid - scale * yw, **tol)
+    # GEGLU backward epilogue
+    dy = _mk((M, d), dtype)
+    du = o.gemm_geglu_bwd(dy, W2, u)
+    dh = dy.float() @ W2.float()
+    uf = u.float().requires_grad_()
+    (uf[:, :H] * F.gelu(uf[:, H:])).backward(dh)
+    report('geglu_bwd du', du, uf.grad, **tol)
+
+
+# ---- attention ----------------------------------------------------------------------------------------------
+def _attn_ref(q, k, v, allow, key_mask=None):
+    s = q @ k.transpose(-1, -2)
+    s = s.masked_fill(~allow, float('-inf'))
+    if key_mask is not None:
+        s = s.masked_fill(~key_mask[:, None, None, :], float('-inf'))
+    p = s.softmax(-1)
+    return p @ v
+
+
+PATTERNS = [('full', 0), ('axial_row', 1), ('axial_col', 2), ('conv_like', 3)]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('kind,code', PATTERNS)
+@pytest.mark.parametrize('n,T,fm', [(24, 9, 4), (100, 37, 8), (191, 65, 12)])
+def test_attention_fwd_bwd_patterns(dtype, kind, code, n, T, fm):
+    o = ops()
+    torch.manual_seed(5)
+    b, h, dh = 2, 2, 64
+    q = _mk((b, h, n, dh), dtype, dh ** -0.5)
+    k = _mk((b, h, n, dh), dtype)
+    v = _mk((b, h, n, dh), dtype)
+    spec = o.AttnSpec(code, causal=True, text_len=T, fmap=fm, kernel_size=5 if kind == 'conv_like' else 0, dilation=1)
+    out, lse = o.attn_fwd(spec, q, k, v)
+    allow = allowed_mask(kind, n, n, T, fm).to(dev())
+    qr, kr, vr = (t.float().detach().requires_grad_() for t in (q, k, v))
+    want = _attn_ref(qr, kr, vr, allow)
+    tol = dict(rtol=RTOL, atol=ATOL) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    report(f'attn_fwd {kind}', out.view(b, n, h, dh).permute(0, 2, 1, 3), want, **tol)
+    g = _mk((b, n, h * dh), dtype)
+    want.backward(g.float().view(b, n, h, dh).permute(0, 2, 1, 3))
+    dqkv = o.attn_bwd(spec, q, k, v, out, lse, g, None, None, 1.0)
+    dq, dk, dv = (dqkv.view(b, n, 3, h, dh)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    tolb = dict(rtol=RTOL, atol=2e-5) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
+    report(f'attn_bwd dq {kind}', dq, qr.grad, **tolb)
+    report(f'attn_bwd dk {kind}', dk, kr.grad, **tolb)
+    report(f'attn_bwd dv {kind}', dv, vr.grad, **tolb)
+
+
+def test_attention_static_mask_noncausal_keymask_and_cache():
+    o = ops()
+    torch.manual_seed(6)
+    b, h, n, dh = 2, 2, 50, 64
+    q, k, v = (_mk((b, h, n, dh), torch.float32, 0.3) for _ in range(3))
+    # non-causal with key mask (CLIP text encoder use, dalle_pytorch.py:324)
+    km = torch.rand(b, n, device=dev()) > 0.3
+    km[:, 0] = True
+    out, _ = o.attn_fwd(o.AttnSpec(0, causal=False), q, k, v, km.to(torch.uint8))
+    want = _attn_ref(q, k, v, torch.ones(n, n, dtype=torch.bool, device=dev()), km)
+    report('noncausal+keymask', out.view(b, n, h, dh).permute(0, 2, 1, 3), want, RTOL, ATOL)
+    # static mask == axial predicate (transformer.py:333-350)
+    T, fm = 15, 6
+    n2 = T + fm * fm - 1
+    q2, k2, v2 = (_mk((b, h, n2, dh), torch.float32, 0.3) for _ in range(3))
+    import dalle_pytorch_b200 as D
+    t = D.Transformer(dim=64, depth=1, seq_len=n2, heads=2, image_fmap_size=fm)
+    sm = t._get_attention_mask('axial_col').to(dev()).to(torch.uint8).contiguous()
+    a, _ = o.attn_fwd(o.AttnSpec(4, causal=True, static_mask=sm), q2, k2, v2)
+    bb, _ = o.attn_fwd(o.AttnSpec(2, causal=True, text_len=T, fmap=fm), q2, k2, v2)
+    report('static == axial_col', a, bb, 1e-6, 1e-6)
+    # cached decoding: the last 3 queries against all keys == the tail of the full causal result
+    full, _ = o.attn_fwd(o.AttnSpec(0, causal=True), q, k, v)
+    tail, _ = o.attn_fwd(o.AttnSpec(0, causal=True), q[:, :, -3:].contiguous(), k, v)
+    report('n_q < n_k', tail, full[:, -3:], 1e-6, 1e-6)
+
+
+def test_attention_full_size_properties():
+    """C2 geometry (n=1280): rows are convex combinations (constant V -> constant out); axial == static-mask dense."""
+    o = ops()
+    torch.manual_seed(7)
+    b, h, n, dh, T, fm = 1, 2, 1280, 64, 257, 32
+    q, k = (_mk((b, h, n, dh), torch.float32, 0.2) for _ in range(2))
+    v = torch.ones(b, h, n, dh, device=dev()) * 0.75
+    for code in (0, 1, 2, 3):
+        out, lse = o.attn_fwd(o.AttnSpec(code, causal=True, text_len=T, fmap=fm, kernel_size=5, dilation=1), q, k, v)
+        assert (out - 0.75).abs().max() < 1e-5 and torch.isfinite(lse).all()
+    import dalle_pytorch_b200 as D
+    t = D.Transformer(dim=64, depth=1, seq_len=n, heads=2, image_fmap_size=fm)
+    v = _mk((b, h, n, dh), torch.float32)
+    for kind, code in (('axial_row', 1), ('axial_col', 2)):
+        sm = t._get_attention_mask(kind).to(dev()).to(torch.uint8).contiguous()
+        a, _ = o.attn_fwd(o.AttnSpec(4, causal=True, static_mask=sm), q, k, v)
+        bb, _ = o.attn_fwd(o.AttnSpec(code, causal=True, text_len=T, fmap=fm), q, k, v)
+        report(f'static == {kind} @1280', a, bb, 1e-5, 1e-6)
+
+
+# ---- glue ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_scale_bwd_colsum_cast_axpby(dtype):
+    o = ops()
+    torch.manual_seed(8)
+    M, d = 777, 64
+    g = torch.randn(M, d, device=dev())
+    y = _mk((M, d), dtype)
+    s = torch.rand(d, device=dev()) + 0.5
+    dy, ds, dbias = o.scale_bwd(g, y, s, -1.0, dtype)
+    tol = dict(rtol=RTOL, atol=1e-4) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    report('scale_bwd dy', dy, -g * s, **tol)
+    report('scale_bwd dscale', ds, (-g * y.float()).sum(0), rtol=1e-3, atol=1e-3)
+    report('scale_bwd dbias', dbias, (-g * s).sum(0), rtol=1e-3, atol=1e-3)
+    report('colsum', o.colsum(y), y.float().sum(0), rtol=1e-3, atol=1e-3)
+    a, bb = torch.randn(1000, device=dev()), torch.randn(1000, device=dev())
+    report('axpby', o.axpby(a, bb, -0.5), a - 0.5 * bb, 1e-6, 1e-6)
+    x = torch.randn(1003, device=dev())
+    assert torch.equal(o.cast_bf16(x), x.to(torch.bfloat16))

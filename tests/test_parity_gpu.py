@@ -1,0 +1,217 @@
+"""Parity of the CUDA path (through the module API -> C ABI) with the reference, on the B200.
+
+ * golden fixtures generated from the UNMODIFIED reference (tests/golden, oracle/make_golden.py): logits, loss and
+   every parameter gradient, fp32 mode, tolerance rtol 1e-3 / atol 1e-5 (BASELINE.json north_star); masked logits
+   must be exactly -fp32max;
+ * the CPU oracle on fresh seeded inputs, sub-layer by sub-layer (localises a failure);
+ * bf16 speed mode against the same goldens with a stated loose tolerance (it is the same computation).
+"""
+import pytest
+import torch
+
+from conftest import load_golden, golden_names
+from util import report
+from dalle_oracle import (OracleConfig, make_state_dict, make_inputs, dalle_forward, layer_params, attn_sublayer, ff_sublayer,
+                          rotary_angle_table, allowed_mask, transformer_forward)
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-3, 1e-5
+
+
+def _cfg(rec):
+    c = dict(rec['cfg'])
+    c['attn_types'] = tuple(c['attn_types'])
+    return OracleConfig(**c)
+
+
+def build(cfg, sd, device='cuda:0'):
+    import dalle_pytorch_b200 as D
+    vae = D.TokenVAE(image_size=8 * cfg.fmap, num_layers=3, num_tokens=cfg.num_image_tokens)
+    m = D.DALLE(dim=cfg.dim, vae=vae, num_text_tokens=cfg.num_text_tokens, text_seq_len=cfg.text_seq_len, depth=cfg.depth,
+                heads=cfg.heads, dim_head=cfg.dim_head, reversible=cfg.reversible, attn_types=cfg.attn_types, stable=cfg.stable,
+                sandwich_norm=cfg.sandwich_norm, shift_tokens=cfg.shift_tokens, loss_img_weight=cfg.loss_img_weight)
+    m.load_state_dict(sd)
+    return m.to(device)
+
+
+def run_model(rec, dtype):
+    import dalle_pytorch_b200 as D
+    cfg = _cfg(rec)
+    sd = make_state_dict(cfg, seed=rec['seed'])
+    m = build(cfg, sd)
+    m.train()
+    text, image = rec['text'].cuda(), rec['image'].cuda()
+    with D.compute_dtype_ctx(dtype):
+        loss = m(text, image, return_loss=True)
+        loss.backward()
+        with torch.no_grad():
+            logits = m(text, image)
+    grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    return loss.detach(), logits, grads
+
+
+@pytest.mark.parametrize('name', golden_names('tiny_'))
+def test_tiny_goldens_fp32(name):
+    rec = load_golden(name)
+    loss, logits, grads = run_model(rec, torch.float32)
+    report('loss', loss, rec['loss'], RTOL, ATOL)
+    lg = logits.cpu()
+    masked = rec['logits'] < -1e30
+    assert torch.equal(lg[masked], rec['logits'][masked]), 'masked logits must be exactly -fp32max'
+    report('logits', lg[~masked], rec['logits'][~masked], RTOL, ATOL)
+    assert set(grads) == set(rec['grads']), set(grads) ^ set(rec['grads'])
+    for k, g in rec['grads'].items():
+        report(f'grad {k}', grads[k], g, RTOL, ATOL)
+
+
+@pytest.mark.parametrize('name', golden_names('c1_'))
+def test_c1_goldens_fp32(name):
+    """BASELINE.json configs[0]: depth 2, dim 256, heads 4, text 64, image 8x8, batch 2."""
+    rec = load_golden(name)
+    loss, logits, grads = run_model(rec, torch.float32)
+    report('loss', loss, rec['loss'], RTOL, ATOL)
+    lg = logits.cpu()
+    samp = lg[..., ::rec['logits_stride']]
+    masked = rec['logits_sample'] < -1e30
+    assert torch.equal(samp[masked], rec['logits_sample'][masked])
+    report('logits sample', samp[~masked], rec['logits_sample'][~masked], RTOL, ATOL)
+    report('logits lse', torch.logsumexp(lg.double(), -1).float(), rec['logits_lse'], RTOL, 1e-4)
+    for k, (vals, step) in rec['grad_samples'].items():
+        mine = grads[k].reshape(-1)[::step][:vals.numel()]
+        report(f'grad {k}', mine, vals, RTOL, ATOL)
+        gn = float(grads[k].double().norm())
+        assert abs(gn - rec['grad_norms'][k]) <= 1e-3 * rec['grad_norms'][k] + 1e-7, (k, gn, rec['grad_norms'][k])
+
+
+@pytest.mark.parametrize('name', ['tiny_full', 'tiny_axial', 'tiny_axial_rev', 'tiny_cycle4', 'c1_full', 'c1_axial_rev'])
+def test_goldens_bf16_mode(name):
+    """Speed mode (bf16 storage, tensor-core GEMMs) computes the same function: loss within 2e-2, logits within
+    6e-2 absolute (bf16 has 8 mantissa bits; SURVEY.md App. C measured 1.5e-2 for a bf16 evaluation of the reference)."""
+    rec = load_golden(name)
+    loss, logits, grads = run_model(rec, torch.bfloat16)
+    report('loss', loss, rec['loss'], 2e-2, 2e-2)
+    lg = logits.cpu()
+    if 'logits' in rec:
+        want, got = rec['logits'], lg
+    else:
+        want, got = rec['logits_sample'], lg[..., ::rec['logits_stride']]
+    masked = want < -1e30
+    assert torch.equal(got[masked], want[masked])
+    report('logits', got[~masked], want[~masked], 0.0, 6e-2)
+    for k, g in grads.items():
+        assert torch.isfinite(g).all(), k
+    if 'grads' in rec:
+        for k, g in rec['grads'].items():
+            scale = float(g.abs().max())
+            report(f'grad {k}', grads[k], g, 0.0, 0.06 * scale + 1e-6)
+
+
+@pytest.mark.parametrize('kind', ['full', 'axial_row', 'axial_col', 'conv_like'])
+@pytest.mark.parametrize('reslike', ['sequential', 'separate_resid'])
+def test_sublayers_against_oracle(kind, reslike):
+    """Fused sub-layer kernels (functional.py) vs the oracle's torch-CPU sub-layer incl. all gradients (fp32)."""
+    import dalle_pytorch_b200 as D
+    from dalle_pytorch_b200 import ops
+    from dalle_pytorch_b200.functional import SublayerGeom, AttnSublayerFn, FFSublayerFn
+    from dalle_pytorch_b200.attention import rotary_tables
+    torch.manual_seed(11)
+    cfg = OracleConfig(dim=128, depth=1, heads=2, text_seq_len=20, fmap=6, num_text_tokens=50, num_image_tokens=32, attn_types=(kind,))
+    sd = make_state_dict(cfg, seed=3)
+    P = layer_params(sd, cfg, 0)
+    b, n, d = 2, cfg.seq_len, cfg.dim
+    x = torch.randn(b, n, d)
+    r = torch.randn(b, n, d)
+    ang = rotary_angle_table(cfg.text_len, cfg.fmap, 64)
+    allow = allowed_mask(kind, n, n, cfg.text_len, cfg.fmap)
+    Pr = {k: v.clone().requires_grad_() for k, v in P.items()}
+    xr, rr = x.clone().requires_grad_(), r.clone().requires_grad_()
+    if reslike == 'sequential':
+        want = xr + attn_sublayer(xr, Pr, cfg, kind, ang, allow)
+    else:
+        want = rr - attn_sublayer(xr, Pr, cfg, kind, ang, allow)
+    gout = torch.randn(b, n, d)
+    want.backward(gout)
+
+    code = {'full': 0, 'axial_row': 1, 'axial_col': 2, 'conv_like': 3}[kind]
+    spec = ops.AttnSpec(code, causal=True, text_len=cfg.text_len, fmap=cfg.fmap, kernel_size=5, dilation=1)
+    g = SublayerGeom(dtype=torch.float32, text_len=cfg.text_len, fmap=cfg.fmap, do_ln=True, do_shift=True, heads=2, dim_head=64, attn_spec=spec)
+    cos_t, sin_t = rotary_tables(ang.cuda(), 64)
+    Pg = {k: v.clone().cuda().requires_grad_() for k, v in P.items()}
+    xg, rg = x.clone().cuda().requires_grad_(), r.clone().cuda().requires_grad_()
+    if reslike == 'sequential':
+        got = AttnSublayerFn.apply(g, True, 1.0, cos_t, sin_t, None, xg, None, Pg['a_ln_w'], Pg['a_ln_b'], Pg['w_qkv'], Pg['w_out'], Pg['b_out'], Pg['a_scale'])
+    else:
+        got = AttnSublayerFn.apply(g, False, -1.0, cos_t, sin_t, None, xg, rg, Pg['a_ln_w'], Pg['a_ln_b'], Pg['w_qkv'], Pg['w_out'], Pg['b_out'], Pg['a_scale'])
+    got.backward(gout.cuda())
+    report('attn sublayer out', got, want, RTOL, ATOL)
+    report('attn dx', xg.grad, xr.grad, RTOL, ATOL)
+    if reslike != 'sequential':
+        report('attn dresid', rg.grad, rr.grad, RTOL, ATOL)
+    for k in ('a_ln_w', 'a_ln_b', 'w_qkv', 'w_out', 'b_out', 'a_scale'):
+        report(f'attn d{k}', Pg[k].grad, Pr[k].grad, RTOL, 2e-5)
+
+    # feed-forward
+    Pr = {k: v.clone().requires_grad_() for k, v in P.items()}
+    xr = x.clone().requires_grad_()
+    want = xr + ff_sublayer(xr, Pr, cfg)
+    want.backward(gout)
+    gf = SublayerGeom(dtype=torch.float32, text_len=cfg.text_len, fmap=cfg.fmap, do_ln=True, do_shift=True)
+    Pg = {k: v.clone().cuda().requires_grad_() for k, v in P.items()}
+    xg = x.clone().cuda().requires_grad_()
+    got = FFSublayerFn.apply(gf, True, 1.0, xg, None, Pg['f_ln_w'], Pg['f_ln_b'], Pg['w1'], Pg['b1'], Pg['w2'], Pg['b2'], Pg['f_scale'])
+    got.backward(gout.cuda())
+    report('ff sublayer out', got, want, RTOL, ATOL)
+    report('ff dx', xg.grad, xr.grad, RTOL, ATOL)
+    for k in ('f_ln_w', 'f_ln_b', 'w1', 'b1', 'w2', 'b2', 'f_scale'):
+        report(f'ff d{k}', Pg[k].grad, Pr[k].grad, RTOL, 2e-5)
+
+
+def test_module_api_standalone_and_cache():
+    """Attention / SparseAxialCausalAttention / FeedForward used stand-alone (reference signatures), shorter
+    sequences (n < seq_len), and KV-cache decoding == full-prefix evaluation (transformer.py:251-260)."""
+    import dalle_pytorch_b200 as D
+    from dalle_oracle import attention_core, feed_forward
+    torch.manual_seed(12)
+    dim, heads, fm, tsl = 128, 2, 4, 8
+    seq_len = tsl + fm * fm
+    T = tsl + 1
+    ang = rotary_angle_table(T, fm, 64)
+    for n in (seq_len, 19):
+        x = torch.randn(2, n, dim)
+        for axis, kind in ((0, 'axial_row'), (1, 'axial_col')):
+            m = D.SparseAxialCausalAttention(dim, seq_len, image_size=fm, axis=axis, heads=heads).cuda()
+            got = m(x.cuda(), rotary_pos_emb=ang[None].cuda())
+            want = attention_core(x, m.to_qkv.weight.cpu(), m.to_out[0].weight.cpu(), m.to_out[0].bias.cpu(), heads, ang,
+                                  allowed_mask(kind, n, n, T, fm), False)
+            report(f'SparseAxialCausalAttention axis={axis} n={n}', got, want, RTOL, ATOL)
+    m = D.Attention(dim, seq_len, causal=True, heads=heads, stable=True).cuda()
+    x = torch.randn(2, seq_len, dim)
+    got = m(x.cuda(), rotary_pos_emb=ang[None].cuda())
+    want = attention_core(x, m.to_qkv.weight.cpu(), m.to_out[0].weight.cpu(), m.to_out[0].bias.cpu(), heads, ang,
+                          allowed_mask('full', seq_len, seq_len, T, fm), True)
+    report('Attention(stable)', got, want, RTOL, ATOL)
+    ff = D.FeedForward(dim, mult=4).cuda()
+    report('FeedForward', ff(x.cuda()), feed_forward(x, ff.net[0].weight.cpu(), ff.net[0].bias.cpu(), ff.net[3].weight.cpu(), ff.net[3].bias.cpu()),
+           RTOL, ATOL)
+    # cached decoding of the optimize_for_inference model == uncached logits at every step
+    cfg = OracleConfig(dim=64, depth=2, heads=2, text_seq_len=8, fmap=4, num_text_tokens=50, num_image_tokens=32,
+                       attn_types=('axial_row', 'axial_col'))
+    sd = make_state_dict(cfg, seed=5)
+    vae = D.TokenVAE(image_size=32, num_layers=3, num_tokens=32)
+    kw = dict(dim=64, vae=vae, num_text_tokens=50, text_seq_len=8, depth=2, heads=2, attn_types=('axial_row', 'axial_col'))
+    fast = D.DALLE(optimize_for_inference=True, **kw)
+    fast.load_state_dict(sd)
+    fast = fast.cuda().eval()
+    text, image = make_inputs(cfg, 2, seed=9)
+    text, image = text.cuda(), image.cuda()
+    with torch.no_grad():
+        full = fast(text, image)                                      # [2, 24, V]
+        want_cpu = dalle_forward(text.cpu(), image.cpu(), sd, cfg)
+        report('optimize_for_inference logits', full.cpu()[want_cpu > -1e30], want_cpu[want_cpu > -1e30], RTOL, ATOL)
+        cache = {}
+        for cur in range(8, 8 + 6):
+            lg = fast(text, image[:, :cur - 8], cache=cache)
+            ref = full[:, cur] if cur < 24 else None
+            live = ref > -1e30
+            report(f'cached step {cur}', lg[:, -1][live], ref[live], RTOL, 2e-5)

@@ -1,0 +1,27 @@
+#!/usr/bin/env bash
+# One gpurun call = several bounded stages; every stage logs to gpurun_out/ so a later failure loses nothing.
+# usage: tools/gpu_stage.sh stage1 [stage2 ...]      stages: simt probe tests smoke bench bench_c3 ncu_list ncu_full
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+export PYTHONPATH="$PWD:$PWD/oracle:${PYTHONPATH:-}"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --format=csv > gpurun_out/gpu_info.txt 2>&1
+for stage in "$@"; do
+  echo "=== stage $stage $(date +%T)"
+  case "$stage" in
+    simt)   DALLE_B200_GEMM=simt timeout 900 python -m pytest tests -m gpu -q -x --no-header -p no:cacheprovider 2>&1 | tail -40 > gpurun_out/tests_simt.log; tail -15 gpurun_out/tests_simt.log ;;
+    simt_all) DALLE_B200_GEMM=simt timeout 1200 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider 2>&1 | tail -150 > gpurun_out/tests_simt.log; tail -60 gpurun_out/tests_simt.log ;;
+    probe)  timeout 900 python tools/gemm_probe.py > gpurun_out/gemm_probe.log 2>&1; cat gpurun_out/gemm_probe.log ;;
+    tests)  timeout 1200 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider 2>&1 | tail -150 > gpurun_out/tests_gpu.log; tail -60 gpurun_out/tests_gpu.log ;;
+    smoke)  timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -5 gpurun_out/smoke.log ;;
+    bench)  timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; tail -3 gpurun_out/bench_c2.err; cat gpurun_out/bench_c2.json ;;
+    bench_simt) DALLE_B200_GEMM=simt timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c2_simt.json 2> gpurun_out/bench_c2_simt.err; tail -3 gpurun_out/bench_c2_simt.err; cat gpurun_out/bench_c2_simt.json ;;
+    bench_c3) timeout 900 python bench.py --config c3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; tail -3 gpurun_out/bench_c3.err; cat gpurun_out/bench_c3.json ;;
+    bench_c4) timeout 900 python bench.py --config c4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; tail -3 gpurun_out/bench_c4.err; cat gpurun_out/bench_c4.json ;;
+    bench_ref) timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json ;;
+    ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1; tail -3 gpurun_out/ncu_list.log ;;
+    ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 40 -c 6 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log ;;
+    *) echo "unknown stage $stage" ;;
+  esac
+done
+echo "=== done $(date +%T)"
