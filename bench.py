@@ -38,6 +38,32 @@ NUM_TEXT_TOKENS, NUM_IMAGE_TOKENS = 10000, 8192
 METRIC = 'DALL-E fwd+bwd tokens/sec at seq=1280, dim=1024'
 
 
+def log(msg):
+    print(f'[bench {time.strftime("%H:%M:%S")}] {msg}', file=sys.stderr, flush=True)
+
+
+def usable_cores():
+    """Host threads this process may actually use: the affinity mask capped by the cgroup CPU quota (a container that sees
+    200 cores but is limited to 8 must not spawn 200 threads)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+        if quota != 'max':
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        try:
+            q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+            per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if q > 0:
+                n = max(1, min(n, int(q / per + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
 def workload_name(name, c):
     return (f"{name}: depth={c['depth']} dim={c['dim']} heads={c['heads']} text_seq={c['text_seq_len']} image={c['fmap']}x{c['fmap']} "
             f"attn={'+'.join(c['attn_types'])}{' reversible' if c['reversible'] else ''} batch/GPU={c['batch']}")
@@ -100,12 +126,12 @@ def cpu_step_fn(cfg_name, sample_batch=1):
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     from dalle_oracle import OracleConfig, make_state_dict, make_inputs, dalle_forward
     c = CONFIGS[cfg_name]
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     cfg = OracleConfig(dim=c['dim'], depth=c['depth'], heads=c['heads'], text_seq_len=c['text_seq_len'], fmap=c['fmap'],
                        num_text_tokens=NUM_TEXT_TOKENS, num_image_tokens=NUM_IMAGE_TOKENS, attn_types=c['attn_types'],
                        reversible=c['reversible'])
-    sd = make_state_dict(cfg, seed=0, perturb=False)
+    sd = make_state_dict(cfg, seed=0, perturb=False, fast=True)
     params = {k: v.requires_grad_(k != 'transformer.pos_emb') for k, v in sd.items()}
     text, image = make_inputs(cfg, sample_batch, seed=1, pad_tail=False)
     tokens = sample_batch * cfg.seq_len
@@ -115,9 +141,19 @@ def cpu_step_fn(cfg_name, sample_batch=1):
             p.grad = None
         loss = dalle_forward(text, image, params, cfg, return_loss=True)
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
 
     return step, tokens, cores
+
+
+def run_cpu_sample(args):
+    """`--cpu-sample`: time ONE oracle step on batch 1 and print {"value", "cores", "seconds"} (called as a subprocess with a
+    hard timeout by the GPU arm so that a slow host can never stall the bench)."""
+    step, tokens, cores = cpu_step_fn(args.config, sample_batch=1)
+    t0 = time.perf_counter()
+    step()
+    dt = time.perf_counter() - t0
+    print(json.dumps({'value': tokens / dt, 'cores': cores, 'seconds': dt, 'tokens': tokens}))
 
 
 def run_reference_arm(args):
@@ -225,9 +261,12 @@ def run_gpu_arm(args):
         return float(ms)
 
     # ---- warm-up -------------------------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    log(f'model built ({sum(p.numel() for p in model.parameters()) / 1e6:.1f} M params); warm-up')
+    for i in range(max(args.warmup, 3)):
+        t0 = time.perf_counter()
         fwd_bwd(text_d, image_d)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        log(f'warm-up step {i}: {1e3 * (time.perf_counter() - t0):.1f} ms')
 
     # ---- device-resident throughput, with per-GEMM CUDA events for the roofline ------------------------------
     sampler = ClockSampler(local_rank)
@@ -238,6 +277,7 @@ def run_gpu_arm(args):
     ms_dev = timed(lambda: fwd_bwd(text_d, image_d), args.steps)
     launches = ops.launches() - n0
     gemm_stats = ops.gemm_timing(False)
+    log(f'device-resident: {ms_dev / args.steps:.2f} ms/step')
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end: host token buffers in, loss out, every step ------------------------------------------------
@@ -249,6 +289,7 @@ def run_gpu_arm(args):
 
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    log(f'e2e: {ms_e2e / args.steps:.2f} ms/step')
 
     tokens_per_step = batch * seq * world
     value = tokens_per_step * args.steps / (ms_dev / 1e3)
@@ -272,12 +313,16 @@ def run_gpu_arm(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        step, tokens, cores = cpu_step_fn(args.config, sample_batch=1)
-        t0 = time.perf_counter()
-        step()
-        dt = time.perf_counter() - t0
-        cpu = {'value': tokens / dt, 'unit': 'tokens/s', 'cores': cores, 'kind': 'port',
-               'sample': f'1 step on batch 1 of {batch} ({tokens} tokens), full depth, fwd+bwd, fp32, oracle/dalle_oracle.py on {cores} torch threads'}
+        log('cpu_baseline: oracle on the host cores (subprocess, 420 s limit)')
+        sample = f'1 step on batch 1 of {batch} ({seq} tokens), full depth, fwd+bwd, fp32, oracle/dalle_oracle.py'
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), '--cpu-sample', '--config', args.config], capture_output=True,
+                               text=True, timeout=420, env={**os.environ, 'CUDA_VISIBLE_DEVICES': ''})
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            cpu = {'value': j['value'], 'unit': 'tokens/s', 'cores': j['cores'], 'kind': 'port',
+                   'sample': sample + f" on {j['cores']} torch threads ({j['seconds']:.1f} s)"}
+        except Exception as ex:   # timeout / parse failure: report the failure, keep the GPU numbers
+            cpu = {'value': None, 'unit': 'tokens/s', 'cores': usable_cores(), 'kind': 'port', 'sample': sample + f' — not completed: {type(ex).__name__}'}
 
     # model FLOPs per token for an MFU figure next to the kernel roofline
     d = c['dim']
@@ -311,8 +356,11 @@ def main():
     ap.add_argument('--batch', type=int, default=None)
     ap.add_argument('--dtype', default=None, choices=['fp32', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-sample', action='store_true', help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.impl == 'reference':
+    if args.cpu_sample:
+        run_cpu_sample(args)
+    elif args.impl == 'reference':
         run_reference_arm(args)
     else:
         run_gpu_arm(args)

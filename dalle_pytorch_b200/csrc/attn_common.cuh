@@ -63,6 +63,16 @@ __device__ __forceinline__ bool attn_tile_needed(const AttnGeom& g, int q0, int 
   return k1 - T >= lo;
 }
 
+// Is EVERY (i in [q0,q1], j in [k0,k1]) pair allowed (so the per-element predicate can be skipped)?  Exact `true`s only.
+__device__ __forceinline__ bool attn_tile_full(const AttnGeom& g, int q0, int q1, int k0, int k1) {
+  switch (g.pattern) {
+    case DB200_ATTN_FULL: return !g.causal || k1 <= q0;
+    case DB200_ATTN_STATIC: return false;
+    default: break;
+  }
+  return k1 < g.text_len && (q0 >= g.text_len || k1 <= q0);
+}
+
 // inverse of the interleaved-pair rotary rotation (adjoint of epi_qkv_pair): given the gradient (g0,g1) of the
 // rotated pair, returns the gradient of the unrotated pair.
 __device__ __forceinline__ void rotary_adjoint(float c, float s, float& g0, float& g1) {

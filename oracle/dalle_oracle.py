@@ -235,28 +235,29 @@ def attention_core(x, w_qkv, w_out, b_out, heads, angles, allow, stable, key_mas
 
 
 def token_shift(x, text_len, fmap):
-    """transformer.py:155-186 (training branch).  x [b,n,d], n >= text_len."""
+    """transformer.py:155-186 (training branch).  x [b,n,d], n >= text_len.
+    Restated as a per-position source-index gather (vectorised so the CPU baseline is not slowed by Python loops):
+      text token p     : channels [0,d/2)   <- token p-1            (zero at p = 0)            (:171-173)
+      image token (r,c): channels [0,d/4)   <- token (r-1,c)        (zero on the first row)    (:177-180)
+                         channels [d/4,d/2) <- token (r,c-1)        (zero on the first column)
+      remaining channels unchanged."""
     b, n, d = x.shape
     if n < text_len:                                            # transformer.py:160-161
         return x
-    out = x.clone()
     half, quarter = d // 2, d // 4
-    # text: first half of channels from the previous text token (zero at position 0) (:171-173)
-    out[:, 0, :half] = 0
-    out[:, 1:text_len, :half] = x[:, 0:text_len - 1, :half]
-    # image token q=(r,c): [0,d/4) from (r-1,c), [d/4,d/2) from (r,c-1), zero outside (:177-180)
-    for p in range(text_len, n):
-        q = p - text_len
-        r, c = q // fmap, q % fmap
-        if r > 0:
-            out[:, p, :quarter] = x[:, p - fmap, :quarter]
-        else:
-            out[:, p, :quarter] = 0
-        if c > 0:
-            out[:, p, quarter:half] = x[:, p - 1, quarter:half]
-        else:
-            out[:, p, quarter:half] = 0
-    return out
+    pos = torch.arange(n)
+    is_text = pos < text_len
+    q = (pos - text_len).clamp(min=0)
+    row, col = q // fmap, q % fmap
+    # first quarter: text <- p-1 ; image <- p-fmap
+    src_a = torch.where(is_text, pos - 1, pos - fmap)
+    ok_a = torch.where(is_text, pos > 0, row > 0)
+    # second quarter: text <- p-1 ; image <- p-1 unless first column
+    src_b = pos - 1
+    ok_b = torch.where(is_text, pos > 0, col > 0)
+    part_a = x[:, :, :quarter].index_select(1, src_a.clamp(min=0)) * ok_a.to(x.dtype)[None, :, None]
+    part_b = x[:, :, quarter:half].index_select(1, src_b.clamp(min=0)) * ok_b.to(x.dtype)[None, :, None]
+    return torch.cat([part_a, part_b, x[:, :, half:]], dim=-1)
 
 
 def feed_forward(x, w1, b1, w2, b2):
@@ -420,7 +421,7 @@ def layerscale_init(layer_index_1based: int) -> float:
     return 1e-6
 
 
-def make_state_dict(cfg: OracleConfig, seed: int = 0, dtype=torch.float32, perturb: bool = True):
+def make_state_dict(cfg: OracleConfig, seed: int = 0, dtype=torch.float32, perturb: bool = True, fast: bool = False):
     """Deterministic synthetic weights in the reference's state-dict format (App. A.8).
 
     Same distributions as the reference's default init (nn.Linear kaiming-uniform(a=sqrt 5) ->
@@ -430,10 +431,11 @@ def make_state_dict(cfg: OracleConfig, seed: int = 0, dtype=torch.float32, pertu
     perturbation so that their gradients / broadcasting are exercised by the parity tests."""
     g = torch.Generator().manual_seed(seed)
     d, inner = cfg.dim, cfg.heads * cfg.dim_head
+    gen_dtype = torch.float32 if fast else torch.float64      # fast: benchmark-sized models (values differ from the fp64 draw)
 
     def uni(shape, fan_in):
         bound = 1.0 / (fan_in ** 0.5)
-        return ((torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+        return ((torch.rand(shape, generator=g, dtype=gen_dtype) * 2 - 1) * bound).to(dtype)
 
     def ln_w():
         w = torch.ones(d, dtype=torch.float64)
@@ -448,8 +450,8 @@ def make_state_dict(cfg: OracleConfig, seed: int = 0, dtype=torch.float32, pertu
         return w.to(dtype)
 
     sd = {}
-    sd['text_emb.weight'] = torch.randn(cfg.total_text_tokens, d, generator=g, dtype=torch.float64).to(dtype)
-    sd['image_emb.weight'] = torch.randn(cfg.num_image_tokens, d, generator=g, dtype=torch.float64).to(dtype)
+    sd['text_emb.weight'] = torch.randn(cfg.total_text_tokens, d, generator=g, dtype=gen_dtype).to(dtype)
+    sd['image_emb.weight'] = torch.randn(cfg.num_image_tokens, d, generator=g, dtype=gen_dtype).to(dtype)
     sd['to_logits.0.weight'], sd['to_logits.0.bias'] = ln_w(), ln_b()
     sd['to_logits.1.weight'] = uni((cfg.total_tokens, d), d)
     sd['to_logits.1.bias'] = uni((cfg.total_tokens,), d)

@@ -107,7 +107,7 @@ def test_gemm_qkv_epilogue(dtype):
     cos_t, sin_t = rotary_tables(ang.to(dev()), dh)
     q, k, v = o.gemm_qkv(A, W, b, n, h, dh, cos_t, sin_t, dh ** -0.5)
     qkv = (A.float() @ W.float().t()).cpu().view(b, n, 3, h, dh).permute(2, 0, 3, 1, 4)
-    wq, wk, wv = (apply_rotary(ang, qkv[i]) for i in range(3))
+    wq, wk, wv = (apply_rotary(ang[:n], qkv[i]) for i in range(3))
     tol = dict(rtol=RTOL, atol=ATOL) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
     report('q', q, wq * dh ** -0.5, **tol)
     report('k', k, wk, **tol)

@@ -14,7 +14,7 @@ for stage in "$@"; do
     probe)  timeout 900 python tools/gemm_probe.py > gpurun_out/gemm_probe.log 2>&1; cat gpurun_out/gemm_probe.log ;;
     tests)  timeout 1200 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider 2>&1 | tail -150 > gpurun_out/tests_gpu.log; tail -60 gpurun_out/tests_gpu.log ;;
     smoke)  timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -5 gpurun_out/smoke.log ;;
-    bench)  timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; tail -3 gpurun_out/bench_c2.err; cat gpurun_out/bench_c2.json ;;
+    bench)  timeout 700 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; tail -12 gpurun_out/bench_c2.err; cat gpurun_out/bench_c2.json ;;
     bench_simt) DALLE_B200_GEMM=simt timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c2_simt.json 2> gpurun_out/bench_c2_simt.err; tail -3 gpurun_out/bench_c2_simt.err; cat gpurun_out/bench_c2_simt.json ;;
     bench_c3) timeout 900 python bench.py --config c3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; tail -3 gpurun_out/bench_c3.err; cat gpurun_out/bench_c3.json ;;
     bench_c4) timeout 900 python bench.py --config c4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; tail -3 gpurun_out/bench_c4.err; cat gpurun_out/bench_c4.json ;;
