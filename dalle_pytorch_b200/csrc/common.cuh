@@ -65,6 +65,30 @@ __device__ __forceinline__ float gelu_erf_grad(float g) {
   return cdf + g * pdf;
 }
 
+// GELU and its derivative from ONE exponential, for the bf16 epilogues (4 epilogue warps-per-quarter do this for every
+// element of the [M, 4d] hidden tensor, so instruction count matters): erf by Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7, far below bf16 resolution), whose exp(-x^2) term with x = g/sqrt(2) is also the Gaussian pdf.
+__device__ __forceinline__ void gelu_fast(float g, float& gelu, float& dgelu) {
+  const float x = g * 0.70710678118654752440f;
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float ex = __expf(-ax * ax);
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, ex, 1.0f);
+  const float cdf = fmaf(0.5f, copysignf(erf_abs, x), 0.5f);
+  gelu = g * cdf;
+  dgelu = fmaf(g * 0.39894228040143267794f, ex, cdf);
+}
+template <typename T> __device__ __forceinline__ void gelu_pair(float g, float& gelu, float& dgelu);
+template <> __device__ __forceinline__ void gelu_pair<float>(float g, float& gelu, float& dgelu) { gelu = gelu_erf(g); dgelu = gelu_erf_grad(g); }
+template <> __device__ __forceinline__ void gelu_pair<__nv_bfloat16>(float g, float& gelu, float& dgelu) { gelu_fast(g, gelu, dgelu); }
+template <typename T> __device__ __forceinline__ float gelu_fwd(float g);
+template <> __device__ __forceinline__ float gelu_fwd<float>(float g) { return gelu_erf(g); }
+template <> __device__ __forceinline__ float gelu_fwd<__nv_bfloat16>(float g) { float a, b; gelu_fast(g, a, b); return a; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -33,7 +33,7 @@ inline EpiArgs make_epi_args(const db200_gemm_params& p) {
 // EPI_STORE ------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void epi_store_pair(const EpiArgs& e, int m, int n, float v0, float v1) {
-  if (e.bias) { v0 += e.bias[n]; v1 += e.bias[n + 1]; }
+  if (e.bias) { const float2 bb = __ldg(reinterpret_cast<const float2*>(e.bias + n)); v0 += bb.x; v1 += bb.y; }
   const long long off = (long long)m * e.ldc + n;
   if (e.c_is_f32) store2<float>(reinterpret_cast<float*>(e.C) + off, v0, v1);
   else            store2<T>(reinterpret_cast<T*>(e.C) + off, v0, v1);
@@ -52,7 +52,7 @@ __device__ __forceinline__ void epi_qkv_pair(const EpiArgs& e, int m, int n, flo
   const int p = m - b * e.seq_n;
   if (e.cos_t) {
     const int ti = (p + e.pos_offset) * (e.dim_head >> 1) + (d >> 1);
-    const float c = e.cos_t[ti], s = e.sin_t[ti];
+    const float c = __ldg(e.cos_t + ti), s = __ldg(e.sin_t + ti);
     const float r0 = v0 * c + (-v1) * s;
     const float r1 = v1 * c + v0 * s;
     v0 = r0; v1 = r1;
@@ -66,11 +66,11 @@ __device__ __forceinline__ void epi_qkv_pair(const EpiArgs& e, int m, int n, flo
 // EPI_RESID: out = resid + sign*scale*(acc+bias) ; optionally keep y = acc+bias for the LayerScale grad ----
 template <typename T>
 __device__ __forceinline__ void epi_resid_pair(const EpiArgs& e, int m, int n, float v0, float v1) {
-  if (e.bias) { v0 += e.bias[n]; v1 += e.bias[n + 1]; }
+  if (e.bias) { const float2 bb = __ldg(reinterpret_cast<const float2*>(e.bias + n)); v0 += bb.x; v1 += bb.y; }
   const long long off = (long long)m * e.N + n;
   if (e.y_out) store2<T>(reinterpret_cast<T*>(e.y_out) + off, v0, v1);
   float s0 = e.sign, s1 = e.sign;
-  if (e.scale) { s0 *= e.scale[n]; s1 *= e.scale[n + 1]; }
+  if (e.scale) { const float2 sc = __ldg(reinterpret_cast<const float2*>(e.scale + n)); s0 *= sc.x; s1 *= sc.y; }
   float r0 = 0.f, r1 = 0.f;
   if (e.resid) { const float2 r = *reinterpret_cast<const float2*>(e.resid + off); r0 = r.x; r1 = r.y; }
   *reinterpret_cast<float2*>(e.out + off) = make_float2(r0 + s0 * v0, r1 + s1 * v1);
@@ -80,8 +80,10 @@ __device__ __forceinline__ void epi_resid_pair(const EpiArgs& e, int m, int n, f
 template <typename T>
 __device__ __forceinline__ void epi_geglu_pair(const EpiArgs& e, int m, int j, float a0, float a1, float g0, float g1) {
   if (e.bias) {
-    a0 += e.bias[j]; a1 += e.bias[j + 1];
-    g0 += e.bias[e.hidden + j]; g1 += e.bias[e.hidden + j + 1];
+    const float2 ba = __ldg(reinterpret_cast<const float2*>(e.bias + j));
+    const float2 bg = __ldg(reinterpret_cast<const float2*>(e.bias + e.hidden + j));
+    a0 += ba.x; a1 += ba.y;
+    g0 += bg.x; g1 += bg.y;
   }
   if (e.u_out) {
     T* u = reinterpret_cast<T*>(e.u_out) + (long long)m * (2 * e.hidden);
@@ -89,7 +91,7 @@ __device__ __forceinline__ void epi_geglu_pair(const EpiArgs& e, int m, int j, f
     store2<T>(u + e.hidden + j, g0, g1);
   }
   T* h = reinterpret_cast<T*>(e.h_out) + (long long)m * e.hidden;
-  store2<T>(h + j, a0 * gelu_erf(g0), a1 * gelu_erf(g1));
+  store2<T>(h + j, a0 * gelu_fwd<T>(g0), a1 * gelu_fwd<T>(g1));
 }
 
 // EPI_GEGLU_BWD: acc = dh[m, j..j+1] --------------------------------------------------------------------
@@ -99,8 +101,11 @@ __device__ __forceinline__ void epi_geglu_bwd_pair(const EpiArgs& e, int m, int 
   const float2 a = load2<T>(u + j);
   const float2 g = load2<T>(u + e.hidden + j);
   T* du = reinterpret_cast<T*>(e.du_out) + (long long)m * (2 * e.hidden);
-  store2<T>(du + j, d0 * gelu_erf(g.x), d1 * gelu_erf(g.y));
-  store2<T>(du + e.hidden + j, d0 * a.x * gelu_erf_grad(g.x), d1 * a.y * gelu_erf_grad(g.y));
+  float f0, f1, df0, df1;
+  gelu_pair<T>(g.x, f0, df0);
+  gelu_pair<T>(g.y, f1, df1);
+  store2<T>(du + j, d0 * f0, d1 * f1);
+  store2<T>(du + e.hidden + j, d0 * a.x * df0, d1 * a.y * df1);
 }
 
 template <int EPI, typename T>
@@ -208,8 +213,10 @@ __device__ __forceinline__ void epi_vec8(const EpiArgs& e, int m, int n, float* 
     Vec8<T>::load(u + e.hidden + n, g);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      da[i] = v[i] * gelu_erf(g[i]);
-      dg[i] = v[i] * a[i] * gelu_erf_grad(g[i]);
+      float f, df;
+      gelu_pair<T>(g[i], f, df);
+      da[i] = v[i] * f;
+      dg[i] = v[i] * a[i] * df;
     }
     T* du = reinterpret_cast<T*>(e.du_out) + (long long)m * (2 * e.hidden);
     Vec8<T>::store(du + n, da);
@@ -234,7 +241,7 @@ __device__ __forceinline__ void epi_geglu_vec8(const EpiArgs& e, int m, int j, f
   }
   float h[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) h[i] = a[i] * gelu_erf(g[i]);
+  for (int i = 0; i < 8; ++i) h[i] = a[i] * gelu_fwd<T>(g[i]);
   Vec8<T>::store(reinterpret_cast<T*>(e.h_out) + (long long)m * e.hidden + j, h);
 }
 

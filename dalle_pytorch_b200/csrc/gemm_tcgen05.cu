@@ -5,8 +5,9 @@
 //   warp 0      : TMA producer   (one elected lane; cp.async.bulk.tensor -> smem ring, mbarrier complete_tx)
 //   warp 1      : MMA issuer     (one elected lane; tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16;
 //                                 tcgen05.commit releases smem stages / publishes the accumulator)
-//   warps 2..5  : epilogue       (tcgen05.ld 32x32b: thread = accumulator row; fused epilogues of epilogue.cuh,
-//                                 16-byte global stores)
+//   warps 2..9  : epilogue       (tcgen05.ld 32x32b gives thread = accumulator row; each 32x32 chunk is transposed through a
+//                                 private 4 KB smem buffer so that LANES RUN ALONG N: every global load/store of the fused
+//                                 epilogues (epilogue.cuh) is then a contiguous 64-128 B row segment per half-warp)
 //
 // All three GEMM shapes of training map onto the same kernel through the operand "major" flags:
 //   forward : A K-major (activations [M,K]),  B K-major (weight [N,K])
@@ -15,109 +16,46 @@
 // (UMMA shared-memory descriptors support both majors for bf16; MN-major tiles are loaded as 64x64 boxes.)
 #include <cuda.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "common.cuh"
 #include "epilogue.cuh"
+#include "tc_common.cuh"
 
 namespace db200 {
+
+using namespace tc;
 
 namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;          // 2 + 8 warps
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;   // per epilogue warp
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr int BOX_MN_BYTES = 64 * BLOCK_K * 2;         // one 64(mn) x 64(k) MN-major box = 8 KB
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 193 * 1024;   // operand ring; + 32 KB epilogue staging + barriers stays under 227 KB
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-// ---- mbarrier ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// A pipeline bug must surface as a launch failure, never as a hung GPU: trap after ~2 s of spinning.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("dalle_b200 gemm_tcgen05: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
-             parity);
-      __trap();
-    }
+// 32x32 fp32 chunk: in[] = 32 consecutive columns of this lane's row  ->  out[2*it], out[2*it+1] = columns
+// 2*(lane&15), +1 of row 2*it + (lane>>4).  Private per-warp buffer, float4 slots XOR-swizzled by the row.
+__device__ __forceinline__ void transpose_chunk(const uint32_t* in, float* out, float* stage, int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(in[4 * j], in[4 * j + 1], in[4 * j + 2], in[4 * j + 3]);
+  __syncwarp();
+  const int j = (lane & 15) >> 1, sub = (lane & 1) << 1;
+#pragma unroll
+  for (int it = 0; it < 16; ++it) {
+    const int rr = 2 * it + (lane >> 4);
+    const float2 v = *reinterpret_cast<const float2*>(stage + rr * 32 + ((j ^ (rr & 7)) << 2) + sub);
+    out[2 * it] = v.x;
+    out[2 * it + 1] = v.y;
   }
-}
-
-// ---- TMA ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-// ---- tcgen05 ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory matrix descriptor (SWIZZLE_128B, sm_100 "version 1"):
-//   bits [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
-//   bits [46,48) = 1 | [61,64) layout type (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
 }
 
 template <int BLOCK_N>
@@ -126,10 +64,12 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual 1 KB alignment slack
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = EPI_OFFSET + NUM_EPI_WARPS * EPI_STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + BAR_BYTES + 1024;   // +1024: manual 1 KB alignment slack
 };
 
-template <int BLOCK_N, int EPI, bool A_MN, bool B_MN>
+template <int BLOCK_N, int EPI, bool A_MN, bool B_MN, bool EPI_COLS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, EpiArgs e) {
   using L = SmemLayout<BLOCK_N>;
@@ -143,7 +83,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   const uint32_t full_bar = smem_u32(bars);                    // [STAGES]
   const uint32_t empty_bar = smem_u32(bars + STAGES);          // [STAGES]
   const uint32_t tfull_bar = smem_u32(bars + 2 * STAGES);      // [2]
@@ -156,7 +96,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, NUM_EPI_WARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -244,54 +184,111 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     __syncwarp();
   } else {
-    // ================================ epilogue (warps 2..5) ================================
+    // ================================ epilogue (warps 2..9) ================================
+    const int ew = warp - 2;
     const int quarter = warp & 3;                            // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;
+    const int half = ew >> 2;                                // which half of the tile's columns
+    float* stage = reinterpret_cast<float*>(smem + L::EPI_OFFSET + ew * EPI_STAGE_BYTES);
+    const int lrow = lane >> 4, lcol = (lane & 15) << 1;
     int as = 0; uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile % num_m) * BLOCK_M;
       const int n0 = (tile / num_m) * BLOCK_N;
-      const int m = m0 + row;
+      const int mbase = m0 + quarter * 32 + lrow;            // + 2*it
       mbar_wait(tfull_bar + 8 * as, aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
-      if constexpr (EPI == DB200_EPI_GEGLU) {
-#pragma unroll 1
-        for (int ch = 0; ch < 128 / 32; ++ch) {
-          uint32_t ra[32], rg[32];
-          tmem_ld32(taddr + ch * 32, ra);
-          tmem_ld32(taddr + 128 + ch * 32, rg);
-          tmem_ld_wait();
-          const int j0 = (n0 >> 1) + ch * 32;
-          if (m < M) {
+      if constexpr (!EPI_COLS) {
+        // ---- row mode: thread = accumulator row, 8-column (16-byte) granules straight from registers ----
+        const int m = m0 + quarter * 32 + lane;
+        if constexpr (EPI == DB200_EPI_GEGLU) {
+          uint32_t ra[2][32], rg[2][32];
+          tmem_ld32(taddr + half * 64, ra[0]);
+          tmem_ld32(taddr + 128 + half * 64, rg[0]);
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              const int j = j0 + o * 8;
-              if (j < e.hidden) {
-                float a[8], g[8];
+          for (int ch = 0; ch < 2; ++ch) {
+            tmem_ld_wait();
+            if (ch + 1 < 2) {
+              tmem_ld32(taddr + half * 64 + 32, ra[1]);
+              tmem_ld32(taddr + 128 + half * 64 + 32, rg[1]);
+            }
+            const int j0 = (n0 >> 1) + half * 64 + ch * 32;
+            if (m < M) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(ra[o * 8 + i]); g[i] = __uint_as_float(rg[o * 8 + i]); }
-                epi_geglu_vec8<__nv_bfloat16>(e, m, j, a, g);
+              for (int o = 0; o < 4; ++o) {
+                const int j = j0 + o * 8;
+                if (j < e.hidden) {
+                  float a[8], g[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(ra[ch][o * 8 + i]); g[i] = __uint_as_float(rg[ch][o * 8 + i]); }
+                  epi_geglu_vec8<__nv_bfloat16>(e, m, j, a, g);
+                }
+              }
+            }
+          }
+        } else {
+          constexpr int NCH = (BLOCK_N / 2) / 32;
+          uint32_t r[2][32];
+          tmem_ld32(taddr + half * (BLOCK_N / 2), r[0]);
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            tmem_ld_wait();
+            if (ch + 1 < NCH) tmem_ld32(taddr + half * (BLOCK_N / 2) + (ch + 1) * 32, r[(ch + 1) & 1]);
+            if (m < M) {
+#pragma unroll
+              for (int o = 0; o < 4; ++o) {
+                const int n = n0 + half * (BLOCK_N / 2) + ch * 32 + o * 8;
+                if (n < N) {
+                  float v[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[ch & 1][o * 8 + i]);
+                  epi_vec8<EPI, __nv_bfloat16>(e, m, n, v);
+                }
               }
             }
           }
         }
-      } else {
-#pragma unroll 1
-        for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
-          uint32_t r[32];
-          tmem_ld32(taddr + ch * 32, r);
+      } else
+      if constexpr (EPI == DB200_EPI_GEGLU) {
+        // a = columns [0,128), g = columns [128,256) of the accumulator; this warp pairs a/g of hidden [half*64, +64)
+        uint32_t ra[2][32], rg[2][32];
+        tmem_ld32(taddr + half * 64, ra[0]);
+        tmem_ld32(taddr + 128 + half * 64, rg[0]);
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
           tmem_ld_wait();
-          if (m < M) {
+          if (ch + 1 < 2) {
+            tmem_ld32(taddr + half * 64 + 32, ra[1]);
+            tmem_ld32(taddr + 128 + half * 64 + 32, rg[1]);
+          }
+          float ta[32], tg[32];
+          transpose_chunk(ra[ch], ta, stage, lane);
+          transpose_chunk(rg[ch], tg, stage, lane);
+          const int j = (n0 >> 1) + half * 64 + ch * 32 + lcol;
+          if (j < e.hidden) {
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              const int n = n0 + ch * 32 + o * 8;
-              if (n < N) {
-                float v[8];
+            for (int it = 0; it < 16; ++it) {
+              const int m = mbase + 2 * it;
+              if (m < M) epi_geglu_pair<__nv_bfloat16>(e, m, j, ta[2 * it], ta[2 * it + 1], tg[2 * it], tg[2 * it + 1]);
+            }
+          }
+        }
+      } else {
+        constexpr int NCH = (BLOCK_N / 2) / 32;
+        uint32_t r[2][32];
+        tmem_ld32(taddr + half * (BLOCK_N / 2), r[0]);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[o * 8 + i]);
-                epi_vec8<EPI, __nv_bfloat16>(e, m, n, v);
-              }
+        for (int ch = 0; ch < NCH; ++ch) {
+          tmem_ld_wait();
+          if (ch + 1 < NCH) tmem_ld32(taddr + half * (BLOCK_N / 2) + (ch + 1) * 32, r[(ch + 1) & 1]);
+          float t[32];
+          transpose_chunk(r[ch & 1], t, stage, lane);
+          const int n = n0 + half * (BLOCK_N / 2) + ch * 32 + lcol;
+          if (n < N) {
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+              const int m = mbase + 2 * it;
+              if (m < M) epi_pair<EPI, __nv_bfloat16>(e, m, n, t[2 * it], t[2 * it + 1]);
             }
           }
         }
@@ -310,51 +307,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-// ---- host side ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-// 2-D bf16 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, outer stride `ld` elements
-int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return set_error(DB200_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t gdim[2] = {inner, outer};
-  cuuint64_t gstride[1] = {ld * 2};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_error(DB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu)", (int)r,
-                                          (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
-  return DB200_OK;
-}
-
-template <int BLOCK_N, int EPI, bool A_MN, bool B_MN>
-int launch_cfg(const db200_gemm_params& p, cudaStream_t st) {
+template <int BLOCK_N, int EPI, bool A_MN, bool B_MN, bool EPI_COLS>
+int launch_cfg_mode(const db200_gemm_params& p, cudaStream_t st) {
   using L = SmemLayout<BLOCK_N>;
   CUtensorMap tmA, tmB;
   int rc;
-  if (!A_MN) rc = make_map(&tmA, p.A, p.K, p.M, p.lda, BLOCK_K, BLOCK_M);
-  else rc = make_map(&tmA, p.A, p.M, p.K, p.lda, 64, BLOCK_K);
+  if (!A_MN) rc = make_tensor_map_bf16(&tmA, p.A, p.K, p.M, p.lda, BLOCK_K, BLOCK_M);
+  else rc = make_tensor_map_bf16(&tmA, p.A, p.M, p.K, p.lda, 64, BLOCK_K);
   if (rc) return rc;
-  if (!B_MN) rc = make_map(&tmB, p.B, p.K, p.N, p.ldb, BLOCK_K, 128);
-  else rc = make_map(&tmB, p.B, p.N, p.K, p.ldb, 64, BLOCK_K);
+  if (!B_MN) rc = make_tensor_map_bf16(&tmB, p.B, p.K, p.N, p.ldb, BLOCK_K, 128);
+  else rc = make_tensor_map_bf16(&tmB, p.B, p.N, p.K, p.ldb, 64, BLOCK_K);
   if (rc) return rc;
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI, A_MN, B_MN, EPI_COLS>;
   static bool attr_done = false;
   if (!attr_done) {
     DB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -366,6 +330,26 @@ int launch_cfg(const db200_gemm_params& p, cudaStream_t st) {
   kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(tmA, tmB, p.M, p.N, p.K, e);
   DB200_LAUNCH_OK("gemm_tcgen05_kernel");
   return DB200_OK;
+}
+
+// Epilogue mode: "rows" (thread = accumulator row, 16-byte granules) or "cols" (32x32 chunks transposed through smem so
+// lanes run along N).  Measured on B200 (profiles/): cols wins only for the GEGLU forward epilogue; DALLE_B200_EPI=rows|cols
+// forces one mode for A/B timing.
+inline int epi_mode_env() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* v = getenv("DALLE_B200_EPI");
+    mode = (v && !strcmp(v, "rows")) ? 1 : (v && !strcmp(v, "cols")) ? 2 : 0;
+  }
+  return mode;
+}
+
+template <int BLOCK_N, int EPI, bool A_MN, bool B_MN>
+int launch_cfg(const db200_gemm_params& p, cudaStream_t st) {
+  const int env = epi_mode_env();
+  const bool cols = env == 2 || (env == 0 && EPI == DB200_EPI_GEGLU);
+  if (cols) return launch_cfg_mode<BLOCK_N, EPI, A_MN, B_MN, true>(p, st);
+  return launch_cfg_mode<BLOCK_N, EPI, A_MN, B_MN, false>(p, st);
 }
 
 template <int EPI, bool A_MN, bool B_MN>
@@ -396,6 +380,49 @@ bool device_is_sm100() {
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
+
+namespace {
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, outer stride `ld` elements
+int make_tensor_map_bf16_impl(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(DB200_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(DB200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu)", (int)r,
+                                          (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+  return DB200_OK;
+}
+
+}  // namespace
+
+namespace tc {
+int make_tensor_map_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                         uint32_t box_outer) {
+  return make_tensor_map_bf16_impl(map, base, inner, outer, ld, box_inner, box_outer);
+}
+}  // namespace tc
 
 bool gemm_tcgen05_supported(const db200_gemm_params& p, const char** why) {
   const char* w = nullptr;

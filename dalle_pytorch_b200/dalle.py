@@ -243,6 +243,10 @@ class DALLE(nn.Module):
         if self.stable:
             out = self.norm_by_max(out)
 
+        if return_loss:
+            assert exists(image), 'when training, image must be supplied'
+            return self._loss_head(out, text, image, seq_len)
+
         logits = self.to_logits(out)
 
         logits_mask = self.logits_mask[:, :seq_len]
@@ -253,14 +257,24 @@ class DALLE(nn.Module):
 
         if exists(cache):
             cache['offset'] = cache.get('offset', 0) + logits.shape[1]
+        return logits
 
-        if not return_loss:
-            return logits
-
-        assert exists(image), 'when training, image must be supplied'
-        offsetted_image = image + self.num_text_tokens
-        labels = torch.cat((text[:, 1:], offsetted_image), dim=1)
-        logits = logits.transpose(1, 2)
-        loss_text = F.cross_entropy(logits[:, :, :self.text_seq_len], labels[:, :self.text_seq_len])
-        loss_img = F.cross_entropy(logits[:, :, self.text_seq_len:], labels[:, self.text_seq_len:])
+    def _loss_head(self, out, text, image, seq_len):
+        """Logits head + weighted cross-entropy of dalle_pytorch.py:644-671 without materialising the masked
+        [b, n, total_tokens] logits: the logits mask (dalle_pytorch.py:441-455) fills every image-vocabulary logit of a text
+        position (and vice versa) with -fp32max, whose softmax weight is exactly 0, so the text loss only needs the
+        text-vocabulary columns at the text positions and the image loss only the image-vocabulary columns at the image
+        positions — the same numbers with 2.1x fewer head FLOPs and no [b, c, n] transposed softmax."""
+        ln, lin = self.to_logits[0], self.to_logits[1]
+        T, ntt = self.text_seq_len, self.num_text_tokens
+        h = ln(out)
+        labels_text = text[:, 1:]                                  # text already carries <bos> at index 0
+        d = h.shape[-1]
+        h_text = h[:, :T].reshape(-1, d)
+        logits_text = F.linear(h_text, lin.weight[:ntt], lin.bias[:ntt])
+        loss_text = F.cross_entropy(logits_text.float(), labels_text[:, :T].reshape(-1))
+        n_img = seq_len - T
+        h_img = h[:, T:seq_len].reshape(-1, d)
+        logits_img = F.linear(h_img, lin.weight[ntt:], lin.bias[ntt:])
+        loss_img = F.cross_entropy(logits_img.float(), image[:, :n_img].reshape(-1))
         return (loss_text + self.loss_img_weight * loss_img) / (self.loss_img_weight + 1)

@@ -16,6 +16,9 @@ for stage in "$@"; do
     smoke)  timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -5 gpurun_out/smoke.log ;;
     bench)  timeout 700 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; tail -12 gpurun_out/bench_c2.err; cat gpurun_out/bench_c2.json ;;
     bench_simt) DALLE_B200_GEMM=simt timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c2_simt.json 2> gpurun_out/bench_c2_simt.err; tail -3 gpurun_out/bench_c2_simt.err; cat gpurun_out/bench_c2_simt.json ;;
+    bench_rows) DALLE_B200_EPI=rows timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c2_rows.json 2> gpurun_out/bench_c2_rows.err; tail -3 gpurun_out/bench_c2_rows.err ;;
+    bench_cols) DALLE_B200_EPI=cols timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c2_cols.json 2> gpurun_out/bench_c2_cols.err; tail -3 gpurun_out/bench_c2_cols.err ;;
+    bench_auto) timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c2_auto.json 2> gpurun_out/bench_c2_auto.err; tail -3 gpurun_out/bench_c2_auto.err ;;
     bench_c3) timeout 900 python bench.py --config c3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; tail -3 gpurun_out/bench_c3.err; cat gpurun_out/bench_c3.json ;;
     bench_c4) timeout 900 python bench.py --config c4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; tail -3 gpurun_out/bench_c4.err; cat gpurun_out/bench_c4.json ;;
     bench_ref) timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json ;;
