@@ -50,6 +50,9 @@ int attn_bwd_simt_launch(const db200_attn_bwd_params& p, cudaStream_t st);
 bool attn_mma_supported(const db200_attn_fwd_params& p);
 int attn_fwd_mma_launch(const db200_attn_fwd_params& p, cudaStream_t st);
 int attn_bwd_mma_launch(const db200_attn_bwd_params& p, cudaStream_t st);
+bool attn_tc_supported(const db200_attn_fwd_params& p);
+int attn_fwd_tc_launch(const db200_attn_fwd_params& p, cudaStream_t st);
+int attn_bwd_tc_launch(const db200_attn_bwd_params& p, cudaStream_t st);
 
 static bool dtype_ok(int d) { return d == DB200_F32 || d == DB200_BF16; }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -168,6 +171,16 @@ int dalle_b200_gemm_select(const db200_gemm_params* p) {
   return gemm_tcgen05_supported(*p, &why) ? DB200_GEMM_TCGEN05 : DB200_GEMM_SIMT;
 }
 
+// 0 = CUDA-core fp32 arithmetic, 1 = mma.sync bf16, 2 = tcgen05 bf16
+static int attn_backend(const db200_attn_fwd_params& f) {
+  const char* v = getenv("DALLE_B200_ATTN");
+  int want = 2;                                   // tcgen05 kernels (attn_tc.cu) whenever the problem qualifies
+  if (v) want = !strcmp(v, "simt") ? 0 : !strcmp(v, "tc") ? 2 : 1;
+  if (want == 2 && !attn_tc_supported(f)) want = 1;
+  if (want == 1 && !attn_mma_supported(f)) want = 0;
+  return want;
+}
+
 static int check_attn(const db200_attn_fwd_params& f, const char* who) {
   DB200_CHECK_ARG(f.batch >= 0 && f.heads > 0 && f.n_q >= 0 && f.n_k >= f.n_q, "%s: bad shape", who);
   if (f.dim_head != 64) return set_error(DB200_ERR_UNSUPPORTED, "%s: dim_head=%d, kernels are specialised for 64", who, f.dim_head);
@@ -186,8 +199,10 @@ int dalle_b200_attn_fwd(const db200_attn_fwd_params* p, void* stream) {
   const int rc = check_attn(*p, "attn_fwd");
   if (rc) return rc;
   if (p->batch == 0 || p->n_q == 0) return DB200_OK;
-  const int env = env_choice("DALLE_B200_ATTN", "simt", "mma");
-  if (env != 1 && attn_mma_supported(*p)) return attn_fwd_mma_launch(*p, (cudaStream_t)stream);
+  // DALLE_B200_ATTN = simt | mma | tc   (default: see attn_default_backend)
+  const int be = attn_backend(*p);
+  if (be == 2) return attn_fwd_tc_launch(*p, (cudaStream_t)stream);
+  if (be == 1) return attn_fwd_mma_launch(*p, (cudaStream_t)stream);
   return attn_fwd_simt_launch(*p, (cudaStream_t)stream);
 }
 
@@ -199,8 +214,9 @@ int dalle_b200_attn_bwd(const db200_attn_bwd_params* p, void* stream) {
   DB200_CHECK_ARG(p->d_out && p->delta && p->dqkv, "attn_bwd: null tensor");
   DB200_CHECK_ARG((p->cos_t == nullptr) == (p->sin_t == nullptr), "attn_bwd: cos/sin tables must come together");
   if (p->f.batch == 0 || p->f.n_q == 0) return DB200_OK;
-  const int env = env_choice("DALLE_B200_ATTN", "simt", "mma");
-  if (env != 1 && attn_mma_supported(p->f)) return attn_bwd_mma_launch(*p, (cudaStream_t)stream);
+  const int be = attn_backend(p->f);
+  if (be == 2) return attn_bwd_tc_launch(*p, (cudaStream_t)stream);
+  if (be == 1) return attn_bwd_mma_launch(*p, (cudaStream_t)stream);
   return attn_bwd_simt_launch(*p, (cudaStream_t)stream);
 }
 

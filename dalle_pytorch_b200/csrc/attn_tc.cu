@@ -1,0 +1,734 @@
+// Fused attention on the 5th-generation tensor cores (tcgen05.mma, accumulators and P in tensor memory), for every
+// sparsity pattern of the reference.  bf16 operands, fp32 accumulation / softmax statistics.
+//
+// One CTA = 128 queries of one (batch, head); 128-key tiles stream through a 2-stage TMA ring.
+//   warp 0     : TMA producer (Q once; K/V tiles)
+//   warp 1     : MMA issuer   S = Q K^T          (SS: both operands in 128B-swizzled smem, D in TMEM cols [0,128))
+//                             O += P V           (TS: A = P read from TMEM, B = V tile read N-major from the same smem image)
+//   warps 2..5 : softmax      thread = query row (tcgen05.ld 32x32b): row max / sum need no shuffles; P is written back to
+//                             TMEM as packed bf16 (tcgen05.st) and O is rescaled in TMEM only when the running max moved by
+//                             more than 2^8 (lazy rescale); final O / l and the log-sum-exp are written by the same threads.
+// Two CTAs fit per SM (80 KB smem, 256 TMEM columns each), so one CTA's softmax overlaps the other's MMAs.
+//
+// Backward: delta = rowsum(dO*O), then a dK/dV kernel (CTA = 128 keys, loops over query tiles, works on the transposed
+// score tile so that thread = key row) and a dQ kernel (CTA = 128 queries, loops over key tiles); both recompute P from
+// the saved log-sum-exp, keep P / dS in TMEM as the A operand of the second-stage MMAs, and fold the rotary adjoint and
+// the q scale into their final stores (which write the [rows, 3*h*64] gradient of the to_qkv output directly).
+#include <cstdlib>
+#include <cstring>
+
+#include "attn_common.cuh"
+#include "tc_common.cuh"
+
+namespace db200 {
+
+using namespace tc;
+
+namespace {
+
+constexpr int TQ = 128, TK = 128, DH = 64;
+constexpr int TILE_BYTES = 128 * DH * 2;     // one [128 x 64] bf16 tile = 16 KB
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float RESCALE_TAU = 8.0f / LOG2E;  // lazy rescale threshold (raw score units): exponentials stay <= 2^8
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+struct FwdArgs {
+  bf16* out; float* lse; const uint8_t* key_mask; int heads, batch;
+};
+
+// smem map (after 1 KB alignment): Q | K0 | K1 | V0 | V1 | [P (SS mode only, 32 KB)] | barriers
+template <bool P_TMEM>
+struct FwdSmem {
+  static constexpr int Q_OFF = 0;
+  static constexpr int K_OFF = TILE_BYTES;
+  static constexpr int V_OFF = 3 * TILE_BYTES;
+  static constexpr int P_OFF = 5 * TILE_BYTES;
+  static constexpr int BAR_OFF = P_OFF + (P_TMEM ? 0 : 2 * TILE_BYTES);
+  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+};
+
+template <bool P_TMEM>
+__global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                          const __grid_constant__ CUtensorMap tmV, FwdArgs P, AttnGeom g) {
+  using L = FwdSmem<P_TMEM>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const uint32_t sQ = smem_u32(smem + L::Q_OFF);
+  const uint32_t sK = smem_u32(smem + L::K_OFF), sV = smem_u32(smem + L::V_OFF), sP = smem_u32(smem + L::P_OFF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  const uint32_t q_full = smem_u32(bars), kv_full = smem_u32(bars + 1), kv_empty = smem_u32(bars + 3);
+  const uint32_t s_full = smem_u32(bars + 5), p_ready = smem_u32(bars + 6), o_done = smem_u32(bars + 7);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  constexpr uint32_t TMEM_COLS = 256;          // S [0,128) | O [128,192) | P [192,256)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, b = bh / P.heads, h = bh - b * P.heads;
+  const int q0 = blockIdx.x * TQ;
+  const int off = g.n_k - g.n_q;
+  const int q_last = min(q0 + TQ, g.n_q) - 1;
+  const int nkt = (g.n_k + TK - 1) / TK;
+  auto needed = [&](int kt) { return attn_tile_needed(g, q0 + off, q_last + off, kt * TK, min(kt * TK + TK, g.n_k) - 1); };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
+    mbar_init(s_full, 1); mbar_init(p_ready, 128); mbar_init(o_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tO = tmem + 128, tP = tmem + 192;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_2d(sQ, &tmQ, q_full, 0, bh * g.n_q + q0);
+      int it = 0;
+      for (int kt = 0; kt < nkt; ++kt) {
+        if (!needed(kt)) continue;
+        const int s = it & 1;
+        mbar_wait(kv_empty + 8 * s, ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(kv_full + 8 * s, 2 * TILE_BYTES);
+        tma_load_2d(sK + s * TILE_BYTES, &tmK, kv_full + 8 * s, 0, bh * g.n_k + kt * TK);
+        tma_load_2d(sV + s * TILE_BYTES, &tmV, kv_full + 8 * s, 0, bh * g.n_k + kt * TK);
+        ++it;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128, false, false);   // S = Q K^T : both K-major
+      constexpr uint32_t IDESC_O = make_idesc_bf16(128, 64, false, true);     // O = P V   : A K-major (TMEM / smem), B N-major
+      mbar_wait(q_full, 0);
+      const uint64_t dq = make_smem_desc(sQ, 16, 1024);
+      int it = 0;
+      for (int kt = 0; kt < nkt; ++kt) {
+        if (!needed(kt)) continue;
+        const int s = it & 1;
+        mbar_wait(kv_full + 8 * s, (it >> 1) & 1);
+        tc_fence_after();
+        const uint64_t dk = make_smem_desc(sK + s * TILE_BYTES, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
+        umma_commit(s_full);
+        mbar_wait(p_ready, it & 1);
+        tc_fence_after();
+        // V tile image [128 keys][64 dh] read as the N-major B operand: K = keys (16 rows = 2048 B per step), N = dh
+        const uint64_t dv = make_smem_desc(sV + s * TILE_BYTES, TILE_BYTES, 1024);
+#pragma unroll
+        for (int k = 0; k < TK / 16; ++k) {
+          if constexpr (P_TMEM) {
+            umma_bf16_ts(tO, tP + 8 * k, dv + 128 * k, IDESC_O, (it | k) != 0);
+          } else {
+            const uint64_t dp = make_smem_desc(sP + (k >> 2) * TILE_BYTES, 16, 1024);
+            umma_bf16(tO, dp + 2 * (k & 3), dv + 128 * k, IDESC_O, (it | k) != 0);
+          }
+        }
+        umma_commit(kv_empty + 8 * s);
+        umma_commit(o_done);
+        ++it;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================== softmax / epilogue =====================================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int qi = q0 + row;                       // query index within [0, n_q)
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint8_t* km = P.key_mask ? P.key_mask + (long long)b * g.n_k : nullptr;
+    float m_run = -1.0e30f, l_run = 0.f;
+    int it = 0;
+    for (int kt = 0; kt < nkt; ++kt) {
+      if (!needed(kt)) continue;
+      const int k0 = kt * TK, k1 = min(k0 + TK, g.n_k) - 1;
+      const bool full = (k1 - k0 == TK - 1) && km == nullptr && attn_tile_full(g, q0 + off, q_last + off, k0, k1);
+      auto masked = [&](int kj) {
+        bool ok = (qi < g.n_q) && (kj < g.n_k) && attn_allowed(g, qi + off, kj);
+        if (ok && km) ok = km[kj] != 0;
+        return !ok;
+      };
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      // ---- pass 1: row max ----
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tS + lane_off + c * 32, r);
+        tmem_ld_wait();
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (!masked(k0 + c * 32 + i)) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+      }
+      const float m_new = (mx > m_run + RESCALE_TAU) ? mx : m_run;
+      const float corr = exp2f((m_run - m_new) * LOG2E);
+      const float mb = m_new * LOG2E;
+      if (it > 0) {                                  // PV of the previous tile must be done: P buffer free, O final
+        mbar_wait(o_done, (it - 1) & 1);
+        tc_fence_after();
+      }
+      // ---- pass 2: P = exp2(S*log2e - m*log2e), row sum, P -> TMEM (or smem) as bf16 ----
+      float rs = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tS + lane_off + c * 32, r);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = exp2f(fmaf(__uint_as_float(r[2 * i]), LOG2E, -mb));
+          float p1 = exp2f(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, -mb));
+          if (!full) {
+            if (masked(k0 + c * 32 + 2 * i)) p0 = 0.f;
+            if (masked(k0 + c * 32 + 2 * i + 1)) p1 = 0.f;
+          }
+          rs += p0 + p1;
+          pk[i] = pack2(p0, p1);
+        }
+        if constexpr (P_TMEM) {
+          tmem_st16(tP + lane_off + c * 16, pk);
+        } else {
+          // K-major [128 rows][128 keys] as two 128B-swizzled [128 x 64] tiles; this thread owns row `row`
+          uint8_t* prow = smem + L::P_OFF + (c >> 1) * TILE_BYTES + row * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = (c & 1) * 4 + j;
+            *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+        }
+      }
+      l_run = l_run * corr + rs;
+      m_run = m_new;
+      // ---- lazy rescale of O (warp-uniform decision: tcgen05.ld/st are warp-collective) ----
+      if (it > 0 && __any_sync(0xffffffffu, corr != 1.0f)) {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tO + lane_off + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+          tmem_st32(tO + lane_off + c * 32, r);
+        }
+      }
+      if constexpr (P_TMEM) tmem_st_wait(); else { tmem_st_wait(); fence_proxy_async(); }
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      ++it;
+    }
+    // ---- epilogue: O / l -> out[b, qi, h*64 ..] (bf16), lse ----
+    const int inner = P.heads * DH;
+    if (it > 0) {
+      mbar_wait(o_done, (it - 1) & 1);
+      tc_fence_after();
+    }
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      if (it > 0) { tmem_ld32(tO + lane_off + c * 32, r); tmem_ld_wait(); }
+      else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      if (qi < g.n_q) {
+        bf16* orow = P.out + ((long long)b * g.n_q + qi) * inner + h * DH + c * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack2(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+          u.y = pack2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+          u.z = pack2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+          u.w = pack2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + 8 * j) = u;
+        }
+      }
+    }
+    if (qi < g.n_q) P.lse[(long long)bh * g.n_q + qi] = l_run > 0.f ? m_run + logf(l_run) : 0.f;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+
+// =============================================== backward ====================================================
+__global__ void attn_delta_tc_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ delta, int batch, int heads,
+                                     int n) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int total = batch * heads * n;
+  if (warp >= total) return;
+  const int i = warp % n, bh = warp / n, h = bh % heads, b = bh / heads;
+  const long long off = ((long long)b * n + i) * heads * DH + h * DH + lane * 2;
+  const float2 o = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(O + off));
+  const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dO + off));
+  const float s = warp_sum(o.x * d.x + o.y * d.y);
+  if (lane == 0) delta[(long long)bh * n + i] = s;
+}
+
+struct BwdArgs {
+  const float* lse; const float* delta; const uint8_t* key_mask; const float* cos_t; const float* sin_t; float q_scale;
+  bf16* dqkv; int heads, batch;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// 64 fp32 accumulator columns of this thread's row -> (rotary adjoint, optional scale) -> bf16 -> dst[0..63]
+__device__ __forceinline__ void store_grad_row(uint32_t taddr, bf16* dst, const float* cos_row, const float* sin_row, float scale, bool valid) {
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+    tmem_ld_wait();
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]) * scale;
+        if (cos_row) {
+          const int pi = (c * 32 + j * 8) >> 1;                      // pair index of the first pair of this granule
+          const float4 cc = *reinterpret_cast<const float4*>(cos_row + pi);
+          const float4 ss = *reinterpret_cast<const float4*>(sin_row + pi);
+          rotary_adjoint(cc.x, ss.x, v[0], v[1]); rotary_adjoint(cc.y, ss.y, v[2], v[3]);
+          rotary_adjoint(cc.z, ss.z, v[4], v[5]); rotary_adjoint(cc.w, ss.w, v[6], v[7]);
+        }
+        uint4 u;
+        u.x = pack2(v[0], v[1]); u.y = pack2(v[2], v[3]); u.z = pack2(v[4], v[5]); u.w = pack2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(dst + c * 32 + j * 8) = u;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dK, dV : CTA = 128 keys; transposed score tile (rows = keys, columns = queries) so that thread = key row.
+//   TMEM: S^T [0,128) | dP^T [128,256) | dV [256,320) | dK [320,384) | P^T bf16 [384,448) | dS^T bf16 [448,512)
+// ---------------------------------------------------------------------------------------------------------------
+struct DkvSmem {
+  static constexpr int K_OFF = 0, V_OFF = TILE_BYTES, Q_OFF = 2 * TILE_BYTES, DO_OFF = 4 * TILE_BYTES;
+  static constexpr int STAT_OFF = 6 * TILE_BYTES;                 // lse*log2e [2][128], delta [2][128]
+  static constexpr int BAR_OFF = STAT_OFF + 4 * 128 * 4;
+  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+};
+
+__global__ void __launch_bounds__(192, 1) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                                                               BwdArgs P, AttnGeom g) {
+  using L = DkvSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const uint32_t sK = smem_u32(smem + L::K_OFF), sV = smem_u32(smem + L::V_OFF), sQ = smem_u32(smem + L::Q_OFF), sdO = smem_u32(smem + L::DO_OFF);
+  float* s_lse = reinterpret_cast<float*>(smem + L::STAT_OFF);      // [2][128]
+  float* s_delta = s_lse + 256;                                      // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  const uint32_t kv_full = smem_u32(bars), q_full = smem_u32(bars + 1), q_empty = smem_u32(bars + 3);
+  const uint32_t st_full = smem_u32(bars + 5), ps_ready = smem_u32(bars + 6), acc_done = smem_u32(bars + 7);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  constexpr uint32_t TMEM_COLS = 512;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, b = bh / P.heads, h = bh - b * P.heads;
+  const int n = g.n_k, inner = P.heads * DH;
+  const int k0 = blockIdx.x * TK, k1 = min(k0 + TK, n) - 1;
+  const int nqt = (n + TQ - 1) / TQ;
+  auto needed = [&](int qt) { return attn_tile_needed(g, qt * TQ, min(qt * TQ + TQ, n) - 1, k0, k1); };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(q_full + 8 * s, 1); mbar_init(q_empty + 8 * s, 1); }
+    mbar_init(st_full, 1); mbar_init(ps_ready, 128); mbar_init(acc_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tSt = tmem, tdPt = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tPt = tmem + 384, tdSt = tmem + 448;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+      tma_load_2d(sK, &tmK, kv_full, 0, bh * n + k0);
+      tma_load_2d(sV, &tmV, kv_full, 0, bh * n + k0);
+      int it = 0;
+      for (int qt = 0; qt < nqt; ++qt) {
+        if (!needed(qt)) continue;
+        const int s = it & 1;
+        mbar_wait(q_empty + 8 * s, ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(q_full + 8 * s, 2 * TILE_BYTES);
+        tma_load_2d(sQ + s * TILE_BYTES, &tmQ, q_full + 8 * s, 0, bh * n + qt * TQ);
+        tma_load_2d(sdO + s * TILE_BYTES, &tmdO, q_full + 8 * s, h * DH, b * n + qt * TQ);
+        ++it;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC_T = make_idesc_bf16(128, 128, false, false);   // S^T = K Q^T, dP^T = V dO^T
+      constexpr uint32_t IDESC_G = make_idesc_bf16(128, 64, false, true);     // dV = P^T dO, dK = dS^T Q   (B N-major)
+      mbar_wait(kv_full, 0);
+      const uint64_t dk = make_smem_desc(sK, 16, 1024), dv = make_smem_desc(sV, 16, 1024);
+      int it = 0;
+      for (int qt = 0; qt < nqt; ++qt) {
+        if (!needed(qt)) continue;
+        const int s = it & 1;
+        mbar_wait(q_full + 8 * s, (it >> 1) & 1);
+        tc_fence_after();
+        const uint64_t dq = make_smem_desc(sQ + s * TILE_BYTES, 16, 1024), ddo = make_smem_desc(sdO + s * TILE_BYTES, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tSt, dk + 2 * k, dq + 2 * k, IDESC_T, k != 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tdPt, dv + 2 * k, ddo + 2 * k, IDESC_T, k != 0);
+        umma_commit(st_full);
+        mbar_wait(ps_ready, it & 1);
+        tc_fence_after();
+        const uint64_t bq = make_smem_desc(sQ + s * TILE_BYTES, TILE_BYTES, 1024), bdo = make_smem_desc(sdO + s * TILE_BYTES, TILE_BYTES, 1024);
+#pragma unroll
+        for (int k = 0; k < TQ / 16; ++k) umma_bf16_ts(tdV, tPt + 8 * k, bdo + 128 * k, IDESC_G, (it | k) != 0);
+#pragma unroll
+        for (int k = 0; k < TQ / 16; ++k) umma_bf16_ts(tdK, tdSt + 8 * k, bq + 128 * k, IDESC_G, (it | k) != 0);
+        umma_commit(q_empty + 8 * s);
+        umma_commit(acc_done);
+        ++it;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int kj = k0 + row;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint8_t* km = P.key_mask ? P.key_mask + (long long)b * n : nullptr;
+    const bool key_ok = kj < n && (km == nullptr || km[kj] != 0);
+    int it = 0;
+    for (int qt = 0; qt < nqt; ++qt) {
+      if (!needed(qt)) continue;
+      const int s = it & 1;
+      const int qq0 = qt * TQ, qq1 = min(qq0 + TQ, n) - 1;
+      {   // per-query statistics of this tile -> smem (this thread loads query `row` of the tile)
+        const int qi = qq0 + row;
+        s_lse[s * 128 + row] = qi < n ? P.lse[(long long)bh * n + qi] * LOG2E : 0.f;
+        s_delta[s * 128 + row] = qi < n ? P.delta[(long long)bh * n + qi] : 0.f;
+      }
+      named_bar_sync(1, 128);
+      const bool full = (k1 - k0 == TK - 1) && (qq1 - qq0 == TQ - 1) && km == nullptr && attn_tile_full(g, qq0, qq1, k0, k1);
+      mbar_wait(st_full, it & 1);
+      tc_fence_after();
+      if (it > 0) {                               // previous dV/dK MMAs done reading P^T / dS^T
+        mbar_wait(acc_done, (it - 1) & 1);
+        tc_fence_after();
+      }
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rd[32];
+        tmem_ld32(tSt + lane_off + c * 32, rs);
+        tmem_ld32(tdPt + lane_off + c * 32, rd);
+        tmem_ld_wait();
+        uint32_t pk[16], dk_[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float pv[2], dsv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int ql = c * 32 + 2 * i + e;
+            bool ok = true;
+            if (!full) ok = key_ok && (qq0 + ql < n) && attn_allowed(g, qq0 + ql, kj);
+            const float p = ok ? exp2f(fmaf(__uint_as_float(rs[2 * i + e]), LOG2E, -s_lse[s * 128 + ql])) : 0.f;
+            pv[e] = p;
+            dsv[e] = p * (__uint_as_float(rd[2 * i + e]) - s_delta[s * 128 + ql]);
+          }
+          pk[i] = pack2(pv[0], pv[1]);
+          dk_[i] = pack2(dsv[0], dsv[1]);
+        }
+        tmem_st16(tPt + lane_off + c * 16, pk);
+        tmem_st16(tdSt + lane_off + c * 16, dk_);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(ps_ready);
+      ++it;
+    }
+    if (it > 0) {
+      mbar_wait(acc_done, (it - 1) & 1);
+      tc_fence_after();
+      bf16* rowp = P.dqkv + ((long long)b * n + (kj < n ? kj : 0)) * (3 * inner) + h * DH;
+      const float* cr = P.cos_t ? P.cos_t + (long long)(kj < n ? kj : 0) * (DH / 2) : nullptr;
+      const float* sr = P.sin_t ? P.sin_t + (long long)(kj < n ? kj : 0) * (DH / 2) : nullptr;
+      store_grad_row(tdK + lane_off, rowp + inner, cr, sr, 1.0f, kj < n);
+      store_grad_row(tdV + lane_off, rowp + 2 * inner, cr, sr, 1.0f, kj < n);
+    } else if (kj < n) {
+      bf16* rowp = P.dqkv + ((long long)b * n + kj) * (3 * inner) + h * DH;
+      for (int d = 0; d < DH; d += 8) {
+        *reinterpret_cast<uint4*>(rowp + inner + d) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(rowp + 2 * inner + d) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dQ : CTA = 128 queries, thread = query row.
+//   TMEM: S [0,128) | dP [128,256) | dS bf16 [256,320) | dQ [320,384)
+// ---------------------------------------------------------------------------------------------------------------
+struct DqSmem {
+  static constexpr int Q_OFF = 0, DO_OFF = TILE_BYTES, K_OFF = 2 * TILE_BYTES, V_OFF = 4 * TILE_BYTES;
+  static constexpr int BAR_OFF = 6 * TILE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+};
+
+__global__ void __launch_bounds__(192, 1) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                                                              BwdArgs P, AttnGeom g) {
+  using L = DqSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const uint32_t sQ = smem_u32(smem + L::Q_OFF), sdO = smem_u32(smem + L::DO_OFF), sK = smem_u32(smem + L::K_OFF), sV = smem_u32(smem + L::V_OFF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  const uint32_t q_full = smem_u32(bars), kv_full = smem_u32(bars + 1), kv_empty = smem_u32(bars + 3);
+  const uint32_t s_full = smem_u32(bars + 5), ds_ready = smem_u32(bars + 6), acc_done = smem_u32(bars + 7);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  constexpr uint32_t TMEM_COLS = 512;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, b = bh / P.heads, h = bh - b * P.heads;
+  const int n = g.n_k, inner = P.heads * DH;
+  const int q0 = blockIdx.x * TQ, q1 = min(q0 + TQ, n) - 1;
+  const int nkt = (n + TK - 1) / TK;
+  auto needed = [&](int kt) { return attn_tile_needed(g, q0, q1, kt * TK, min(kt * TK + TK, n) - 1); };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
+    mbar_init(s_full, 1); mbar_init(ds_ready, 128); mbar_init(acc_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdS = tmem + 256, tdQ = tmem + 320;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * TILE_BYTES);
+      tma_load_2d(sQ, &tmQ, q_full, 0, bh * n + q0);
+      tma_load_2d(sdO, &tmdO, q_full, h * DH, b * n + q0);
+      int it = 0;
+      for (int kt = 0; kt < nkt; ++kt) {
+        if (!needed(kt)) continue;
+        const int s = it & 1;
+        mbar_wait(kv_empty + 8 * s, ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(kv_full + 8 * s, 2 * TILE_BYTES);
+        tma_load_2d(sK + s * TILE_BYTES, &tmK, kv_full + 8 * s, 0, bh * n + kt * TK);
+        tma_load_2d(sV + s * TILE_BYTES, &tmV, kv_full + 8 * s, 0, bh * n + kt * TK);
+        ++it;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t IDESC_G = make_idesc_bf16(128, 64, false, true);
+      mbar_wait(q_full, 0);
+      const uint64_t dq = make_smem_desc(sQ, 16, 1024), ddo = make_smem_desc(sdO, 16, 1024);
+      int it = 0;
+      for (int kt = 0; kt < nkt; ++kt) {
+        if (!needed(kt)) continue;
+        const int s = it & 1;
+        mbar_wait(kv_full + 8 * s, (it >> 1) & 1);
+        tc_fence_after();
+        const uint64_t dk = make_smem_desc(sK + s * TILE_BYTES, 16, 1024), dv = make_smem_desc(sV + s * TILE_BYTES, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tdP, ddo + 2 * k, dv + 2 * k, IDESC_S, k != 0);
+        umma_commit(s_full);
+        mbar_wait(ds_ready, it & 1);
+        tc_fence_after();
+        const uint64_t bk = make_smem_desc(sK + s * TILE_BYTES, TILE_BYTES, 1024);
+#pragma unroll
+        for (int k = 0; k < TK / 16; ++k) umma_bf16_ts(tdQ, tdS + 8 * k, bk + 128 * k, IDESC_G, (it | k) != 0);
+        umma_commit(kv_empty + 8 * s);
+        umma_commit(acc_done);
+        ++it;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int qi = q0 + row;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint8_t* km = P.key_mask ? P.key_mask + (long long)b * n : nullptr;
+    const float lse_r = qi < n ? P.lse[(long long)bh * n + qi] * LOG2E : 0.f;
+    const float delta_r = qi < n ? P.delta[(long long)bh * n + qi] : 0.f;
+    int it = 0;
+    for (int kt = 0; kt < nkt; ++kt) {
+      if (!needed(kt)) continue;
+      const int k0 = kt * TK, k1 = min(k0 + TK, n) - 1;
+      const bool full = (k1 - k0 == TK - 1) && km == nullptr && attn_tile_full(g, q0, q1, k0, k1);
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      if (it > 0) {
+        mbar_wait(acc_done, (it - 1) & 1);
+        tc_fence_after();
+      }
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rd[32];
+        tmem_ld32(tS + lane_off + c * 32, rs);
+        tmem_ld32(tdP + lane_off + c * 32, rd);
+        tmem_ld_wait();
+        uint32_t dk_[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float dsv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int kj = k0 + c * 32 + 2 * i + e;
+            bool ok = true;
+            if (!full) {
+              ok = (qi < n) && (kj < n) && attn_allowed(g, qi, kj);
+              if (ok && km) ok = km[kj] != 0;
+            }
+            const float p = ok ? exp2f(fmaf(__uint_as_float(rs[2 * i + e]), LOG2E, -lse_r)) : 0.f;
+            dsv[e] = p * (__uint_as_float(rd[2 * i + e]) - delta_r);
+          }
+          dk_[i] = pack2(dsv[0], dsv[1]);
+        }
+        tmem_st16(tdS + lane_off + c * 16, dk_);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(ds_ready);
+      ++it;
+    }
+    if (it > 0) {
+      mbar_wait(acc_done, (it - 1) & 1);
+      tc_fence_after();
+      const int qs = qi < n ? qi : 0;
+      bf16* rowp = P.dqkv + ((long long)b * n + qs) * (3 * inner) + h * DH;
+      const float* cr = P.cos_t ? P.cos_t + (long long)qs * (DH / 2) : nullptr;
+      const float* sr = P.sin_t ? P.sin_t + (long long)qs * (DH / 2) : nullptr;
+      store_grad_row(tdQ + lane_off, rowp, cr, sr, P.q_scale, qi < n);    // q = rot(x) * scale (attention.py:69)
+    } else if (qi < n) {
+      bf16* rowp = P.dqkv + ((long long)b * n + qi) * (3 * inner) + h * DH;
+      for (int d = 0; d < DH; d += 8) *reinterpret_cast<uint4*>(rowp + d) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int tc_mode_env() {   // DALLE_B200_ATTN_P=smem forces the SS variant (P staged through shared memory)
+  const char* v = getenv("DALLE_B200_ATTN_P");
+  return (v && !strcmp(v, "smem")) ? 1 : 0;
+}
+
+template <bool P_TMEM>
+int launch_fwd(const db200_attn_fwd_params& p, cudaStream_t st) {
+  using L = FwdSmem<P_TMEM>;
+  CUtensorMap tmQ, tmK, tmV;
+  const uint64_t bh = (uint64_t)p.batch * p.heads;
+  int rc = make_tensor_map_bf16(&tmQ, p.q, DH, bh * p.n_q, DH, DH, TQ);
+  if (rc) return rc;
+  if ((rc = make_tensor_map_bf16(&tmK, p.k, DH, bh * p.n_k, DH, DH, TK))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmV, p.v, DH, bh * p.n_k, DH, DH, TK))) return rc;
+  auto kern = attn_fwd_tc_kernel<P_TMEM>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_done = true;
+  }
+  FwdArgs A{reinterpret_cast<bf16*>(p.out), p.lse, p.key_mask, p.heads, p.batch};
+  dim3 grid(ceil_div(p.n_q, TQ), p.batch * p.heads);
+  kern<<<grid, 192, L::TOTAL, st>>>(tmQ, tmK, tmV, A, make_geom(p));
+  DB200_LAUNCH_OK("attn_fwd_tc_kernel");
+  return DB200_OK;
+}
+
+}  // namespace
+
+bool attn_tc_supported(const db200_attn_fwd_params& p) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  return major == 10 && p.dtype == DB200_BF16 && p.dim_head == 64 && al16(p.q) && al16(p.k) && al16(p.v) && al16(p.out);
+}
+
+int attn_fwd_tc_launch(const db200_attn_fwd_params& p, cudaStream_t st) {
+  return tc_mode_env() ? launch_fwd<false>(p, st) : launch_fwd<true>(p, st);
+}
+
+int attn_bwd_tc_launch(const db200_attn_bwd_params& p, cudaStream_t st) {
+  const db200_attn_fwd_params& f = p.f;
+  const int n = f.n_k;
+  if (!al16(p.d_out) || !al16(p.dqkv)) return set_error(DB200_ERR_BAD_ARG, "attn_bwd: d_out / dqkv must be 16-byte aligned");
+  CUtensorMap tmQ, tmK, tmV, tmdO;
+  const uint64_t bh = (uint64_t)f.batch * f.heads;
+  const uint64_t inner = (uint64_t)f.heads * DH;
+  int rc;
+  if ((rc = make_tensor_map_bf16(&tmQ, f.q, DH, bh * n, DH, DH, TQ))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmK, f.k, DH, bh * n, DH, DH, TK))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmV, f.v, DH, bh * n, DH, DH, TK))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmdO, p.d_out, inner, (uint64_t)f.batch * n, inner, DH, TQ))) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DB200_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::TOTAL));
+    DB200_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL));
+    attr_done = true;
+  }
+  const int total_rows = f.batch * f.heads * n;
+  attn_delta_tc_kernel<<<ceil_div(total_rows * 32, 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(f.out),
+                                                                       reinterpret_cast<const bf16*>(p.d_out), p.delta, f.batch, f.heads, n);
+  DB200_LAUNCH_OK("attn_delta_tc_kernel");
+  BwdArgs A{f.lse, p.delta, f.key_mask, p.cos_t, p.sin_t, p.q_scale, reinterpret_cast<bf16*>(p.dqkv), f.heads, f.batch};
+  const AttnGeom g = make_geom(f);
+  dim3 grid(ceil_div(n, TQ), f.batch * f.heads);
+  attn_bwd_dkv_tc_kernel<<<grid, 192, DkvSmem::TOTAL, st>>>(tmQ, tmK, tmV, tmdO, A, g);
+  DB200_LAUNCH_OK("attn_bwd_dkv_tc_kernel");
+  attn_bwd_dq_tc_kernel<<<grid, 192, DqSmem::TOTAL, st>>>(tmQ, tmK, tmV, tmdO, A, g);
+  DB200_LAUNCH_OK("attn_bwd_dq_tc_kernel");
+  return DB200_OK;
+}
+
+}  // namespace db200

@@ -251,3 +251,35 @@ def test_scale_bwd_colsum_cast_axpby(dtype):
     report('axpby', o.axpby(a, bb, -0.5), a - 0.5 * bb, 1e-6, 1e-6)
     x = torch.randn(1003, device=dev())
     assert torch.equal(o.cast_bf16(x), x.to(torch.bfloat16))
+
+
+# ---- attention backends (CUDA-core fp32 / mma.sync / tcgen05) must agree ----------------------------------------
+@pytest.mark.parametrize('backend', ['simt', 'mma', 'tc', 'tc_smem'])
+@pytest.mark.parametrize('kind,code', PATTERNS)
+@pytest.mark.parametrize('n,T,fm', [(191, 65, 12), (300, 45, 16), (1280, 257, 32)])
+def test_attention_backends_bf16(backend, kind, code, n, T, fm, monkeypatch):
+    o = ops()
+    torch.manual_seed(9)
+    monkeypatch.setenv('DALLE_B200_ATTN', 'tc' if backend.startswith('tc') else backend)
+    if backend == 'tc_smem':
+        monkeypatch.setenv('DALLE_B200_ATTN_P', 'smem')
+    else:
+        monkeypatch.delenv('DALLE_B200_ATTN_P', raising=False)
+    b, h, dh = 2, 2, 64
+    q = _mk((b, h, n, dh), torch.bfloat16, dh ** -0.5)
+    k = _mk((b, h, n, dh), torch.bfloat16)
+    v = _mk((b, h, n, dh), torch.bfloat16)
+    spec = o.AttnSpec(code, causal=True, text_len=T, fmap=fm, kernel_size=5 if kind == 'conv_like' else 0, dilation=1)
+    out, lse = o.attn_fwd(spec, q, k, v)
+    allow = allowed_mask(kind, n, n, T, fm).to(dev())
+    qr, kr, vr = (t.float().detach().requires_grad_() for t in (q, k, v))
+    want = _attn_ref(qr, kr, vr, allow)
+    report(f'attn_fwd[{backend}] {kind} n={n}', out.view(b, n, h, dh).permute(0, 2, 1, 3), want, 2e-2, 2e-2)
+    s = (qr @ kr.transpose(-1, -2)).masked_fill(~allow, float('-inf'))
+    report(f'lse[{backend}] {kind} n={n}', lse, torch.logsumexp(s, -1), 1e-2, 1e-2)
+    g = _mk((b, n, h * dh), torch.bfloat16)
+    want.backward(g.float().view(b, n, h, dh).permute(0, 2, 1, 3))
+    dqkv = o.attn_bwd(spec, q, k, v, out, lse, g, None, None, 1.0)
+    dq, dk, dv = (dqkv.view(b, n, 3, h, dh)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    for name, got, ref in (('dq', dq, qr.grad), ('dk', dk, kr.grad), ('dv', dv, vr.grad)):
+        report(f'attn_bwd[{backend}] {name} {kind} n={n}', got, ref, 3e-2, 3e-2 * float(ref.abs().max()))
