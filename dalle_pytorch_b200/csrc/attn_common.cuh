@@ -73,6 +73,124 @@ __device__ __forceinline__ bool attn_tile_full(const AttnGeom& g, int q0, int q1
   return k1 < g.text_len && (q0 >= g.text_len || k1 <= q0);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 128-wide allowed-bit masks of one query row / one key column inside a tile.  For the reference's patterns the allowed set of
+// a row is a union of a few index ranges (or an arithmetic progression for axial columns), so the mask costs O(1) per tile
+// instead of 128 predicate evaluations with integer divisions; the softmax loops then only test bits.
+// ---------------------------------------------------------------------------------------------------------------------
+struct Mask128 { uint32_t w[4]; };
+
+__device__ __forceinline__ uint32_t range_bits32(int lo, int hi, int base) {      // bits of [lo,hi] in [base, base+31]
+  const int a = lo - base > 0 ? lo - base : 0;
+  const int b = hi - base < 31 ? hi - base : 31;
+  if (a > b) return 0u;
+  return (0xffffffffu >> (31 - b)) & (0xffffffffu << a);
+}
+__device__ __forceinline__ void mask_or_range(Mask128& m, int lo, int hi, int t0) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) m.w[c] |= range_bits32(lo, hi, t0 + 32 * c);
+}
+__device__ __forceinline__ void mask_or_bit(Mask128& m, int pos, int t0) {
+  const int d = pos - t0;
+  if (d >= 0 && d < 128) m.w[d >> 5] |= 1u << (d & 31);
+}
+
+// bit b = may query i (absolute position) attend key k0 + b ;  keys >= n_k are never allowed
+__device__ __forceinline__ Mask128 attn_row_bits(const AttnGeom& g, int i, int k0, const uint8_t* km) {
+  Mask128 m = {{0u, 0u, 0u, 0u}};
+  const int kend = (k0 + 127 < g.n_k - 1) ? k0 + 127 : g.n_k - 1;
+  const int T = g.text_len, fm = g.fmap;
+  switch (g.pattern) {
+    case DB200_ATTN_FULL:
+      mask_or_range(m, k0, g.causal ? (i < kend ? i : kend) : kend, k0);
+      break;
+    case DB200_ATTN_STATIC:
+      for (int b = 0; k0 + b <= kend; ++b)
+        if ((!g.causal || k0 + b <= i) && g.static_mask[(long long)i * g.static_ld + k0 + b]) m.w[b >> 5] |= 1u << (b & 31);
+      break;
+    default: {
+      if (i < T) { mask_or_range(m, 0, i < kend ? i : kend, k0); break; }
+      mask_or_range(m, 0, T - 1 < kend ? T - 1 : kend, k0);
+      const int qi = i - T, qr = qi / fm, qc = qi - qr * fm;
+      const int hi = i < kend ? i : kend;
+      if (g.pattern == DB200_ATTN_AXIAL_ROW) {
+        mask_or_range(m, T + qr * fm, hi, k0);
+      } else if (g.pattern == DB200_ATTN_AXIAL_COL) {
+        int j = T + qc;                                   // keys (r', qc), r' = 0..qr
+        if (j < k0) j += ((k0 - j + fm - 1) / fm) * fm;
+        for (; j <= hi; j += fm) mask_or_bit(m, j, k0);
+      } else {                                            // conv_like: rows qr - a*dil, columns qc - b*dil
+        const int span = (g.ksize - 1) * g.dil;
+        for (int a = 0; a < g.ksize; ++a) {
+          const int rr = qr - a * g.dil;
+          if (rr < 0) break;
+          const int rowbase = T + rr * fm;
+          if (g.dil == 1) {
+            mask_or_range(m, rowbase + (qc - span > 0 ? qc - span : 0), rowbase + qc < hi ? rowbase + qc : hi, k0);
+          } else {
+            for (int bb = 0; bb < g.ksize; ++bb) {
+              const int cc = qc - bb * g.dil;
+              if (cc < 0) break;
+              if (rowbase + cc <= hi) mask_or_bit(m, rowbase + cc, k0);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (km) {
+    for (int b = 0; k0 + b <= kend; ++b)
+      if (!km[k0 + b]) m.w[b >> 5] &= ~(1u << (b & 31));
+  }
+  return m;
+}
+
+// bit b = may query q0 + b attend key j ;  queries >= n are never allowed (training: n_q == n_k == n, positions absolute)
+__device__ __forceinline__ Mask128 attn_col_bits(const AttnGeom& g, int j, int q0, int n) {
+  Mask128 m = {{0u, 0u, 0u, 0u}};
+  const int qend = (q0 + 127 < n - 1) ? q0 + 127 : n - 1;
+  const int T = g.text_len, fm = g.fmap;
+  switch (g.pattern) {
+    case DB200_ATTN_FULL:
+      mask_or_range(m, g.causal ? (j > q0 ? j : q0) : q0, qend, q0);
+      break;
+    case DB200_ATTN_STATIC:
+      for (int b = 0; q0 + b <= qend; ++b)
+        if ((!g.causal || j <= q0 + b) && g.static_mask[(long long)(q0 + b) * g.static_ld + j]) m.w[b >> 5] |= 1u << (b & 31);
+      break;
+    default: {
+      if (j < T) { mask_or_range(m, j > q0 ? j : q0, qend, q0); break; }   // text key: text queries >= j, every image query
+      const int kj = j - T, kr = kj / fm, kc = kj - kr * fm;
+      if (g.pattern == DB200_ATTN_AXIAL_ROW) {
+        const int rowend = T + kr * fm + fm - 1;
+        mask_or_range(m, j, rowend < qend ? rowend : qend, q0);
+      } else if (g.pattern == DB200_ATTN_AXIAL_COL) {
+        int i = j;
+        if (i < q0) i += ((q0 - i + fm - 1) / fm) * fm;
+        for (; i <= qend; i += fm) mask_or_bit(m, i, q0);
+      } else {
+        const int span = (g.ksize - 1) * g.dil;
+        for (int a = 0; a < g.ksize; ++a) {
+          const int rr = kr + a * g.dil;
+          if (rr >= fm) break;
+          const int rowbase = T + rr * fm;
+          if (g.dil == 1) {
+            const int chi = kc + span < fm - 1 ? kc + span : fm - 1;
+            mask_or_range(m, rowbase + kc, rowbase + chi < qend ? rowbase + chi : qend, q0);
+          } else {
+            for (int bb = 0; bb < g.ksize; ++bb) {
+              const int cc = kc + bb * g.dil;
+              if (cc >= fm) break;
+              if (rowbase + cc <= qend) mask_or_bit(m, rowbase + cc, q0);
+            }
+          }
+        }
+      }
+    }
+  }
+  return m;
+}
+
 // inverse of the interleaved-pair rotary rotation (adjoint of epi_qkv_pair): given the gradient (g0,g1) of the
 // rotated pair, returns the gradient of the unrotated pair.
 __device__ __forceinline__ void rotary_adjoint(float c, float s, float& g0, float& g1) {

@@ -37,6 +37,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sel_bit(uint32_t bits, int i, float a, float b) { return (bits >> i) & 1u ? a : b; }
+
 struct FwdArgs {
   bf16* out; float* lse; const uint8_t* key_mask; int heads, batch;
 };
@@ -154,32 +161,33 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
       if (!needed(kt)) continue;
       const int k0 = kt * TK, k1 = min(k0 + TK, g.n_k) - 1;
       const bool full = (k1 - k0 == TK - 1) && km == nullptr && attn_tile_full(g, q0 + off, q_last + off, k0, k1);
-      auto masked = [&](int kj) {
-        bool ok = (qi < g.n_q) && (kj < g.n_k) && attn_allowed(g, qi + off, kj);
-        if (ok && km) ok = km[kj] != 0;
-        return !ok;
-      };
+      Mask128 mk = {{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}};
+      if (!full) {
+        if (qi < g.n_q) mk = attn_row_bits(g, qi + off, k0, km);
+        else mk.w[0] = mk.w[1] = mk.w[2] = mk.w[3] = 0u;
+      }
       mbar_wait(s_full, it & 1);
       tc_fence_after();
       // ---- pass 1: row max ----
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
+        const uint32_t mb = c == 0 ? mk.w[0] : c == 1 ? mk.w[1] : c == 2 ? mk.w[2] : mk.w[3];
+        if (__all_sync(0xffffffffu, mb == 0u)) continue;            // whole 32x32 chunk masked (warp-uniform)
         uint32_t r[32];
         tmem_ld32(tS + lane_off + c * 32, r);
         tmem_ld_wait();
-        if (full) {
+        if (mb == 0xffffffffu) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (!masked(k0 + c * 32 + i)) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, sel_bit(mb, i, __uint_as_float(r[i]), -INFINITY));
         }
       }
       const float m_new = (mx > m_run + RESCALE_TAU) ? mx : m_run;
-      const float corr = exp2f((m_run - m_new) * LOG2E);
-      const float mb = m_new * LOG2E;
+      const float corr = ex2((m_run - m_new) * LOG2E);
+      const float mb2 = m_new * LOG2E;
       if (it > 0) {                                  // PV of the previous tile must be done: P buffer free, O final
         mbar_wait(o_done, (it - 1) & 1);
         tc_fence_after();
@@ -188,20 +196,32 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
       float rs = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS + lane_off + c * 32, r);
-        tmem_ld_wait();
+        const uint32_t mb = c == 0 ? mk.w[0] : c == 1 ? mk.w[1] : c == 2 ? mk.w[2] : mk.w[3];
         uint32_t pk[16];
+        if (__all_sync(0xffffffffu, mb == 0u)) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = exp2f(fmaf(__uint_as_float(r[2 * i]), LOG2E, -mb));
-          float p1 = exp2f(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, -mb));
-          if (!full) {
-            if (masked(k0 + c * 32 + 2 * i)) p0 = 0.f;
-            if (masked(k0 + c * 32 + 2 * i + 1)) p1 = 0.f;
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+        } else {
+          uint32_t r[32];
+          tmem_ld32(tS + lane_off + c * 32, r);
+          tmem_ld_wait();
+          if (mb == 0xffffffffu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), LOG2E, -mb2));
+              const float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, -mb2));
+              rs += p0 + p1;
+              pk[i] = pack2(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = sel_bit(mb, 2 * i, ex2(fmaf(__uint_as_float(r[2 * i]), LOG2E, -mb2)), 0.f);
+              const float p1 = sel_bit(mb, 2 * i + 1, ex2(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, -mb2)), 0.f);
+              rs += p0 + p1;
+              pk[i] = pack2(p0, p1);
+            }
           }
-          rs += p0 + p1;
-          pk[i] = pack2(p0, p1);
         }
         if constexpr (P_TMEM) {
           tmem_st16(tP + lane_off + c * 16, pk);
@@ -437,6 +457,11 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dkv_tc_kernel(const __grid_co
       }
       named_bar_sync(1, 128);
       const bool full = (k1 - k0 == TK - 1) && (qq1 - qq0 == TQ - 1) && km == nullptr && attn_tile_full(g, qq0, qq1, k0, k1);
+      Mask128 mk = {{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}};
+      if (!full) {
+        if (key_ok) mk = attn_col_bits(g, kj, qq0, n);
+        else mk.w[0] = mk.w[1] = mk.w[2] = mk.w[3] = 0u;
+      }
       mbar_wait(st_full, it & 1);
       tc_fence_after();
       if (it > 0) {                               // previous dV/dK MMAs done reading P^T / dS^T
@@ -445,25 +470,26 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dkv_tc_kernel(const __grid_co
       }
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        uint32_t rs[32], rd[32];
-        tmem_ld32(tSt + lane_off + c * 32, rs);
-        tmem_ld32(tdPt + lane_off + c * 32, rd);
-        tmem_ld_wait();
+        const uint32_t mb = c == 0 ? mk.w[0] : c == 1 ? mk.w[1] : c == 2 ? mk.w[2] : mk.w[3];
         uint32_t pk[16], dk_[16];
+        if (__all_sync(0xffffffffu, mb == 0u)) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float pv[2], dsv[2];
+          for (int i = 0; i < 16; ++i) { pk[i] = 0u; dk_[i] = 0u; }
+        } else {
+          uint32_t rs[32], rd[32];
+          tmem_ld32(tSt + lane_off + c * 32, rs);
+          tmem_ld32(tdPt + lane_off + c * 32, rd);
+          tmem_ld_wait();
+          const float* ls = s_lse + s * 128 + c * 32;
+          const float* dl = s_delta + s * 128 + c * 32;
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int ql = c * 32 + 2 * i + e;
-            bool ok = true;
-            if (!full) ok = key_ok && (qq0 + ql < n) && attn_allowed(g, qq0 + ql, kj);
-            const float p = ok ? exp2f(fmaf(__uint_as_float(rs[2 * i + e]), LOG2E, -s_lse[s * 128 + ql])) : 0.f;
-            pv[e] = p;
-            dsv[e] = p * (__uint_as_float(rd[2 * i + e]) - s_delta[s * 128 + ql]);
+          for (int i = 0; i < 16; ++i) {
+            float p0 = ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -ls[2 * i]));
+            float p1 = ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -ls[2 * i + 1]));
+            if (mb != 0xffffffffu) { p0 = sel_bit(mb, 2 * i, p0, 0.f); p1 = sel_bit(mb, 2 * i + 1, p1, 0.f); }
+            pk[i] = pack2(p0, p1);
+            dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - dl[2 * i]), p1 * (__uint_as_float(rd[2 * i + 1]) - dl[2 * i + 1]));
           }
-          pk[i] = pack2(pv[0], pv[1]);
-          dk_[i] = pack2(dsv[0], dsv[1]);
         }
         tmem_st16(tPt + lane_off + c * 16, pk);
         tmem_st16(tdSt + lane_off + c * 16, dk_);
@@ -600,6 +626,11 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dq_tc_kernel(const __grid_con
       if (!needed(kt)) continue;
       const int k0 = kt * TK, k1 = min(k0 + TK, n) - 1;
       const bool full = (k1 - k0 == TK - 1) && km == nullptr && attn_tile_full(g, q0, q1, k0, k1);
+      Mask128 mk = {{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}};
+      if (!full) {
+        if (qi < n) mk = attn_row_bits(g, qi, k0, km);
+        else mk.w[0] = mk.w[1] = mk.w[2] = mk.w[3] = 0u;
+      }
       mbar_wait(s_full, it & 1);
       tc_fence_after();
       if (it > 0) {
@@ -608,26 +639,23 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dq_tc_kernel(const __grid_con
       }
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
-        uint32_t rs[32], rd[32];
-        tmem_ld32(tS + lane_off + c * 32, rs);
-        tmem_ld32(tdP + lane_off + c * 32, rd);
-        tmem_ld_wait();
+        const uint32_t mb = c == 0 ? mk.w[0] : c == 1 ? mk.w[1] : c == 2 ? mk.w[2] : mk.w[3];
         uint32_t dk_[16];
+        if (__all_sync(0xffffffffu, mb == 0u)) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float dsv[2];
+          for (int i = 0; i < 16; ++i) dk_[i] = 0u;
+        } else {
+          uint32_t rs[32], rd[32];
+          tmem_ld32(tS + lane_off + c * 32, rs);
+          tmem_ld32(tdP + lane_off + c * 32, rd);
+          tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int kj = k0 + c * 32 + 2 * i + e;
-            bool ok = true;
-            if (!full) {
-              ok = (qi < n) && (kj < n) && attn_allowed(g, qi, kj);
-              if (ok && km) ok = km[kj] != 0;
-            }
-            const float p = ok ? exp2f(fmaf(__uint_as_float(rs[2 * i + e]), LOG2E, -lse_r)) : 0.f;
-            dsv[e] = p * (__uint_as_float(rd[2 * i + e]) - delta_r);
+          for (int i = 0; i < 16; ++i) {
+            float p0 = ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -lse_r));
+            float p1 = ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -lse_r));
+            if (mb != 0xffffffffu) { p0 = sel_bit(mb, 2 * i, p0, 0.f); p1 = sel_bit(mb, 2 * i + 1, p1, 0.f); }
+            dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - delta_r), p1 * (__uint_as_float(rd[2 * i + 1]) - delta_r));
           }
-          dk_[i] = pack2(dsv[0], dsv[1]);
         }
         tmem_st16(tdS + lane_off + c * 16, dk_);
       }
