@@ -40,6 +40,7 @@ int ln_shift_fwd_launch(const db200_ln_shift_fwd_params& P, cudaStream_t st);
 int ln_shift_bwd_launch(const db200_ln_shift_bwd_params& P, cudaStream_t st);
 int scale_bwd_launch(const db200_scale_bwd_params& P, cudaStream_t st);
 int colsum_launch(const void* x, int dtype, int rows, int cols, float* out, cudaStream_t st);
+int geglu_bwd_launch(const void* dh, const void* u, void* du, float* dbias, int dtype, int rows, int hidden, cudaStream_t st);
 int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st);
 int axpby_launch(const float* a, const float* b, float alpha, float* y, int64_t count, cudaStream_t st);
 int gemm_simt_launch(const db200_gemm_params& p, cudaStream_t st);
@@ -230,6 +231,12 @@ int dalle_b200_scale_bwd(const db200_scale_bwd_params* p, void* stream) {
 int dalle_b200_colsum(const void* x, int dtype, int rows, int cols, float* out, void* stream) {
   DB200_CHECK_ARG(x && out && rows >= 0 && cols > 0 && (cols & 1) == 0 && dtype_ok(dtype), "colsum: bad args");
   return colsum_launch(x, dtype, rows, cols, out, (cudaStream_t)stream);
+}
+
+int dalle_b200_geglu_bwd(const void* dh, const void* u, void* du, float* dbias, int dtype, int rows, int hidden, void* stream) {
+  DB200_CHECK_ARG(dh && u && du && rows >= 0 && hidden > 0 && (hidden & 7) == 0 && dtype_ok(dtype), "geglu_bwd: bad args (hidden must be a multiple of 8)");
+  DB200_CHECK_ARG(aligned16(dh) && aligned16(u) && aligned16(du), "geglu_bwd: tensors must be 16-byte aligned");
+  return geglu_bwd_launch(dh, u, du, dbias, dtype, rows, hidden, (cudaStream_t)stream);
 }
 
 int dalle_b200_cast_bf16(const float* src, void* dst, int64_t count, void* stream) {

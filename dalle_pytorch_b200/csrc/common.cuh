@@ -71,7 +71,8 @@ __device__ __forceinline__ float gelu_erf_grad(float g) {
 __device__ __forceinline__ void gelu_fast(float g, float& gelu, float& dgelu) {
   const float x = g * 0.70710678118654752440f;
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
   const float ex = __expf(-ax * ax);
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(t, poly, 1.421413741f);

@@ -1,6 +1,7 @@
 // HBM-bound glue kernels of the DALL-E block: LayerNorm + token-shift (forward and backward), LayerScale /
 // residual backward, column sums, casts.  Each is one pass over its tensor with 16-byte accesses.
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace db200 {
 
@@ -171,6 +172,224 @@ __global__ void __launch_bounds__(LN_THREADS) ln_shift_bwd_kernel(db200_ln_shift
   }
 }
 
+
+// =====================================================================================================================
+// Warp-per-row variants for d = 128 * NCH (every benchmark configuration): the whole row lives in registers (4*NCH floats per
+// lane), all reductions are warp shuffles (no block barriers), every global access is a contiguous 256-512 B segment per
+// warp instruction.  These are the kernels that run in C2..C5; the CTA-per-row kernels above cover arbitrary d.
+// =====================================================================================================================
+constexpr int WR_WARPS = 8;
+
+template <typename TO, int NCH>
+__global__ void __launch_bounds__(WR_WARPS * 32) ln_shift_fwd_warp_kernel(db200_ln_shift_fwd_params P) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = P.batch * P.n;
+  const int r = blockIdx.x * WR_WARPS + warp;
+  if (r >= rows) return;
+  const int n = P.n, d = P.d;
+  const int b = r / n, p = r - b * n;
+  const float* xr = P.x + (long long)r * d;
+  float4 v[NCH];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    v[k] = *reinterpret_cast<const float4*>(xr + k * 128 + lane * 4);
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (P.do_ln) {
+    mean = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const float a0 = v[k].x - mean, a1 = v[k].y - mean, a2 = v[k].z - mean, a3 = v[k].w - mean;
+      q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+    rstd = 1.0f / sqrtf(warp_sum(q) / d + P.eps);
+    if (lane == 0) { P.mean[r] = mean; P.rstd[r] = rstd; }
+  }
+  TO* out = reinterpret_cast<TO*>(P.out);
+  const long long brow = (long long)b * n;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int c = k * 128 + lane * 4;
+    float4 y = v[k];
+    if (P.do_ln) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(P.gamma + c));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(P.beta + c));
+      y.x = (y.x - mean) * rstd * g.x + be.x;
+      y.y = (y.y - mean) * rstd * g.y + be.y;
+      y.z = (y.z - mean) * rstd * g.z + be.z;
+      y.w = (y.w - mean) * rstd * g.w + be.w;
+    }
+    const int dest = shift_dest(p, c, n, d, P.text_len, P.fmap, P.do_shift);
+    if (dest >= 0) {
+      TO* o = out + (brow + dest) * d + c;
+      store2<TO>(o, y.x, y.y);
+      store2<TO>(o + 2, y.z, y.w);
+    }
+    if (P.do_shift && c < (d >> 1)) {
+      bool zero;
+      if (p < P.text_len) zero = (p == 0);
+      else {
+        const int q = p - P.text_len;
+        const int rr = q / P.fmap, cc = q - rr * P.fmap;
+        zero = (c < (d >> 2)) ? (rr == 0) : (cc == 0);
+      }
+      if (zero) {
+        TO* o = out + (brow + p) * d + c;
+        store2<TO>(o, 0.f, 0.f);
+        store2<TO>(o + 2, 0.f, 0.f);
+      }
+    }
+  }
+}
+
+template <typename TI, int NCH>
+__global__ void __launch_bounds__(WR_WARPS * 32, 2) ln_shift_bwd_warp_kernel(db200_ln_shift_bwd_params P) {
+  extern __shared__ float sm[];          // [2][d] block partials of dgamma / dbeta
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = P.n, d = P.d;
+  const int rows = P.batch * n;
+  if (P.do_ln) {
+    for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
+    __syncthreads();
+  }
+  // Two passes per row keep the register footprint small (only the dgamma/dbeta partials persist across rows), so two
+  // blocks fit per SM; the second pass re-reads the row's 6 KB from L1/L2, not from HBM.
+  float4 ag[NCH], ab[NCH];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) { ag[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  const TI* dA = reinterpret_cast<const TI*>(P.d_out);
+  for (int r = blockIdx.x * WR_WARPS + warp; r < rows; r += gridDim.x * WR_WARPS) {
+    const int b = r / n, p = r - b * n;
+    const long long brow = (long long)b * n;
+    const float* xr = P.x + (long long)r * d;
+    float mean = 0.f, rstd = 1.f;
+    if (P.do_ln) { mean = P.mean[r]; rstd = P.rstd[r]; }
+    int srcs[NCH];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = k * 128 + lane * 4;
+      srcs[k] = shift_dest(p, c, n, d, P.text_len, P.fmap, P.do_shift);
+      if (P.do_ln) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (srcs[k] >= 0) {
+          const TI* gp = dA + (brow + srcs[k]) * d + c;
+          const float2 a = load2<TI>(gp), bb = load2<TI>(gp + 2);
+          g = make_float4(a.x, a.y, bb.x, bb.y);
+        }
+        const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(P.gamma + c));
+        const float h0 = (xv.x - mean) * rstd, h1 = (xv.y - mean) * rstd, h2 = (xv.z - mean) * rstd, h3 = (xv.w - mean) * rstd;
+        ag[k].x += g.x * h0; ag[k].y += g.y * h1; ag[k].z += g.z * h2; ag[k].w += g.w * h3;
+        ab[k].x += g.x; ab[k].y += g.y; ab[k].z += g.z; ab[k].w += g.w;
+        g.x *= ga.x; g.y *= ga.y; g.z *= ga.z; g.w *= ga.w;
+        s1 += (g.x + g.y) + (g.z + g.w);
+        s2 += (g.x * h0 + g.y * h1) + (g.z * h2 + g.w * h3);
+      }
+    }
+    float m1 = 0.f, m2 = 0.f;
+    if (P.do_ln) { m1 = warp_sum(s1) / d; m2 = warp_sum(s2) / d; }
+    float* dxr = P.dx + (long long)r * d;
+    const float* dr = P.dres ? P.dres + (long long)r * d : nullptr;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = k * 128 + lane * 4;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (srcs[k] >= 0) {
+        const TI* gp = dA + (brow + srcs[k]) * d + c;
+        const float2 a = load2<TI>(gp), bb = load2<TI>(gp + 2);
+        o = make_float4(a.x, a.y, bb.x, bb.y);
+      }
+      if (P.do_ln) {
+        const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(P.gamma + c));
+        o.x = rstd * (o.x * ga.x - m1 - (xv.x - mean) * rstd * m2);
+        o.y = rstd * (o.y * ga.y - m1 - (xv.y - mean) * rstd * m2);
+        o.z = rstd * (o.z * ga.z - m1 - (xv.z - mean) * rstd * m2);
+        o.w = rstd * (o.w * ga.w - m1 - (xv.w - mean) * rstd * m2);
+      }
+      if (dr) {
+        const float4 e = *reinterpret_cast<const float4*>(dr + c);
+        o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+      }
+      *reinterpret_cast<float4*>(dxr + c) = o;
+    }
+  }
+  if (P.do_ln && P.dgamma) {
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = k * 128 + lane * 4;
+      atomicAdd(sm + c, ag[k].x); atomicAdd(sm + c + 1, ag[k].y); atomicAdd(sm + c + 2, ag[k].z); atomicAdd(sm + c + 3, ag[k].w);
+      atomicAdd(sm + d + c, ab[k].x); atomicAdd(sm + d + c + 1, ab[k].y); atomicAdd(sm + d + c + 2, ab[k].z); atomicAdd(sm + d + c + 3, ab[k].w);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      atomicAdd(P.dgamma + c, sm[c]);
+      atomicAdd(P.dbeta + c, sm[d + c]);
+    }
+  }
+}
+
+// scale_bwd, warp-per-row streaming: lane owns 8 consecutive channels of every 256-channel chunk (d = 256 * NCH8)
+template <typename T, int NCH8>
+__global__ void __launch_bounds__(WR_WARPS * 32) scale_bwd_warp_kernel(db200_scale_bwd_params P) {
+  extern __shared__ float sm[];          // [2][d]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = P.d;
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  float as[NCH8][8], ab[NCH8][8], sc[NCH8][8];
+#pragma unroll
+  for (int k = 0; k < NCH8; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      as[k][i] = 0.f; ab[k][i] = 0.f;
+      sc[k][i] = P.scale ? P.sign * __ldg(P.scale + k * 256 + lane * 8 + i) : P.sign;
+    }
+  const T* y = reinterpret_cast<const T*>(P.y);
+  T* dy = reinterpret_cast<T*>(P.dy);
+  const bool want_s = P.dscale != nullptr && y != nullptr;
+  for (int r = blockIdx.x * WR_WARPS + warp; r < P.rows; r += gridDim.x * WR_WARPS) {
+    const long long off = (long long)r * d;
+#pragma unroll
+    for (int k = 0; k < NCH8; ++k) {
+      const int c = k * 256 + lane * 8;
+      const float4 g0 = *reinterpret_cast<const float4*>(P.d_out + off + c);
+      const float4 g1 = *reinterpret_cast<const float4*>(P.d_out + off + c + 4);
+      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float ov[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { ov[i] = sc[k][i] * gv[i]; ab[k][i] += ov[i]; }
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) store2<T>(dy + off + c + i, ov[i], ov[i + 1]);
+      if (want_s) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const float2 yy = load2<T>(y + off + c + i);
+          as[k][i] += P.sign * gv[i] * yy.x;
+          as[k][i + 1] += P.sign * gv[i + 1] * yy.y;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NCH8; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = k * 256 + lane * 8 + i;
+      atomicAdd(sm + c, as[k][i]);
+      atomicAdd(sm + d + c, ab[k][i]);
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    if (P.dscale) atomicAdd(P.dscale + c, sm[c]);
+    if (P.dbias) atomicAdd(P.dbias + c, sm[d + c]);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) scale_bwd_kernel(db200_scale_bwd_params P) {
   extern __shared__ float sm[];
@@ -201,6 +420,42 @@ __global__ void __launch_bounds__(256) scale_bwd_kernel(db200_scale_bwd_params P
   for (int c = threadIdx.x * 2; c < d; c += blockDim.x * 2) {
     if (P.dscale) { atomicAdd(P.dscale + c, accs[c]); atomicAdd(P.dscale + c + 1, accs[c + 1]); }
     if (P.dbias) { atomicAdd(P.dbias + c, accb[c]); atomicAdd(P.dbias + c + 1, accb[c + 1]); }
+  }
+}
+
+// GEGLU adjoint as one streaming pass (transformer.py:106-109 autograd): du = [dh*gelu(g) | dh*a*gelu'(g)], plus the column
+// sums of du (= gradient of net.0.bias) accumulated on the fly.  Thread = 8 hidden columns, block = 2048 columns x GB_ROWS rows.
+constexpr int GB_ROWS = 64;
+template <typename T>
+__global__ void __launch_bounds__(256) geglu_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ u, T* __restrict__ du,
+                                                        float* __restrict__ dbias, int rows, int hidden) {
+  const int j = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (j >= hidden) return;
+  const int r0 = blockIdx.y * GB_ROWS, r1 = min(rows, r0 + GB_ROWS);
+  float sa[8], sg[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sa[i] = 0.f; sg[i] = 0.f; }
+#pragma unroll 2
+  for (int r = r0; r < r1; ++r) {
+    float d[8], a[8], g[8], da[8], dg[8];
+    Vec8<T>::load(dh + (long long)r * hidden + j, d);
+    Vec8<T>::load(u + (long long)r * 2 * hidden + j, a);
+    Vec8<T>::load(u + (long long)r * 2 * hidden + hidden + j, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float f, df;
+      gelu_pair<T>(g[i], f, df);
+      da[i] = d[i] * f;
+      dg[i] = d[i] * a[i] * df;
+      sa[i] += da[i];
+      sg[i] += dg[i];
+    }
+    Vec8<T>::store(du + (long long)r * 2 * hidden + j, da);
+    Vec8<T>::store(du + (long long)r * 2 * hidden + hidden + j, dg);
+  }
+  if (dbias) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { atomicAdd(dbias + j + i, sa[i]); atomicAdd(dbias + hidden + j + i, sg[i]); }
   }
 }
 
@@ -262,6 +517,19 @@ __global__ void axpby_kernel(const float* __restrict__ a, const float* __restric
 int ln_shift_fwd_launch(const db200_ln_shift_fwd_params& P, cudaStream_t st) {
   const int rows = P.batch * P.n;
   if (rows == 0) return DB200_OK;
+  const int wgrid = ceil_div(rows, WR_WARPS);
+#define DB200_LN_FWD_WARP(NCH)                                                                                              \
+  do {                                                                                                                      \
+    if (P.out_dtype == DB200_F32) ln_shift_fwd_warp_kernel<float, NCH><<<wgrid, WR_WARPS * 32, 0, st>>>(P);               \
+    else ln_shift_fwd_warp_kernel<__nv_bfloat16, NCH><<<wgrid, WR_WARPS * 32, 0, st>>>(P);                                 \
+    DB200_LAUNCH_OK("ln_shift_fwd_warp_kernel");                                                                           \
+    return DB200_OK;                                                                                                        \
+  } while (0)
+  if (P.d == 256) DB200_LN_FWD_WARP(2);
+  if (P.d == 512) DB200_LN_FWD_WARP(4);
+  if (P.d == 1024) DB200_LN_FWD_WARP(8);
+  if (P.d == 2048) DB200_LN_FWD_WARP(16);
+#undef DB200_LN_FWD_WARP
   const size_t smem = (size_t)P.d * sizeof(float);
   if (P.out_dtype == DB200_F32) ln_shift_fwd_kernel<float><<<rows, LN_THREADS, smem, st>>>(P);
   else ln_shift_fwd_kernel<__nv_bfloat16><<<rows, LN_THREADS, smem, st>>>(P);
@@ -272,6 +540,21 @@ int ln_shift_fwd_launch(const db200_ln_shift_fwd_params& P, cudaStream_t st) {
 int ln_shift_bwd_launch(const db200_ln_shift_bwd_params& P, cudaStream_t st) {
   const int rows = P.batch * P.n;
   if (rows == 0) return DB200_OK;
+  {
+    const int wgrid = ceil_div(rows, WR_WARPS) < sm_count() * 6 ? ceil_div(rows, WR_WARPS) : sm_count() * 6;
+    const size_t wsmem = (size_t)2 * P.d * sizeof(float);
+#define DB200_LN_BWD_WARP(NCH)                                                                                              \
+  do {                                                                                                                      \
+    if (P.dout_dtype == DB200_F32) ln_shift_bwd_warp_kernel<float, NCH><<<wgrid, WR_WARPS * 32, wsmem, st>>>(P);           \
+    else ln_shift_bwd_warp_kernel<__nv_bfloat16, NCH><<<wgrid, WR_WARPS * 32, wsmem, st>>>(P);                             \
+    DB200_LAUNCH_OK("ln_shift_bwd_warp_kernel");                                                                           \
+    return DB200_OK;                                                                                                        \
+  } while (0)
+    if (P.d == 256) DB200_LN_BWD_WARP(2);
+    if (P.d == 512) DB200_LN_BWD_WARP(4);
+    if (P.d == 1024) DB200_LN_BWD_WARP(8);
+#undef DB200_LN_BWD_WARP
+  }
   const size_t smem = (size_t)4 * P.d * sizeof(float);
   const int grid = rows < sm_count() * 8 ? rows : sm_count() * 8;
   if (P.dout_dtype == DB200_F32) ln_shift_bwd_kernel<float><<<grid, LN_THREADS, smem, st>>>(P);
@@ -283,10 +566,37 @@ int ln_shift_bwd_launch(const db200_ln_shift_bwd_params& P, cudaStream_t st) {
 int scale_bwd_launch(const db200_scale_bwd_params& P, cudaStream_t st) {
   if (P.rows == 0) return DB200_OK;
   const size_t smem = (size_t)2 * P.d * sizeof(float);
+  {
+    const int wgrid = ceil_div(P.rows, WR_WARPS) < sm_count() * 4 ? ceil_div(P.rows, WR_WARPS) : sm_count() * 4;
+#define DB200_SCALE_WARP(NCH8)                                                                                              \
+  do {                                                                                                                      \
+    if (P.dtype == DB200_F32) scale_bwd_warp_kernel<float, NCH8><<<wgrid, WR_WARPS * 32, smem, st>>>(P);                   \
+    else scale_bwd_warp_kernel<__nv_bfloat16, NCH8><<<wgrid, WR_WARPS * 32, smem, st>>>(P);                                \
+    DB200_LAUNCH_OK("scale_bwd_warp_kernel");                                                                              \
+    return DB200_OK;                                                                                                        \
+  } while (0)
+    if (P.d == 256) DB200_SCALE_WARP(1);
+    if (P.d == 512) DB200_SCALE_WARP(2);
+    if (P.d == 1024) DB200_SCALE_WARP(4);
+#undef DB200_SCALE_WARP
+  }
   const int grid = P.rows < sm_count() * 4 ? P.rows : sm_count() * 4;
   if (P.dtype == DB200_F32) scale_bwd_kernel<float><<<grid, 256, smem, st>>>(P);
   else scale_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(P);
   DB200_LAUNCH_OK("scale_bwd_kernel");
+  return DB200_OK;
+}
+
+int geglu_bwd_launch(const void* dh, const void* u, void* du, float* dbias, int dtype, int rows, int hidden, cudaStream_t st) {
+  if (rows == 0) return DB200_OK;
+  dim3 grid(ceil_div(hidden, 2048), ceil_div(rows, GB_ROWS));
+  if (dtype == DB200_F32)
+    geglu_bwd_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(dh), reinterpret_cast<const float*>(u),
+                                                  reinterpret_cast<float*>(du), dbias, rows, hidden);
+  else
+    geglu_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dh), reinterpret_cast<const __nv_bfloat16*>(u),
+                                                          reinterpret_cast<__nv_bfloat16*>(du), dbias, rows, hidden);
+  DB200_LAUNCH_OK("geglu_bwd_kernel");
   return DB200_OK;
 }
 

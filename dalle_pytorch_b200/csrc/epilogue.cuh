@@ -245,4 +245,133 @@ __device__ __forceinline__ void epi_geglu_vec8(const EpiArgs& e, int m, int j, f
   Vec8<T>::store(reinterpret_cast<T*>(e.h_out) + (long long)m * e.hidden + j, h);
 }
 
+
+// =====================================================================================================================
+// "cols" epilogue granule for the tcgen05 kernel: after the smem transpose a lane owns TWO adjacent columns (n, n+1) of 16
+// rows (m = mbase + 2*it, it = 0..15; t[2*it], t[2*it+1] are the accumulators).  Per-column constants (bias, LayerScale,
+// head/offset arithmetic) are hoisted out of the row loop and every global INPUT of the chunk is fetched up front (batched
+// read-only loads), so the 16 rows do not serialise on memory latency.
+// =====================================================================================================================
+template <int EPI, typename T>
+__device__ __forceinline__ void epi_chunk_cols(const EpiArgs& e, int mbase, int n, const float* t, int M) {
+  if constexpr (EPI == DB200_EPI_STORE) {
+    float b0 = 0.f, b1 = 0.f;
+    if (e.bias) { const float2 bb = __ldg(reinterpret_cast<const float2*>(e.bias + n)); b0 = bb.x; b1 = bb.y; }
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int m = mbase + 2 * it;
+      if (m < M) {
+        const long long off = (long long)m * e.ldc + n;
+        if (e.c_is_f32) store2<float>(reinterpret_cast<float*>(e.C) + off, t[2 * it] + b0, t[2 * it + 1] + b1);
+        else store2<T>(reinterpret_cast<T*>(e.C) + off, t[2 * it] + b0, t[2 * it + 1] + b1);
+      }
+    }
+  } else if constexpr (EPI == DB200_EPI_RESID) {
+    float b0 = 0.f, b1 = 0.f, s0 = e.sign, s1 = e.sign;
+    if (e.bias) { const float2 bb = __ldg(reinterpret_cast<const float2*>(e.bias + n)); b0 = bb.x; b1 = bb.y; }
+    if (e.scale) { const float2 sc = __ldg(reinterpret_cast<const float2*>(e.scale + n)); s0 *= sc.x; s1 *= sc.y; }
+    float2 rr[16];
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int m = mbase + 2 * it;
+      rr[it] = make_float2(0.f, 0.f);
+      if (e.resid && m < M) rr[it] = __ldg(reinterpret_cast<const float2*>(e.resid + (long long)m * e.N + n));
+    }
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int m = mbase + 2 * it;
+      if (m < M) {
+        const long long off = (long long)m * e.N + n;
+        const float v0 = t[2 * it] + b0, v1 = t[2 * it + 1] + b1;
+        if (e.y_out) store2<T>(reinterpret_cast<T*>(e.y_out) + off, v0, v1);
+        *reinterpret_cast<float2*>(e.out + off) = make_float2(rr[it].x + s0 * v0, rr[it].y + s1 * v1);
+      }
+    }
+  } else if constexpr (EPI == DB200_EPI_QKV) {
+    const int inner = e.heads * e.dim_head;
+    const int which = n / inner;
+    const int rem = n - which * inner;
+    const int head = rem / e.dim_head;
+    const int d = rem - head * e.dim_head;
+    const float qs = which == 0 ? e.q_scale : 1.0f;
+    T* base = reinterpret_cast<T*>(which == 0 ? e.q : (which == 1 ? e.k : e.v));
+    const int b0 = mbase / e.seq_n;
+    const int p0 = mbase - b0 * e.seq_n;
+    float cs[16], sn[16];
+    {
+      int b = b0, p = p0;
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        while (p >= e.seq_n) { p -= e.seq_n; ++b; }
+        cs[it] = 1.f; sn[it] = 0.f;
+        if (e.cos_t && mbase + 2 * it < M) {
+          const int ti = (p + e.pos_offset) * (e.dim_head >> 1) + (d >> 1);
+          cs[it] = __ldg(e.cos_t + ti);
+          sn[it] = __ldg(e.sin_t + ti);
+        }
+        p += 2;
+      }
+    }
+    int b = b0, p = p0;
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      while (p >= e.seq_n) { p -= e.seq_n; ++b; }
+      if (mbase + 2 * it < M) {
+        const float x0 = t[2 * it], x1 = t[2 * it + 1];
+        T* dst = base + (((long long)b * e.heads + head) * e.seq_n + p) * e.dim_head + d;
+        store2<T>(dst, (x0 * cs[it] + (-x1) * sn[it]) * qs, (x1 * cs[it] + x0 * sn[it]) * qs);
+      }
+      p += 2;
+    }
+  } else if constexpr (EPI == DB200_EPI_GEGLU_BWD) {
+    float2 a[16], g[16];
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int m = mbase + 2 * it;
+      a[it] = make_float2(0.f, 0.f); g[it] = make_float2(0.f, 0.f);
+      if (m < M) {
+        const T* u = reinterpret_cast<const T*>(e.u_in) + (long long)m * (2 * e.hidden);
+        a[it] = load2<T>(u + n);
+        g[it] = load2<T>(u + e.hidden + n);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const int m = mbase + 2 * it;
+      if (m < M) {
+        float f0, f1, df0, df1;
+        gelu_pair<T>(g[it].x, f0, df0);
+        gelu_pair<T>(g[it].y, f1, df1);
+        T* du = reinterpret_cast<T*>(e.du_out) + (long long)m * (2 * e.hidden);
+        store2<T>(du + n, t[2 * it] * f0, t[2 * it + 1] * f1);
+        store2<T>(du + e.hidden + n, t[2 * it] * a[it].x * df0, t[2 * it + 1] * a[it].y * df1);
+      }
+    }
+  }
+}
+
+// GEGLU forward, cols granule: ta / tg = a and gate accumulators of hidden columns (j, j+1) for the 16 rows
+template <typename T>
+__device__ __forceinline__ void epi_chunk_cols_geglu(const EpiArgs& e, int mbase, int j, const float* ta, const float* tg, int M) {
+  float ba0 = 0.f, ba1 = 0.f, bg0 = 0.f, bg1 = 0.f;
+  if (e.bias) {
+    const float2 ba = __ldg(reinterpret_cast<const float2*>(e.bias + j));
+    const float2 bg = __ldg(reinterpret_cast<const float2*>(e.bias + e.hidden + j));
+    ba0 = ba.x; ba1 = ba.y; bg0 = bg.x; bg1 = bg.y;
+  }
+#pragma unroll
+  for (int it = 0; it < 16; ++it) {
+    const int m = mbase + 2 * it;
+    if (m < M) {
+      const float a0 = ta[2 * it] + ba0, a1 = ta[2 * it + 1] + ba1, g0 = tg[2 * it] + bg0, g1 = tg[2 * it + 1] + bg1;
+      if (e.u_out) {
+        T* u = reinterpret_cast<T*>(e.u_out) + (long long)m * (2 * e.hidden);
+        store2<T>(u + j, a0, a1);
+        store2<T>(u + e.hidden + j, g0, g1);
+      }
+      store2<T>(reinterpret_cast<T*>(e.h_out) + (long long)m * e.hidden + j, a0 * gelu_fwd<T>(g0), a1 * gelu_fwd<T>(g1));
+    }
+  }
+}
+
 }  // namespace db200

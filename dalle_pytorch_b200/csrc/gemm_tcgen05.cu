@@ -70,6 +70,7 @@ struct SmemLayout {
 };
 
 template <int BLOCK_N, int EPI, bool A_MN, bool B_MN, bool EPI_COLS>
+// 320 threads are allocated as 12 warps of registers (4-warp granularity) -> 168 registers per thread at most
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, EpiArgs e) {
   using L = SmemLayout<BLOCK_N>;
@@ -251,46 +252,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       } else
       if constexpr (EPI == DB200_EPI_GEGLU) {
         // a = columns [0,128), g = columns [128,256) of the accumulator; this warp pairs a/g of hidden [half*64, +64)
-        uint32_t ra[2][32], rg[2][32];
-        tmem_ld32(taddr + half * 64, ra[0]);
-        tmem_ld32(taddr + 128 + half * 64, rg[0]);
+        uint32_t ra[32], rg[32];
+        tmem_ld32(taddr + half * 64, ra);
+        tmem_ld32(taddr + 128 + half * 64, rg);
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           tmem_ld_wait();
-          if (ch + 1 < 2) {
-            tmem_ld32(taddr + half * 64 + 32, ra[1]);
-            tmem_ld32(taddr + 128 + half * 64 + 32, rg[1]);
-          }
           float ta[32], tg[32];
-          transpose_chunk(ra[ch], ta, stage, lane);
-          transpose_chunk(rg[ch], tg, stage, lane);
-          const int j = (n0 >> 1) + half * 64 + ch * 32 + lcol;
-          if (j < e.hidden) {
-#pragma unroll
-            for (int it = 0; it < 16; ++it) {
-              const int m = mbase + 2 * it;
-              if (m < M) epi_geglu_pair<__nv_bfloat16>(e, m, j, ta[2 * it], ta[2 * it + 1], tg[2 * it], tg[2 * it + 1]);
-            }
+          transpose_chunk(ra, ta, stage, lane);
+          transpose_chunk(rg, tg, stage, lane);
+          if (ch + 1 < 2) {                                  // the raw registers are free again: fetch the next chunk now
+            tmem_ld32(taddr + half * 64 + 32, ra);
+            tmem_ld32(taddr + 128 + half * 64 + 32, rg);
           }
+          const int j = (n0 >> 1) + half * 64 + ch * 32 + lcol;
+          if (j < e.hidden) epi_chunk_cols_geglu<__nv_bfloat16>(e, mbase, j, ta, tg, M);
         }
       } else {
         constexpr int NCH = (BLOCK_N / 2) / 32;
-        uint32_t r[2][32];
-        tmem_ld32(taddr + half * (BLOCK_N / 2), r[0]);
+        uint32_t r[32];
+        tmem_ld32(taddr + half * (BLOCK_N / 2), r);
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) {
           tmem_ld_wait();
-          if (ch + 1 < NCH) tmem_ld32(taddr + half * (BLOCK_N / 2) + (ch + 1) * 32, r[(ch + 1) & 1]);
           float t[32];
-          transpose_chunk(r[ch & 1], t, stage, lane);
+          transpose_chunk(r, t, stage, lane);
+          if (ch + 1 < NCH) tmem_ld32(taddr + half * (BLOCK_N / 2) + (ch + 1) * 32, r);
           const int n = n0 + half * (BLOCK_N / 2) + ch * 32 + lcol;
-          if (n < N) {
-#pragma unroll
-            for (int it = 0; it < 16; ++it) {
-              const int m = mbase + 2 * it;
-              if (m < M) epi_pair<EPI, __nv_bfloat16>(e, m, n, t[2 * it], t[2 * it + 1]);
-            }
-          }
+          if (n < N) epi_chunk_cols<EPI, __nv_bfloat16>(e, mbase, n, t, M);
         }
       }
       tc_fence_before();
@@ -347,7 +336,7 @@ inline int epi_mode_env() {
 template <int BLOCK_N, int EPI, bool A_MN, bool B_MN>
 int launch_cfg(const db200_gemm_params& p, cudaStream_t st) {
   const int env = epi_mode_env();
-  const bool cols = env == 2 || (env == 0 && EPI == DB200_EPI_GEGLU);
+  const bool cols = env == 2 || (env == 0 && (EPI == DB200_EPI_GEGLU || EPI == DB200_EPI_RESID));   // measured, see profiles/
   if (cols) return launch_cfg_mode<BLOCK_N, EPI, A_MN, B_MN, true>(p, st);
   return launch_cfg_mode<BLOCK_N, EPI, A_MN, B_MN, false>(p, st);
 }

@@ -261,6 +261,16 @@ def scale_bwd(d_out, y, scale, sign, dtype, want_dscale=True, want_dbias=True):
     return dy, dscale, dbias
 
 
+def geglu_bwd(dh, u, want_dbias=True):
+    """dh [M,H], u [M,2H] -> (du [M,2H], db1 [2H] fp32 | None): streaming GEGLU adjoint + bias gradient in one pass"""
+    M, H = dh.shape
+    du = torch.empty_like(u)
+    db = torch.zeros(2 * H, device=dh.device, dtype=torch.float32) if want_dbias else None
+    _lib.check(_lib.lib().dalle_b200_geglu_bwd(_p(_c(dh)), _p(_c(u)), _p(du), _p(db), dt_code(dh.dtype), M, H, _stream()), 'geglu_bwd')
+    _count()
+    return du, db
+
+
 def colsum(x):
     rows, cols = x.shape
     out = torch.zeros(cols, device=x.device, dtype=torch.float32)

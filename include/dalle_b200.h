@@ -198,6 +198,10 @@ int dalle_b200_scale_bwd(const db200_scale_bwd_params* p, void* stream);
 /* column sums: out[c] += sum_m x[m,c]  (bias gradient of net.0, transformer.py:114) */
 int dalle_b200_colsum(const void* x, int dtype, int rows, int cols, float* out, void* stream);
 
+/* GEGLU adjoint as a streaming pass: dh [rows, hidden], u = [a|g] [rows, 2*hidden] -> du [rows, 2*hidden] (dtype);
+ * dbias [2*hidden] fp32 (optional, +=) receives the column sums of du = gradient of net.0.bias (transformer.py:106-115) */
+int dalle_b200_geglu_bwd(const void* dh, const void* u, void* du, float* dbias, int dtype, int rows, int hidden, void* stream);
+
 /* fp32 -> bf16 cast of `count` elements (weights are kept in fp32 and cast once per step) */
 int dalle_b200_cast_bf16(const float* src, void* dst, int64_t count, void* stream);
 

@@ -143,6 +143,11 @@ def test_gemm_resid_geglu_epilogues(dtype):
     uf = u.float().requires_grad_()
     (uf[:, :H] * F.gelu(uf[:, H:])).backward(dh)
     report('geglu_bwd du', du, uf.grad, **tol)
+    # the same adjoint as a streaming pass (plain dgrad GEMM + dalle_b200_geglu_bwd), with the bias gradient
+    dh_t = o.gemm_store(dy, W2, a_mn=False, b_mn=True)
+    du2, db1 = o.geglu_bwd(dh_t, u)
+    report('geglu_bwd (streaming) du', du2, uf.grad, **tol)
+    report('geglu_bwd (streaming) db1', db1, uf.grad.sum(0), rtol=2e-2, atol=2e-2 * float(uf.grad.sum(0).abs().max()) + 1e-4)
 
 
 # ---- attention ----------------------------------------------------------------------------------------------
