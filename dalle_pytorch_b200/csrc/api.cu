@@ -40,6 +40,8 @@ int ln_shift_fwd_launch(const db200_ln_shift_fwd_params& P, cudaStream_t st);
 int ln_shift_bwd_launch(const db200_ln_shift_bwd_params& P, cudaStream_t st);
 int scale_bwd_launch(const db200_scale_bwd_params& P, cudaStream_t st);
 int colsum_launch(const void* x, int dtype, int rows, int cols, float* out, cudaStream_t st);
+int ce_fwd_launch(const void* logits, int dtype, int rows, int vocab, const long long* labels, float coef, float* row_lse, float* loss_acc, cudaStream_t st);
+int ce_bwd_launch(void* logits, int dtype, int rows, int vocab, const long long* labels, float coef, const float* row_lse, const float* upstream, cudaStream_t st);
 int geglu_bwd_launch(const void* dh, const void* u, void* du, float* dbias, int dtype, int rows, int hidden, cudaStream_t st);
 int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st);
 int axpby_launch(const float* a, const float* b, float alpha, float* y, int64_t count, cudaStream_t st);
@@ -237,6 +239,21 @@ int dalle_b200_geglu_bwd(const void* dh, const void* u, void* du, float* dbias, 
   DB200_CHECK_ARG(dh && u && du && rows >= 0 && hidden > 0 && (hidden & 7) == 0 && dtype_ok(dtype), "geglu_bwd: bad args (hidden must be a multiple of 8)");
   DB200_CHECK_ARG(aligned16(dh) && aligned16(u) && aligned16(du), "geglu_bwd: tensors must be 16-byte aligned");
   return geglu_bwd_launch(dh, u, du, dbias, dtype, rows, hidden, (cudaStream_t)stream);
+}
+
+int dalle_b200_ce_fwd(const void* logits, int dtype, int rows, int vocab, const int64_t* labels, float coef, float* row_lse, float* loss_acc,
+                      void* stream) {
+  DB200_CHECK_ARG(logits && labels && row_lse && loss_acc && rows >= 0 && vocab > 0 && (vocab & 7) == 0 && dtype_ok(dtype),
+                  "ce_fwd: bad args (vocab must be a multiple of 8)");
+  DB200_CHECK_ARG(aligned16(logits), "ce_fwd: logits must be 16-byte aligned");
+  return ce_fwd_launch(logits, dtype, rows, vocab, reinterpret_cast<const long long*>(labels), coef, row_lse, loss_acc, (cudaStream_t)stream);
+}
+
+int dalle_b200_ce_bwd(void* logits, int dtype, int rows, int vocab, const int64_t* labels, float coef, const float* row_lse, const float* upstream,
+                      void* stream) {
+  DB200_CHECK_ARG(logits && labels && row_lse && upstream && rows >= 0 && vocab > 0 && (vocab & 7) == 0 && dtype_ok(dtype), "ce_bwd: bad args");
+  DB200_CHECK_ARG(aligned16(logits), "ce_bwd: logits must be 16-byte aligned");
+  return ce_bwd_launch(logits, dtype, rows, vocab, reinterpret_cast<const long long*>(labels), coef, row_lse, upstream, (cudaStream_t)stream);
 }
 
 int dalle_b200_cast_bf16(const float* src, void* dst, int64_t count, void* stream) {

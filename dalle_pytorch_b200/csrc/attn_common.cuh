@@ -96,9 +96,9 @@ __device__ __forceinline__ void mask_or_bit(Mask128& m, int pos, int t0) {
 }
 
 // bit b = may query i (absolute position) attend key k0 + b ;  keys >= n_k are never allowed
-__device__ __forceinline__ Mask128 attn_row_bits(const AttnGeom& g, int i, int k0, const uint8_t* km) {
+__device__ __forceinline__ Mask128 attn_row_bits(const AttnGeom& g, int i, int k0, const uint8_t* km, int width = 128) {
   Mask128 m = {{0u, 0u, 0u, 0u}};
-  const int kend = (k0 + 127 < g.n_k - 1) ? k0 + 127 : g.n_k - 1;
+  const int kend = (k0 + width - 1 < g.n_k - 1) ? k0 + width - 1 : g.n_k - 1;
   const int T = g.text_len, fm = g.fmap;
   switch (g.pattern) {
     case DB200_ATTN_FULL:
@@ -146,9 +146,9 @@ __device__ __forceinline__ Mask128 attn_row_bits(const AttnGeom& g, int i, int k
 }
 
 // bit b = may query q0 + b attend key j ;  queries >= n are never allowed (training: n_q == n_k == n, positions absolute)
-__device__ __forceinline__ Mask128 attn_col_bits(const AttnGeom& g, int j, int q0, int n) {
+__device__ __forceinline__ Mask128 attn_col_bits(const AttnGeom& g, int j, int q0, int n, int width = 128) {
   Mask128 m = {{0u, 0u, 0u, 0u}};
-  const int qend = (q0 + 127 < n - 1) ? q0 + 127 : n - 1;
+  const int qend = (q0 + width - 1 < n - 1) ? q0 + width - 1 : n - 1;
   const int T = g.text_len, fm = g.fmap;
   switch (g.pattern) {
     case DB200_ATTN_FULL:

@@ -344,37 +344,43 @@ __device__ __forceinline__ void store_grad_row(uint32_t taddr, bf16* dst, const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// dK, dV : CTA = 128 keys; transposed score tile (rows = keys, columns = queries) so that thread = key row.
-//   TMEM: S^T [0,128) | dP^T [128,256) | dV [256,320) | dK [320,384) | P^T bf16 [384,448) | dS^T bf16 [448,512)
+// Backward tiles are 128 rows x BW = 64 columns so that each kernel needs only 256 TMEM columns and ~64 KB of smem: TWO CTAs
+// run per SM and one CTA's softmax-backward overlaps the other's MMAs.  P / dS (bf16) are written over the first half of the
+// S / dP columns they were computed from (each thread only overwrites columns of its own row that it has already read).
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int BW = 64;
+constexpr int HALF_TILE = BW * DH * 2;            // one [64 x 64] bf16 tile = 8 KB
+
+// dK, dV : CTA = 128 keys; transposed score tile (rows = keys, columns = 64 queries) so that thread = key row.
+//   TMEM: S^T [0,64) (P^T bf16 aliased on [0,32)) | dP^T [64,128) (dS^T aliased on [64,96)) | dV [128,192) | dK [192,256)
 struct DkvSmem {
-  static constexpr int K_OFF = 0, V_OFF = TILE_BYTES, Q_OFF = 2 * TILE_BYTES, DO_OFF = 4 * TILE_BYTES;
-  static constexpr int STAT_OFF = 6 * TILE_BYTES;                 // lse*log2e [2][128], delta [2][128]
-  static constexpr int BAR_OFF = STAT_OFF + 4 * 128 * 4;
+  static constexpr int K_OFF = 0, V_OFF = TILE_BYTES, Q_OFF = 2 * TILE_BYTES, DO_OFF = 2 * TILE_BYTES + 2 * HALF_TILE;
+  static constexpr int STAT_OFF = 2 * TILE_BYTES + 4 * HALF_TILE;   // lse*log2e [2][64], delta [2][64]
+  static constexpr int BAR_OFF = STAT_OFF + 4 * BW * 4;
   static constexpr int TOTAL = BAR_OFF + 128 + 1024;
 };
 
-__global__ void __launch_bounds__(192, 1) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+__global__ void __launch_bounds__(192, 2) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                                                                BwdArgs P, AttnGeom g) {
   using L = DkvSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t sK = smem_u32(smem + L::K_OFF), sV = smem_u32(smem + L::V_OFF), sQ = smem_u32(smem + L::Q_OFF), sdO = smem_u32(smem + L::DO_OFF);
-  float* s_lse = reinterpret_cast<float*>(smem + L::STAT_OFF);      // [2][128]
-  float* s_delta = s_lse + 256;                                      // [2][128]
+  float* s_lse = reinterpret_cast<float*>(smem + L::STAT_OFF);      // [2][64]
+  float* s_delta = s_lse + 2 * BW;                                   // [2][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   const uint32_t kv_full = smem_u32(bars), q_full = smem_u32(bars + 1), q_empty = smem_u32(bars + 3);
   const uint32_t st_full = smem_u32(bars + 5), ps_ready = smem_u32(bars + 6), acc_done = smem_u32(bars + 7);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t TMEM_COLS = 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / P.heads, h = bh - b * P.heads;
   const int n = g.n_k, inner = P.heads * DH;
   const int k0 = blockIdx.x * TK, k1 = min(k0 + TK, n) - 1;
-  const int nqt = (n + TQ - 1) / TQ;
-  auto needed = [&](int qt) { return attn_tile_needed(g, qt * TQ, min(qt * TQ + TQ, n) - 1, k0, k1); };
+  const int nqt = (n + BW - 1) / BW;
+  auto needed = [&](int qt) { return attn_tile_needed(g, qt * BW, min(qt * BW + BW, n) - 1, k0, k1); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
@@ -388,7 +394,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dkv_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tSt = tmem, tdPt = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tPt = tmem + 384, tdSt = tmem + 448;
+  const uint32_t tSt = tmem, tdPt = tmem + 64, tdV = tmem + 128, tdK = tmem + 192, tPt = tmem, tdSt = tmem + 64;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -400,16 +406,16 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dkv_tc_kernel(const __grid_co
         if (!needed(qt)) continue;
         const int s = it & 1;
         mbar_wait(q_empty + 8 * s, ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(q_full + 8 * s, 2 * TILE_BYTES);
-        tma_load_2d(sQ + s * TILE_BYTES, &tmQ, q_full + 8 * s, 0, bh * n + qt * TQ);
-        tma_load_2d(sdO + s * TILE_BYTES, &tmdO, q_full + 8 * s, h * DH, b * n + qt * TQ);
+        mbar_expect_tx(q_full + 8 * s, 2 * HALF_TILE);
+        tma_load_2d(sQ + s * HALF_TILE, &tmQ, q_full + 8 * s, 0, bh * n + qt * BW);
+        tma_load_2d(sdO + s * HALF_TILE, &tmdO, q_full + 8 * s, h * DH, b * n + qt * BW);
         ++it;
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t IDESC_T = make_idesc_bf16(128, 128, false, false);   // S^T = K Q^T, dP^T = V dO^T
+      constexpr uint32_t IDESC_T = make_idesc_bf16(128, BW, false, false);    // S^T = K Q^T, dP^T = V dO^T
       constexpr uint32_t IDESC_G = make_idesc_bf16(128, 64, false, true);     // dV = P^T dO, dK = dS^T Q   (B N-major)
       mbar_wait(kv_full, 0);
       const uint64_t dk = make_smem_desc(sK, 16, 1024), dv = make_smem_desc(sV, 16, 1024);
@@ -419,7 +425,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dkv_tc_kernel(const __grid_co
         const int s = it & 1;
         mbar_wait(q_full + 8 * s, (it >> 1) & 1);
         tc_fence_after();
-        const uint64_t dq = make_smem_desc(sQ + s * TILE_BYTES, 16, 1024), ddo = make_smem_desc(sdO + s * TILE_BYTES, 16, 1024);
+        const uint64_t dq = make_smem_desc(sQ + s * HALF_TILE, 16, 1024), ddo = make_smem_desc(sdO + s * HALF_TILE, 16, 1024);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) umma_bf16(tSt, dk + 2 * k, dq + 2 * k, IDESC_T, k != 0);
 #pragma unroll
@@ -427,11 +433,11 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dkv_tc_kernel(const __grid_co
         umma_commit(st_full);
         mbar_wait(ps_ready, it & 1);
         tc_fence_after();
-        const uint64_t bq = make_smem_desc(sQ + s * TILE_BYTES, TILE_BYTES, 1024), bdo = make_smem_desc(sdO + s * TILE_BYTES, TILE_BYTES, 1024);
+        const uint64_t bq = make_smem_desc(sQ + s * HALF_TILE, HALF_TILE, 1024), bdo = make_smem_desc(sdO + s * HALF_TILE, HALF_TILE, 1024);
 #pragma unroll
-        for (int k = 0; k < TQ / 16; ++k) umma_bf16_ts(tdV, tPt + 8 * k, bdo + 128 * k, IDESC_G, (it | k) != 0);
+        for (int k = 0; k < BW / 16; ++k) umma_bf16_ts(tdV, tPt + 8 * k, bdo + 128 * k, IDESC_G, (it | k) != 0);
 #pragma unroll
-        for (int k = 0; k < TQ / 16; ++k) umma_bf16_ts(tdK, tdSt + 8 * k, bq + 128 * k, IDESC_G, (it | k) != 0);
+        for (int k = 0; k < BW / 16; ++k) umma_bf16_ts(tdK, tdSt + 8 * k, bq + 128 * k, IDESC_G, (it | k) != 0);
         umma_commit(q_empty + 8 * s);
         umma_commit(acc_done);
         ++it;
@@ -449,28 +455,26 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dkv_tc_kernel(const __grid_co
     for (int qt = 0; qt < nqt; ++qt) {
       if (!needed(qt)) continue;
       const int s = it & 1;
-      const int qq0 = qt * TQ, qq1 = min(qq0 + TQ, n) - 1;
-      {   // per-query statistics of this tile -> smem (this thread loads query `row` of the tile)
+      const int qq0 = qt * BW, qq1 = min(qq0 + BW, n) - 1;
+      if (row < BW) {   // per-query statistics of this tile -> smem
         const int qi = qq0 + row;
-        s_lse[s * 128 + row] = qi < n ? P.lse[(long long)bh * n + qi] * LOG2E : 0.f;
-        s_delta[s * 128 + row] = qi < n ? P.delta[(long long)bh * n + qi] : 0.f;
+        s_lse[s * BW + row] = qi < n ? P.lse[(long long)bh * n + qi] * LOG2E : 0.f;
+        s_delta[s * BW + row] = qi < n ? P.delta[(long long)bh * n + qi] : 0.f;
       }
       named_bar_sync(1, 128);
-      const bool full = (k1 - k0 == TK - 1) && (qq1 - qq0 == TQ - 1) && km == nullptr && attn_tile_full(g, qq0, qq1, k0, k1);
-      Mask128 mk = {{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}};
+      const bool full = (k1 - k0 == TK - 1) && (qq1 - qq0 == BW - 1) && km == nullptr && attn_tile_full(g, qq0, qq1, k0, k1);
+      Mask128 mk = {{0xffffffffu, 0xffffffffu, 0u, 0u}};
       if (!full) {
-        if (key_ok) mk = attn_col_bits(g, kj, qq0, n);
-        else mk.w[0] = mk.w[1] = mk.w[2] = mk.w[3] = 0u;
+        if (key_ok) mk = attn_col_bits(g, kj, qq0, n, BW);
+        else mk.w[0] = mk.w[1] = 0u;
       }
       mbar_wait(st_full, it & 1);
       tc_fence_after();
-      if (it > 0) {                               // previous dV/dK MMAs done reading P^T / dS^T
-        mbar_wait(acc_done, (it - 1) & 1);
-        tc_fence_after();
-      }
+      // (the MMAs of this tile were issued after the previous tile's dV/dK MMAs, which read P^T / dS^T from the columns
+      //  written below: the tensor pipe executes in order, so st_full also means those reads are complete)
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t mb = c == 0 ? mk.w[0] : c == 1 ? mk.w[1] : c == 2 ? mk.w[2] : mk.w[3];
+      for (int c = 0; c < BW / 32; ++c) {
+        const uint32_t mb = c == 0 ? mk.w[0] : mk.w[1];
         uint32_t pk[16], dk_[16];
         if (__all_sync(0xffffffffu, mb == 0u)) {
 #pragma unroll
@@ -480,8 +484,8 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dkv_tc_kernel(const __grid_co
           tmem_ld32(tSt + lane_off + c * 32, rs);
           tmem_ld32(tdPt + lane_off + c * 32, rd);
           tmem_ld_wait();
-          const float* ls = s_lse + s * 128 + c * 32;
-          const float* dl = s_delta + s * 128 + c * 32;
+          const float* ls = s_lse + s * BW + c * 32;
+          const float* dl = s_delta + s * BW + c * 32;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float p0 = ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -ls[2 * i]));
@@ -524,16 +528,16 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dkv_tc_kernel(const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// dQ : CTA = 128 queries, thread = query row.
-//   TMEM: S [0,128) | dP [128,256) | dS bf16 [256,320) | dQ [320,384)
+// dQ : CTA = 128 queries, thread = query row, 64-key tiles.
+//   TMEM: S [0,64) | dP [64,128) (dS bf16 aliased on [64,96)) | dQ [128,192)
 // ---------------------------------------------------------------------------------------------------------------
 struct DqSmem {
-  static constexpr int Q_OFF = 0, DO_OFF = TILE_BYTES, K_OFF = 2 * TILE_BYTES, V_OFF = 4 * TILE_BYTES;
-  static constexpr int BAR_OFF = 6 * TILE_BYTES;
+  static constexpr int Q_OFF = 0, DO_OFF = TILE_BYTES, K_OFF = 2 * TILE_BYTES, V_OFF = 2 * TILE_BYTES + 2 * HALF_TILE;
+  static constexpr int BAR_OFF = 2 * TILE_BYTES + 4 * HALF_TILE;
   static constexpr int TOTAL = BAR_OFF + 128 + 1024;
 };
 
-__global__ void __launch_bounds__(192, 1) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+__global__ void __launch_bounds__(192, 2) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                                                               BwdArgs P, AttnGeom g) {
   using L = DqSmem;
@@ -544,14 +548,14 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dq_tc_kernel(const __grid_con
   const uint32_t q_full = smem_u32(bars), kv_full = smem_u32(bars + 1), kv_empty = smem_u32(bars + 3);
   const uint32_t s_full = smem_u32(bars + 5), ds_ready = smem_u32(bars + 6), acc_done = smem_u32(bars + 7);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t TMEM_COLS = 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / P.heads, h = bh - b * P.heads;
   const int n = g.n_k, inner = P.heads * DH;
   const int q0 = blockIdx.x * TQ, q1 = min(q0 + TQ, n) - 1;
-  const int nkt = (n + TK - 1) / TK;
-  auto needed = [&](int kt) { return attn_tile_needed(g, q0, q1, kt * TK, min(kt * TK + TK, n) - 1); };
+  const int nkt = (n + BW - 1) / BW;
+  auto needed = [&](int kt) { return attn_tile_needed(g, q0, q1, kt * BW, min(kt * BW + BW, n) - 1); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
@@ -565,7 +569,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dq_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tdP = tmem + 128, tdS = tmem + 256, tdQ = tmem + 320;
+  const uint32_t tS = tmem, tdP = tmem + 64, tdS = tmem + 64, tdQ = tmem + 128;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -577,16 +581,16 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dq_tc_kernel(const __grid_con
         if (!needed(kt)) continue;
         const int s = it & 1;
         mbar_wait(kv_empty + 8 * s, ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(kv_full + 8 * s, 2 * TILE_BYTES);
-        tma_load_2d(sK + s * TILE_BYTES, &tmK, kv_full + 8 * s, 0, bh * n + kt * TK);
-        tma_load_2d(sV + s * TILE_BYTES, &tmV, kv_full + 8 * s, 0, bh * n + kt * TK);
+        mbar_expect_tx(kv_full + 8 * s, 2 * HALF_TILE);
+        tma_load_2d(sK + s * HALF_TILE, &tmK, kv_full + 8 * s, 0, bh * n + kt * BW);
+        tma_load_2d(sV + s * HALF_TILE, &tmV, kv_full + 8 * s, 0, bh * n + kt * BW);
         ++it;
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t IDESC_S = make_idesc_bf16(128, BW, false, false);
       constexpr uint32_t IDESC_G = make_idesc_bf16(128, 64, false, true);
       mbar_wait(q_full, 0);
       const uint64_t dq = make_smem_desc(sQ, 16, 1024), ddo = make_smem_desc(sdO, 16, 1024);
@@ -596,7 +600,7 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dq_tc_kernel(const __grid_con
         const int s = it & 1;
         mbar_wait(kv_full + 8 * s, (it >> 1) & 1);
         tc_fence_after();
-        const uint64_t dk = make_smem_desc(sK + s * TILE_BYTES, 16, 1024), dv = make_smem_desc(sV + s * TILE_BYTES, 16, 1024);
+        const uint64_t dk = make_smem_desc(sK + s * HALF_TILE, 16, 1024), dv = make_smem_desc(sV + s * HALF_TILE, 16, 1024);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
 #pragma unroll
@@ -604,9 +608,9 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dq_tc_kernel(const __grid_con
         umma_commit(s_full);
         mbar_wait(ds_ready, it & 1);
         tc_fence_after();
-        const uint64_t bk = make_smem_desc(sK + s * TILE_BYTES, TILE_BYTES, 1024);
+        const uint64_t bk = make_smem_desc(sK + s * HALF_TILE, HALF_TILE, 1024);
 #pragma unroll
-        for (int k = 0; k < TK / 16; ++k) umma_bf16_ts(tdQ, tdS + 8 * k, bk + 128 * k, IDESC_G, (it | k) != 0);
+        for (int k = 0; k < BW / 16; ++k) umma_bf16_ts(tdQ, tdS + 8 * k, bk + 128 * k, IDESC_G, (it | k) != 0);
         umma_commit(kv_empty + 8 * s);
         umma_commit(acc_done);
         ++it;
@@ -624,22 +628,18 @@ __global__ void __launch_bounds__(192, 1) attn_bwd_dq_tc_kernel(const __grid_con
     int it = 0;
     for (int kt = 0; kt < nkt; ++kt) {
       if (!needed(kt)) continue;
-      const int k0 = kt * TK, k1 = min(k0 + TK, n) - 1;
-      const bool full = (k1 - k0 == TK - 1) && km == nullptr && attn_tile_full(g, q0, q1, k0, k1);
-      Mask128 mk = {{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}};
+      const int k0 = kt * BW, k1 = min(k0 + BW, n) - 1;
+      const bool full = (k1 - k0 == BW - 1) && km == nullptr && attn_tile_full(g, q0, q1, k0, k1);
+      Mask128 mk = {{0xffffffffu, 0xffffffffu, 0u, 0u}};
       if (!full) {
-        if (qi < n) mk = attn_row_bits(g, qi, k0, km);
-        else mk.w[0] = mk.w[1] = mk.w[2] = mk.w[3] = 0u;
+        if (qi < n) mk = attn_row_bits(g, qi, k0, km, BW);
+        else mk.w[0] = mk.w[1] = 0u;
       }
       mbar_wait(s_full, it & 1);
       tc_fence_after();
-      if (it > 0) {
-        mbar_wait(acc_done, (it - 1) & 1);
-        tc_fence_after();
-      }
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t mb = c == 0 ? mk.w[0] : c == 1 ? mk.w[1] : c == 2 ? mk.w[2] : mk.w[3];
+      for (int c = 0; c < BW / 32; ++c) {
+        const uint32_t mb = c == 0 ? mk.w[0] : mk.w[1];
         uint32_t dk_[16];
         if (__all_sync(0xffffffffu, mb == 0u)) {
 #pragma unroll
@@ -731,14 +731,19 @@ int attn_bwd_tc_launch(const db200_attn_bwd_params& p, cudaStream_t st) {
   const db200_attn_fwd_params& f = p.f;
   const int n = f.n_k;
   if (!al16(p.d_out) || !al16(p.dqkv)) return set_error(DB200_ERR_BAD_ARG, "attn_bwd: d_out / dqkv must be 16-byte aligned");
-  CUtensorMap tmQ, tmK, tmV, tmdO;
+  // 128-row boxes for the CTA's own rows, 64-row boxes for the streamed column tiles
+  CUtensorMap tmQ128, tmK128, tmV128, tmdO128, tmQ64, tmK64, tmV64, tmdO64;
   const uint64_t bh = (uint64_t)f.batch * f.heads;
   const uint64_t inner = (uint64_t)f.heads * DH;
   int rc;
-  if ((rc = make_tensor_map_bf16(&tmQ, f.q, DH, bh * n, DH, DH, TQ))) return rc;
-  if ((rc = make_tensor_map_bf16(&tmK, f.k, DH, bh * n, DH, DH, TK))) return rc;
-  if ((rc = make_tensor_map_bf16(&tmV, f.v, DH, bh * n, DH, DH, TK))) return rc;
-  if ((rc = make_tensor_map_bf16(&tmdO, p.d_out, inner, (uint64_t)f.batch * n, inner, DH, TQ))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmQ128, f.q, DH, bh * n, DH, DH, 128))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmK128, f.k, DH, bh * n, DH, DH, 128))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmV128, f.v, DH, bh * n, DH, DH, 128))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmdO128, p.d_out, inner, (uint64_t)f.batch * n, inner, DH, 128))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmQ64, f.q, DH, bh * n, DH, DH, BW))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmK64, f.k, DH, bh * n, DH, DH, BW))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmV64, f.v, DH, bh * n, DH, DH, BW))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmdO64, p.d_out, inner, (uint64_t)f.batch * n, inner, DH, BW))) return rc;
   static bool attr_done = false;
   if (!attr_done) {
     DB200_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::TOTAL));
@@ -752,9 +757,9 @@ int attn_bwd_tc_launch(const db200_attn_bwd_params& p, cudaStream_t st) {
   BwdArgs A{f.lse, p.delta, f.key_mask, p.cos_t, p.sin_t, p.q_scale, reinterpret_cast<bf16*>(p.dqkv), f.heads, f.batch};
   const AttnGeom g = make_geom(f);
   dim3 grid(ceil_div(n, TQ), f.batch * f.heads);
-  attn_bwd_dkv_tc_kernel<<<grid, 192, DkvSmem::TOTAL, st>>>(tmQ, tmK, tmV, tmdO, A, g);
+  attn_bwd_dkv_tc_kernel<<<grid, 192, DkvSmem::TOTAL, st>>>(tmQ64, tmK128, tmV128, tmdO64, A, g);
   DB200_LAUNCH_OK("attn_bwd_dkv_tc_kernel");
-  attn_bwd_dq_tc_kernel<<<grid, 192, DqSmem::TOTAL, st>>>(tmQ, tmK, tmV, tmdO, A, g);
+  attn_bwd_dq_tc_kernel<<<grid, 192, DqSmem::TOTAL, st>>>(tmQ128, tmK64, tmV64, tmdO128, A, g);
   DB200_LAUNCH_OK("attn_bwd_dq_tc_kernel");
   return DB200_OK;
 }

@@ -459,6 +459,68 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const T* __restrict__ dh
   }
 }
 
+// ---- logits head: cross-entropy over rows of [rows, vocab] logits (dalle_pytorch.py:667-670) -----------------------------
+// One 256-thread block per row, single pass with per-thread online (max, sum) pairs merged by shuffles: the logits are read
+// once.  loss_acc += coef * (lse - logit[label]);  row_lse is kept for the backward pass.
+__device__ __forceinline__ void ms_merge(float& m, float& s, float m2, float s2) {
+  const float mn = fmaxf(m, m2);
+  s = s * __expf(m - mn) + s2 * __expf(m2 - mn);
+  m = mn;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ logits, const long long* __restrict__ labels, int vocab,
+                                                     float coef, float* __restrict__ row_lse, float* __restrict__ loss_acc) {
+  __shared__ float sm_m[8], sm_s[8];
+  const int r = blockIdx.x;
+  const T* row = logits + (long long)r * vocab;
+  float m = -1.0e30f, s = 0.f;
+  for (int j = threadIdx.x * 8; j < vocab; j += 256 * 8) {
+    float v[8];
+    Vec8<T>::load(row + j, v);
+    float mx = v[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, v[i]);
+    const float mn = fmaxf(m, mx);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += __expf(v[i] - mn);
+    s = s * __expf(m - mn) + acc;
+    m = mn;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    ms_merge(m, s, m2, s2);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sm_m[w] = m; sm_s[w] = s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) ms_merge(m, s, sm_m[i], sm_s[i]);
+    const float lse = m + logf(s);
+    row_lse[r] = lse;
+    const float tgt = to_f32(row[labels[r]]);
+    atomicAdd(loss_acc, coef * (lse - tgt));
+  }
+}
+// d logits = upstream * coef * (softmax - onehot), written in place over the logits buffer
+template <typename T>
+__global__ void __launch_bounds__(256) ce_bwd_kernel(T* __restrict__ logits, const long long* __restrict__ labels, int vocab, float coef,
+                                                     const float* __restrict__ row_lse, const float* __restrict__ upstream) {
+  const int r = blockIdx.x;
+  T* row = logits + (long long)r * vocab;
+  const float lse = row_lse[r];
+  const float gsc = coef * __ldg(upstream);
+  const int lab = (int)labels[r];
+  for (int j = threadIdx.x * 8; j < vocab; j += 256 * 8) {
+    float v[8];
+    Vec8<T>::load(row + j, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = gsc * (__expf(v[i] - lse) - ((j + i) == lab ? 1.f : 0.f));
+    Vec8<T>::store(row + j, v);
+  }
+}
+
 constexpr int CS_ROWS = 512;
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int rows, int cols, float* __restrict__ out) {
@@ -597,6 +659,23 @@ int geglu_bwd_launch(const void* dh, const void* u, void* du, float* dbias, int 
     geglu_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dh), reinterpret_cast<const __nv_bfloat16*>(u),
                                                           reinterpret_cast<__nv_bfloat16*>(du), dbias, rows, hidden);
   DB200_LAUNCH_OK("geglu_bwd_kernel");
+  return DB200_OK;
+}
+
+int ce_fwd_launch(const void* logits, int dtype, int rows, int vocab, const long long* labels, float coef, float* row_lse, float* loss_acc,
+                  cudaStream_t st) {
+  if (rows == 0) return DB200_OK;
+  if (dtype == DB200_F32) ce_fwd_kernel<float><<<rows, 256, 0, st>>>(reinterpret_cast<const float*>(logits), labels, vocab, coef, row_lse, loss_acc);
+  else ce_fwd_kernel<__nv_bfloat16><<<rows, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(logits), labels, vocab, coef, row_lse, loss_acc);
+  DB200_LAUNCH_OK("ce_fwd_kernel");
+  return DB200_OK;
+}
+int ce_bwd_launch(void* logits, int dtype, int rows, int vocab, const long long* labels, float coef, const float* row_lse, const float* upstream,
+                  cudaStream_t st) {
+  if (rows == 0) return DB200_OK;
+  if (dtype == DB200_F32) ce_bwd_kernel<float><<<rows, 256, 0, st>>>(reinterpret_cast<float*>(logits), labels, vocab, coef, row_lse, upstream);
+  else ce_bwd_kernel<__nv_bfloat16><<<rows, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(logits), labels, vocab, coef, row_lse, upstream);
+  DB200_LAUNCH_OK("ce_bwd_kernel");
   return DB200_OK;
 }
 

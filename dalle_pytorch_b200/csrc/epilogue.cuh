@@ -9,7 +9,7 @@ namespace db200 {
 struct EpiArgs {
   int M, N;
   // STORE
-  void* C; long long ldc; int c_is_f32; const float* bias;
+  void* C; long long ldc; int c_is_f32; const float* bias; int atomic_c;
   // QKV
   void* q; void* k; void* v; const float* cos_t; const float* sin_t;
   int seq_n, heads, dim_head, pos_offset; float q_scale;
@@ -22,7 +22,7 @@ struct EpiArgs {
 inline EpiArgs make_epi_args(const db200_gemm_params& p) {
   EpiArgs e;
   e.M = p.M; e.N = p.N;
-  e.C = p.C; e.ldc = p.ldc; e.c_is_f32 = (p.c_dtype == DB200_F32); e.bias = p.bias;
+  e.C = p.C; e.ldc = p.ldc; e.c_is_f32 = (p.c_dtype == DB200_F32); e.bias = p.bias; e.atomic_c = 0;
   e.q = p.q; e.k = p.k; e.v = p.v; e.cos_t = p.cos_t; e.sin_t = p.sin_t;
   e.seq_n = p.seq_n; e.heads = p.heads; e.dim_head = p.dim_head; e.pos_offset = p.pos_offset; e.q_scale = p.q_scale;
   e.resid = p.resid; e.scale = p.scale; e.sign = p.sign; e.y_out = p.y_out; e.out = p.out;
@@ -160,7 +160,11 @@ __device__ __forceinline__ void epi_vec8(const EpiArgs& e, int m, int n, float* 
       for (int i = 0; i < 8; ++i) v[i] += bb[i];
     }
     const long long off = (long long)m * e.ldc + n;
-    if (e.c_is_f32) Vec8<float>::store(reinterpret_cast<float*>(e.C) + off, v);
+    if (e.atomic_c) {                                  // split-K partial sum (fp32 C, zero-initialised by the caller)
+      float* c = reinterpret_cast<float*>(e.C) + off;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(c + i, v[i]);
+    } else if (e.c_is_f32) Vec8<float>::store(reinterpret_cast<float*>(e.C) + off, v);
     else Vec8<T>::store(reinterpret_cast<T*>(e.C) + off, v);
   } else if constexpr (EPI == DB200_EPI_QKV) {
     const int inner = e.heads * e.dim_head;
@@ -262,7 +266,8 @@ __device__ __forceinline__ void epi_chunk_cols(const EpiArgs& e, int mbase, int 
       const int m = mbase + 2 * it;
       if (m < M) {
         const long long off = (long long)m * e.ldc + n;
-        if (e.c_is_f32) store2<float>(reinterpret_cast<float*>(e.C) + off, t[2 * it] + b0, t[2 * it + 1] + b1);
+        if (e.atomic_c) { atomicAdd(reinterpret_cast<float*>(e.C) + off, t[2 * it]); atomicAdd(reinterpret_cast<float*>(e.C) + off + 1, t[2 * it + 1]); }
+        else if (e.c_is_f32) store2<float>(reinterpret_cast<float*>(e.C) + off, t[2 * it] + b0, t[2 * it + 1] + b1);
         else store2<T>(reinterpret_cast<T*>(e.C) + off, t[2 * it] + b0, t[2 * it + 1] + b1);
       }
     }

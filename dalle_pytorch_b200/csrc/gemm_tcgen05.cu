@@ -72,7 +72,8 @@ struct SmemLayout {
 template <int BLOCK_N, int EPI, bool A_MN, bool B_MN, bool EPI_COLS>
 // 320 threads are allocated as 12 warps of registers (4-warp granularity) -> 168 registers per thread at most
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, EpiArgs e) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, int k_splits,
+                    EpiArgs e) {
   using L = SmemLayout<BLOCK_N>;
   constexpr int STAGES = L::STAGES;
   constexpr int B_STAGE_BYTES = L::B_STAGE_BYTES;
@@ -111,17 +112,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
   const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = num_m * num_n;
-  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int num_mn = num_m * num_n;
+  const int num_tiles = num_mn * k_splits;                    // split-K: tile = (split, n, m); partial sums are reduced with
+  const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;           // fp32 red.global.add in the STORE epilogue (C pre-zeroed)
+  const int kb_per = (total_kb + k_splits - 1) / k_splits;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % num_m) * BLOCK_M;
-        const int n0 = (tile / num_m) * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int mn = tile % num_mn, split = tile / num_mn;
+        const int m0 = (mn % num_m) * BLOCK_M;
+        const int n0 = (mn / num_m) * BLOCK_N;
+        const int kb0 = split * kb_per, kb1 = min(total_kb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + 8 * s, ph ^ 1);
           const uint32_t fb = full_bar + 8 * s;
           mbar_expect_tx(fb, L::STAGE_BYTES);
@@ -168,16 +173,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(tempty_bar + 8 * as, aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int split = tile / num_mn;
+        const int kb0 = split * kb_per, kb1 = min(total_kb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar + 8 * s, ph);
           tc_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES), A_LBO, 1024);
           const uint64_t db = make_smem_desc(smem_u32(smem_b + s * B_STAGE_BYTES), B_LBO, 1024);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_bf16(tmem_c, da + static_cast<uint64_t>(k * A_KSTEP), db + static_cast<uint64_t>(k * B_KSTEP), idesc, (kb | k) != 0);
+            umma_bf16(tmem_c, da + static_cast<uint64_t>(k * A_KSTEP), db + static_cast<uint64_t>(k * B_KSTEP), idesc, (kb > kb0) || (k != 0));
           umma_commit(empty_bar + 8 * s);                    // smem stage free once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(tfull_bar + 8 * as);   // accumulator complete
+          if (kb == kb1 - 1) umma_commit(tfull_bar + 8 * as);   // accumulator complete
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         if (++as == 2) { as = 0; aph ^= 1; }
@@ -193,8 +200,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int lrow = lane >> 4, lcol = (lane & 15) << 1;
     int as = 0; uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % num_m) * BLOCK_M;
-      const int n0 = (tile / num_m) * BLOCK_N;
+      const int mn = tile % num_mn;
+      const int m0 = (mn % num_m) * BLOCK_M;
+      const int n0 = (mn / num_m) * BLOCK_N;
       const int mbase = m0 + quarter * 32 + lrow;            // + 2*it
       mbar_wait(tfull_bar + 8 * as, aph);
       tc_fence_after();
@@ -313,10 +321,21 @@ int launch_cfg_mode(const db200_gemm_params& p, cudaStream_t st) {
     DB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_done = true;
   }
-  const int num_tiles = ceil_div(p.M, BLOCK_M) * ceil_div(p.N, BLOCK_N);
+  const int num_mn = ceil_div(p.M, BLOCK_M) * ceil_div(p.N, BLOCK_N);
+  // split-K only where the reduction is free to express: fp32 STORE without bias into a buffer the caller has zeroed
+  int k_splits = 1;
+  if (EPI == DB200_EPI_STORE && p.split_k_ok && p.c_dtype == DB200_F32 && p.bias == nullptr) {
+    const int total_kb = ceil_div(p.K, BLOCK_K);
+    k_splits = sm_count() / num_mn;
+    if (k_splits > 8) k_splits = 8;
+    if (k_splits > total_kb / 8) k_splits = total_kb / 8;       // keep >= 8 k-blocks per split
+    if (k_splits < 1) k_splits = 1;
+  }
+  const int num_tiles = num_mn * k_splits;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  const EpiArgs e = make_epi_args(p);
-  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(tmA, tmB, p.M, p.N, p.K, e);
+  EpiArgs e = make_epi_args(p);
+  e.atomic_c = k_splits > 1;
+  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(tmA, tmB, p.M, p.N, p.K, k_splits, e);
   DB200_LAUNCH_OK("gemm_tcgen05_kernel");
   return DB200_OK;
 }

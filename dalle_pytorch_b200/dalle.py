@@ -267,6 +267,16 @@ class DALLE(nn.Module):
         positions — the same numbers with 2.1x fewer head FLOPs and no [b, c, n] transposed softmax."""
         ln, lin = self.to_logits[0], self.to_logits[1]
         T, ntt = self.text_seq_len, self.num_text_tokens
+        n_img_ = seq_len - T
+        if out.is_cuda and ntt % 8 == 0 and self.num_image_tokens % 8 == 0 and out.shape[-1] % 8 == 0:
+            # library path: LayerNorm + both vocabulary GEMMs + cross-entropy as kernels (functional.HeadLossFn)
+            from .functional import HeadLossFn
+            from . import config
+            d_ = out.shape[-1]
+            x2 = torch.cat((out[:, :T].reshape(-1, d_), out[:, T:seq_len].reshape(-1, d_)), dim=0).float()
+            return HeadLossFn.apply(x2, ln.weight, ln.bias, lin.weight, lin.bias, text[:, 1:T + 1].reshape(-1).contiguous(),
+                                    image[:, :n_img_].reshape(-1).contiguous(), ntt, float(self.loss_img_weight),
+                                    config.compute_dtype(), ln.eps)
         h = ln(out)
         labels_text = text[:, 1:]                                  # text already carries <bos> at index 0
         d = h.shape[-1]

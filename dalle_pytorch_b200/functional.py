@@ -224,3 +224,60 @@ class LayerNormFn(torch.autograd.Function):
         dx = ops.ln_shift_bwd(d_out.contiguous().view(-1, d).float(), x3, mean, rstd, w, None, 0, 1, do_ln=True, do_shift=False,
                               dgamma=dw, dbeta=db)
         return dx.view(d_out.shape), dw, db, None
+
+
+class HeadLossFn(torch.autograd.Function):
+    """to_logits (LayerNorm + Linear) + the weighted text/image cross-entropy of dalle_pytorch.py:644-671 on the library
+    kernels, restricted to the live vocabulary of each position class (see DALLE._loss_head): rows of `x` must be ordered
+    [all text positions | all image positions].
+        loss = (CE_text + w * CE_img) / (w + 1)
+    forward : ln_shift_fwd -> 2 GEMMs (+bias) -> ce_fwd (one pass, keeps row log-sum-exp)
+    backward: ce_bwd (in place over the logits) -> dgrad / wgrad GEMMs + colsum -> ln_shift_bwd"""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w, bias, labels_text, labels_img, ntt, w_img, dtype, eps):
+        M, d = x.shape
+        Rt, Ri = labels_text.numel(), labels_img.numel()
+        assert Rt + Ri == M
+        x3 = x.contiguous().view(1, M, d)
+        h, mean, rstd = ops.ln_shift_fwd(x3, ln_w, ln_b, dtype, 0, 1, do_ln=True, do_shift=False, eps=eps)
+        wc = _w(w, dtype)
+        bias = bias.detach()
+        loss = torch.zeros(1, device=x.device, dtype=torch.float32)
+        ct, ci = 1.0 / ((w_img + 1) * max(Rt, 1)), w_img / ((w_img + 1) * max(Ri, 1))
+        lt = li = lse_t = lse_i = None
+        if Rt:
+            lt = ops.gemm_store(h[:Rt], wc[:ntt], bias=bias[:ntt])
+            lse_t = ops.ce_fwd(lt, labels_text, ct, loss)
+        if Ri:
+            li = ops.gemm_store(h[Rt:], wc[ntt:], bias=bias[ntt:])
+            lse_i = ops.ce_fwd(li, labels_img, ci, loss)
+        ctx.saved = (x3, mean, rstd, h, wc, lt, li, lse_t, lse_i, labels_text, labels_img, ln_w)
+        ctx.cfg = (ntt, ct, ci, Rt, Ri)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        x3, mean, rstd, h, wc, lt, li, lse_t, lse_i, labels_text, labels_img, ln_w = ctx.saved
+        ctx.saved = None
+        ntt, ct, ci, Rt, Ri = ctx.cfg
+        M, d = h.shape
+        V = wc.shape[0]
+        up = dloss.detach().reshape(1).float().contiguous()
+        dh = torch.empty(M, d, device=h.device, dtype=h.dtype)
+        dw = torch.zeros(V, d, device=h.device, dtype=torch.float32) if (not Rt or not Ri) else torch.empty(V, d, device=h.device, dtype=torch.float32)
+        db = torch.zeros(V, device=h.device, dtype=torch.float32)
+        if Rt:
+            ops.ce_bwd_(lt, labels_text, ct, lse_t, up)
+            ops.gemm_store(lt, wc[:ntt], a_mn=False, b_mn=True, out=dh[:Rt])
+            ops.gemm_store(lt, h[:Rt], a_mn=True, b_mn=True, out=dw[:ntt])
+            db[:ntt] = ops.colsum(lt)
+        if Ri:
+            ops.ce_bwd_(li, labels_img, ci, lse_i, up)
+            ops.gemm_store(li, wc[ntt:], a_mn=False, b_mn=True, out=dh[Rt:])
+            ops.gemm_store(li, h[Rt:], a_mn=True, b_mn=True, out=dw[ntt:])
+            db[ntt:] = ops.colsum(li)
+        dln_w = torch.zeros(d, device=h.device, dtype=torch.float32)
+        dln_b = torch.zeros(d, device=h.device, dtype=torch.float32)
+        dx = ops.ln_shift_bwd(dh, x3, mean, rstd, ln_w, None, 0, 1, do_ln=True, do_shift=False, dgamma=dln_w, dbeta=dln_b)
+        return dx.view(M, d), dln_w, dln_b, dw, db, None, None, None, None, None, None

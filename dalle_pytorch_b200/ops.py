@@ -129,8 +129,9 @@ def _base(M, N, K, A, lda, a_mn, B, ldb, b_mn, epilogue, backend=GEMM_AUTO):
                            B=_p(B), ldb=ldb, b_mn_major=int(b_mn), epilogue=epilogue)
 
 
-def gemm_store(A, B, a_mn=False, b_mn=False, out_dtype=None, bias=None, backend=GEMM_AUTO):
-    """acc[M,N] = sum_k A(m,k) B(n,k).  A: [M,K] (a_mn=False) or [K,M] (a_mn=True); B: [N,K] or [K,N]."""
+def gemm_store(A, B, a_mn=False, b_mn=False, out_dtype=None, bias=None, backend=GEMM_AUTO, out=None):
+    """acc[M,N] = sum_k A(m,k) B(n,k).  A: [M,K] (a_mn=False) or [K,M] (a_mn=True); B: [N,K] or [K,N].
+    `out` (optional, contiguous [M,N]) receives the result instead of a fresh tensor."""
     _c(A), _c(B)
     if a_mn:
         K, M = A.shape
@@ -141,10 +142,18 @@ def gemm_store(A, B, a_mn=False, b_mn=False, out_dtype=None, bias=None, backend=
     else:
         N, Kb = B.shape
     assert K == Kb, (A.shape, B.shape, a_mn, b_mn)
-    out_dtype = out_dtype or A.dtype
-    C = torch.empty(M, N, device=A.device, dtype=out_dtype)
+    if out is not None:
+        assert out.shape == (M, N) and out.is_contiguous()
+        C, out_dtype = out, out.dtype
+    else:
+        out_dtype = out_dtype or A.dtype
+        C = None
+    # weight-gradient shapes (few output tiles, very long K): let the kernel split K; it needs a zeroed fp32 C
+    split_ok = out is None and out_dtype == torch.float32 and bias is None and A.dtype == torch.bfloat16 and M * N <= 4096 * 1024 and K >= 4096
+    if C is None:
+        C = (torch.zeros if split_ok else torch.empty)(M, N, device=A.device, dtype=out_dtype)
     P = _base(M, N, K, A, A.shape[1], a_mn, B, B.shape[1], b_mn, EPI_STORE, backend)
-    P.C, P.ldc, P.c_dtype, P.bias = _p(C), N, dt_code(out_dtype), _p(bias)
+    P.C, P.ldc, P.c_dtype, P.bias, P.split_k_ok = _p(C), N, dt_code(out_dtype), _p(bias), int(split_ok)
     _gemm(P)
     return C
 
@@ -269,6 +278,23 @@ def geglu_bwd(dh, u, want_dbias=True):
     _lib.check(_lib.lib().dalle_b200_geglu_bwd(_p(_c(dh)), _p(_c(u)), _p(du), _p(db), dt_code(dh.dtype), M, H, _stream()), 'geglu_bwd')
     _count()
     return du, db
+
+
+def ce_fwd(logits, labels, coef, loss_acc):
+    """logits [R,V], labels [R] int64; loss_acc (fp32 scalar tensor) += coef * sum(CE rows).  Returns row_lse [R]."""
+    R, V = logits.shape
+    lse = torch.empty(R, device=logits.device, dtype=torch.float32)
+    _lib.check(_lib.lib().dalle_b200_ce_fwd(_p(_c(logits)), dt_code(logits.dtype), R, V, _p(_c(labels)), coef, _p(lse), _p(loss_acc), _stream()), 'ce_fwd')
+    _count()
+    return lse
+
+
+def ce_bwd_(logits, labels, coef, row_lse, upstream):
+    """In place: logits <- upstream * coef * (softmax(logits) - onehot(labels)) (the gradient w.r.t. the logits)."""
+    R, V = logits.shape
+    _lib.check(_lib.lib().dalle_b200_ce_bwd(_p(_c(logits)), dt_code(logits.dtype), R, V, _p(_c(labels)), coef, _p(row_lse), _p(upstream), _stream()), 'ce_bwd')
+    _count()
+    return logits
 
 
 def colsum(x):

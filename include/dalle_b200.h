@@ -124,6 +124,7 @@ typedef struct {
   int epilogue;             /* db200_epilogue */
   /* STORE */
   void* C; int64_t ldc; int c_dtype; const float* bias;   /* bias [N] fp32 optional */
+  int split_k_ok;           /* STORE, fp32 C, no bias: C is zero-initialised, the kernel may split K and reduce with fp32 atomics */
   /* QKV: N = 3*heads*dim_head; rows m = b*seq_n + p */
   void* q; void* k; void* v;                 /* [batch, heads, seq_n, dim_head] (dtype)                  */
   const float* cos_t; const float* sin_t;    /* [n_pos, dim_head/2] fp32, (1,0) on pass-through pairs; NULL = no rotary */
@@ -201,6 +202,14 @@ int dalle_b200_colsum(const void* x, int dtype, int rows, int cols, float* out, 
 /* GEGLU adjoint as a streaming pass: dh [rows, hidden], u = [a|g] [rows, 2*hidden] -> du [rows, 2*hidden] (dtype);
  * dbias [2*hidden] fp32 (optional, +=) receives the column sums of du = gradient of net.0.bias (transformer.py:106-115) */
 int dalle_b200_geglu_bwd(const void* dh, const void* u, void* du, float* dbias, int dtype, int rows, int hidden, void* stream);
+
+/* Cross-entropy over the rows of logits [rows, vocab] (dtype) with int64 labels (F.cross_entropy, dalle_pytorch.py:667-668):
+ * fwd: row_lse[r] = logsumexp(logits[r,:]);  *loss_acc += coef * sum_r (row_lse[r] - logits[r, labels[r]])   (coef = weight/rows)
+ * bwd: logits[r,j] <- (*upstream) * coef * (exp(logits[r,j] - row_lse[r]) - [j == labels[r]])   IN PLACE (becomes d logits) */
+int dalle_b200_ce_fwd(const void* logits, int dtype, int rows, int vocab, const int64_t* labels, float coef, float* row_lse, float* loss_acc,
+                      void* stream);
+int dalle_b200_ce_bwd(void* logits, int dtype, int rows, int vocab, const int64_t* labels, float coef, const float* row_lse, const float* upstream,
+                      void* stream);
 
 /* fp32 -> bf16 cast of `count` elements (weights are kept in fp32 and cast once per step) */
 int dalle_b200_cast_bf16(const float* src, void* dst, int64_t count, void* stream);
