@@ -486,13 +486,22 @@ __global__ void __launch_bounds__(192, 2) attn_bwd_dkv_tc_kernel(const __grid_co
           tmem_ld_wait();
           const float* ls = s_lse + s * BW + c * 32;
           const float* dl = s_delta + s * BW + c * 32;
+          if (mb == 0xffffffffu) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0 = ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -ls[2 * i]));
-            float p1 = ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -ls[2 * i + 1]));
-            if (mb != 0xffffffffu) { p0 = sel_bit(mb, 2 * i, p0, 0.f); p1 = sel_bit(mb, 2 * i + 1, p1, 0.f); }
-            pk[i] = pack2(p0, p1);
-            dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - dl[2 * i]), p1 * (__uint_as_float(rd[2 * i + 1]) - dl[2 * i + 1]));
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -ls[2 * i]));
+              const float p1 = ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -ls[2 * i + 1]));
+              pk[i] = pack2(p0, p1);
+              dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - dl[2 * i]), p1 * (__uint_as_float(rd[2 * i + 1]) - dl[2 * i + 1]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = sel_bit(mb, 2 * i, ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -ls[2 * i])), 0.f);
+              const float p1 = sel_bit(mb, 2 * i + 1, ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -ls[2 * i + 1])), 0.f);
+              pk[i] = pack2(p0, p1);
+              dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - dl[2 * i]), p1 * (__uint_as_float(rd[2 * i + 1]) - dl[2 * i + 1]));
+            }
           }
         }
         tmem_st16(tPt + lane_off + c * 16, pk);
@@ -649,12 +658,20 @@ __global__ void __launch_bounds__(192, 2) attn_bwd_dq_tc_kernel(const __grid_con
           tmem_ld32(tS + lane_off + c * 32, rs);
           tmem_ld32(tdP + lane_off + c * 32, rd);
           tmem_ld_wait();
+          if (mb == 0xffffffffu) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0 = ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -lse_r));
-            float p1 = ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -lse_r));
-            if (mb != 0xffffffffu) { p0 = sel_bit(mb, 2 * i, p0, 0.f); p1 = sel_bit(mb, 2 * i + 1, p1, 0.f); }
-            dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - delta_r), p1 * (__uint_as_float(rd[2 * i + 1]) - delta_r));
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -lse_r));
+              const float p1 = ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -lse_r));
+              dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - delta_r), p1 * (__uint_as_float(rd[2 * i + 1]) - delta_r));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = sel_bit(mb, 2 * i, ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -lse_r)), 0.f);
+              const float p1 = sel_bit(mb, 2 * i + 1, ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -lse_r)), 0.f);
+              dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - delta_r), p1 * (__uint_as_float(rd[2 * i + 1]) - delta_r));
+            }
           }
         }
         tmem_st16(tdS + lane_off + c * 16, dk_);

@@ -33,6 +33,32 @@ __device__ __forceinline__ int shift_dest(int p, int c, int n, int d, int text_l
   return (cc + 1 < fmap && p + 1 < n) ? p + 1 : -1;
 }
 
+// Same mapping resolved ONCE per token row (one integer division), then applied per channel range with compares only: the
+// streaming kernels below are issue-bound, not HBM-bound, if the division is repeated for every 4-channel chunk (ncu, r01).
+struct ShiftRow {
+  int dest_q1, dest_q2;     // where channels [0,d/4) / [d/4,d/2) of this row go (-1 = dropped); channels >= d/2 stay
+  bool zero_q1, zero_q2;    // does this row receive nothing in those ranges (so zeros must be written)
+  int self;
+};
+__device__ __forceinline__ ShiftRow make_shift_row(int p, int n, int text_len, int fmap, int do_shift) {
+  ShiftRow s;
+  s.self = p;
+  if (!do_shift) { s.dest_q1 = s.dest_q2 = p; s.zero_q1 = s.zero_q2 = false; return s; }
+  if (p < text_len) {
+    s.dest_q1 = s.dest_q2 = (p + 1 < text_len) ? p + 1 : -1;
+    s.zero_q1 = s.zero_q2 = (p == 0);
+  } else {
+    const int q = p - text_len;
+    const int r = q / fmap, cc = q - r * fmap;
+    s.dest_q1 = (r + 1 < fmap && p + fmap < n) ? p + fmap : -1;
+    s.dest_q2 = (cc + 1 < fmap && p + 1 < n) ? p + 1 : -1;
+    s.zero_q1 = (r == 0);
+    s.zero_q2 = (cc == 0);
+  }
+  return s;
+}
+__device__ __forceinline__ int shift_row_dest(const ShiftRow& s, int c, int d) { return c >= (d >> 1) ? s.self : (c < (d >> 2) ? s.dest_q1 : s.dest_q2); }
+
 template <typename TO>
 __global__ void __launch_bounds__(LN_THREADS) ln_shift_fwd_kernel(db200_ln_shift_fwd_params P) {
   extern __shared__ float row[];
@@ -210,6 +236,7 @@ __global__ void __launch_bounds__(WR_WARPS * 32) ln_shift_fwd_warp_kernel(db200_
   }
   TO* out = reinterpret_cast<TO*>(P.out);
   const long long brow = (long long)b * n;
+  const ShiftRow sr = make_shift_row(p, n, P.text_len, P.fmap, P.do_shift);
 #pragma unroll
   for (int k = 0; k < NCH; ++k) {
     const int c = k * 128 + lane * 4;
@@ -222,94 +249,90 @@ __global__ void __launch_bounds__(WR_WARPS * 32) ln_shift_fwd_warp_kernel(db200_
       y.z = (y.z - mean) * rstd * g.z + be.z;
       y.w = (y.w - mean) * rstd * g.w + be.w;
     }
-    const int dest = shift_dest(p, c, n, d, P.text_len, P.fmap, P.do_shift);
+    const int dest = shift_row_dest(sr, c, d);
     if (dest >= 0) {
       TO* o = out + (brow + dest) * d + c;
       store2<TO>(o, y.x, y.y);
       store2<TO>(o + 2, y.z, y.w);
     }
-    if (P.do_shift && c < (d >> 1)) {
-      bool zero;
-      if (p < P.text_len) zero = (p == 0);
-      else {
-        const int q = p - P.text_len;
-        const int rr = q / P.fmap, cc = q - rr * P.fmap;
-        zero = (c < (d >> 2)) ? (rr == 0) : (cc == 0);
-      }
-      if (zero) {
-        TO* o = out + (brow + p) * d + c;
-        store2<TO>(o, 0.f, 0.f);
-        store2<TO>(o + 2, 0.f, 0.f);
-      }
+    if (c < (d >> 1) && ((c < (d >> 2)) ? sr.zero_q1 : sr.zero_q2)) {
+      TO* o = out + (brow + p) * d + c;
+      store2<TO>(o, 0.f, 0.f);
+      store2<TO>(o + 2, 0.f, 0.f);
     }
   }
 }
 
+// LayerNorm(+shift) backward is split in two streaming kernels so that neither needs many registers:
+//   (1) dx   : warp per row, single pass, row gradient and x_hat in registers (no cross-row state)  -> high occupancy
+//   (2) dgamma/dbeta : thread = 4 channels, block = 1024 channels x SLAB_ROWS rows, register partial sums, one atomic per
+//       channel and block.  (2) re-reads dA and x (126 MB at C2, ~20 us) which is cheaper than carrying 2*d/32 accumulators
+//       per lane through (1).
 template <typename TI, int NCH>
-__global__ void __launch_bounds__(WR_WARPS * 32, 2) ln_shift_bwd_warp_kernel(db200_ln_shift_bwd_params P) {
-  extern __shared__ float sm[];          // [2][d] block partials of dgamma / dbeta
+__global__ void __launch_bounds__(WR_WARPS * 32, 3) ln_shift_bwd_dx_kernel(db200_ln_shift_bwd_params P) {
+  // dgamma / dbeta partials of the whole (persistent) block live in shared memory; lanes add into bank-conflict-free slots
+  // ([k][j][lane]) with RED.shared, and the block issues ONE global atomic per channel at the end.
+  extern __shared__ float sm[];          // [2][d]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = P.n, d = P.d;
   const int rows = P.batch * n;
-  if (P.do_ln) {
+  const bool want_p = P.do_ln && P.dgamma != nullptr;
+  if (want_p) {
     for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
     __syncthreads();
   }
-  // Two passes per row keep the register footprint small (only the dgamma/dbeta partials persist across rows), so two
-  // blocks fit per SM; the second pass re-reads the row's 6 KB from L1/L2, not from HBM.
-  float4 ag[NCH], ab[NCH];
-#pragma unroll
-  for (int k = 0; k < NCH; ++k) { ag[k] = make_float4(0.f, 0.f, 0.f, 0.f); ab[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
-  const TI* dA = reinterpret_cast<const TI*>(P.d_out);
+  const TI* __restrict__ dA = reinterpret_cast<const TI*>(P.d_out);
   for (int r = blockIdx.x * WR_WARPS + warp; r < rows; r += gridDim.x * WR_WARPS) {
     const int b = r / n, p = r - b * n;
     const long long brow = (long long)b * n;
-    const float* xr = P.x + (long long)r * d;
+    const float* __restrict__ xr = P.x + (long long)r * d;
     float mean = 0.f, rstd = 1.f;
     if (P.do_ln) { mean = P.mean[r]; rstd = P.rstd[r]; }
-    int srcs[NCH];
+    float4 g[NCH], h[NCH];
     float s1 = 0.f, s2 = 0.f;
+    const ShiftRow sr = make_shift_row(p, n, P.text_len, P.fmap, P.do_shift);
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       const int c = k * 128 + lane * 4;
-      srcs[k] = shift_dest(p, c, n, d, P.text_len, P.fmap, P.do_shift);
-      if (P.do_ln) {
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (srcs[k] >= 0) {
-          const TI* gp = dA + (brow + srcs[k]) * d + c;
-          const float2 a = load2<TI>(gp), bb = load2<TI>(gp + 2);
-          g = make_float4(a.x, a.y, bb.x, bb.y);
-        }
-        const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+      const int src = shift_row_dest(sr, c, d);
+      g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src >= 0) {
+        const TI* gp = dA + (brow + src) * d + c;
+        const float2 a = load2<TI>(gp), bb = load2<TI>(gp + 2);
+        g[k] = make_float4(a.x, a.y, bb.x, bb.y);
+      }
+      h[k] = P.do_ln ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (P.do_ln) {
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int c = k * 128 + lane * 4;
         const float4 ga = __ldg(reinterpret_cast<const float4*>(P.gamma + c));
-        const float h0 = (xv.x - mean) * rstd, h1 = (xv.y - mean) * rstd, h2 = (xv.z - mean) * rstd, h3 = (xv.w - mean) * rstd;
-        ag[k].x += g.x * h0; ag[k].y += g.y * h1; ag[k].z += g.z * h2; ag[k].w += g.w * h3;
-        ab[k].x += g.x; ab[k].y += g.y; ab[k].z += g.z; ab[k].w += g.w;
-        g.x *= ga.x; g.y *= ga.y; g.z *= ga.z; g.w *= ga.w;
-        s1 += (g.x + g.y) + (g.z + g.w);
-        s2 += (g.x * h0 + g.y * h1) + (g.z * h2 + g.w * h3);
+        h[k] = make_float4((h[k].x - mean) * rstd, (h[k].y - mean) * rstd, (h[k].z - mean) * rstd, (h[k].w - mean) * rstd);
+        if (want_p) {
+          float* sg = sm + (k * 4) * 32 + lane;
+          float* sb = sm + d + (k * 4) * 32 + lane;
+          atomicAdd(sg, g[k].x * h[k].x); atomicAdd(sg + 32, g[k].y * h[k].y); atomicAdd(sg + 64, g[k].z * h[k].z); atomicAdd(sg + 96, g[k].w * h[k].w);
+          atomicAdd(sb, g[k].x); atomicAdd(sb + 32, g[k].y); atomicAdd(sb + 64, g[k].z); atomicAdd(sb + 96, g[k].w);
+        }
+        g[k].x *= ga.x; g[k].y *= ga.y; g[k].z *= ga.z; g[k].w *= ga.w;
+        s1 += (g[k].x + g[k].y) + (g[k].z + g[k].w);
+        s2 += (g[k].x * h[k].x + g[k].y * h[k].y) + (g[k].z * h[k].z + g[k].w * h[k].w);
       }
     }
     float m1 = 0.f, m2 = 0.f;
     if (P.do_ln) { m1 = warp_sum(s1) / d; m2 = warp_sum(s2) / d; }
-    float* dxr = P.dx + (long long)r * d;
-    const float* dr = P.dres ? P.dres + (long long)r * d : nullptr;
+    float* __restrict__ dxr = P.dx + (long long)r * d;
+    const float* __restrict__ dr = P.dres ? P.dres + (long long)r * d : nullptr;
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
       const int c = k * 128 + lane * 4;
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (srcs[k] >= 0) {
-        const TI* gp = dA + (brow + srcs[k]) * d + c;
-        const float2 a = load2<TI>(gp), bb = load2<TI>(gp + 2);
-        o = make_float4(a.x, a.y, bb.x, bb.y);
-      }
+      float4 o = g[k];
       if (P.do_ln) {
-        const float4 xv = *reinterpret_cast<const float4*>(xr + c);
-        const float4 ga = __ldg(reinterpret_cast<const float4*>(P.gamma + c));
-        o.x = rstd * (o.x * ga.x - m1 - (xv.x - mean) * rstd * m2);
-        o.y = rstd * (o.y * ga.y - m1 - (xv.y - mean) * rstd * m2);
-        o.z = rstd * (o.z * ga.z - m1 - (xv.z - mean) * rstd * m2);
-        o.w = rstd * (o.w * ga.w - m1 - (xv.w - mean) * rstd * m2);
+        o.x = rstd * (o.x - m1 - h[k].x * m2);
+        o.y = rstd * (o.y - m1 - h[k].y * m2);
+        o.z = rstd * (o.z - m1 - h[k].z * m2);
+        o.w = rstd * (o.w - m1 - h[k].w * m2);
       }
       if (dr) {
         const float4 e = *reinterpret_cast<const float4*>(dr + c);
@@ -318,76 +341,100 @@ __global__ void __launch_bounds__(WR_WARPS * 32, 2) ln_shift_bwd_warp_kernel(db2
       *reinterpret_cast<float4*>(dxr + c) = o;
     }
   }
-  if (P.do_ln && P.dgamma) {
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const int c = k * 128 + lane * 4;
-      atomicAdd(sm + c, ag[k].x); atomicAdd(sm + c + 1, ag[k].y); atomicAdd(sm + c + 2, ag[k].z); atomicAdd(sm + c + 3, ag[k].w);
-      atomicAdd(sm + d + c, ab[k].x); atomicAdd(sm + d + c + 1, ab[k].y); atomicAdd(sm + d + c + 2, ab[k].z); atomicAdd(sm + d + c + 3, ab[k].w);
-    }
+  if (want_p) {
     __syncthreads();
-    for (int c = threadIdx.x; c < d; c += blockDim.x) {
-      atomicAdd(P.dgamma + c, sm[c]);
-      atomicAdd(P.dbeta + c, sm[d + c]);
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+      // slot i = (k*4 + j)*32 + lane  <->  channel k*128 + lane*4 + j
+      const int lane_i = i & 31, kj = i >> 5, k = kj >> 2, j = kj & 3;
+      const int c = k * 128 + lane_i * 4 + j;
+      atomicAdd(P.dgamma + c, sm[i]);
+      atomicAdd(P.dbeta + c, sm[d + i]);
     }
   }
 }
 
-// scale_bwd, warp-per-row streaming: lane owns 8 consecutive channels of every 256-channel chunk (d = 256 * NCH8)
-template <typename T, int NCH8>
-__global__ void __launch_bounds__(WR_WARPS * 32) scale_bwd_warp_kernel(db200_scale_bwd_params P) {
-  extern __shared__ float sm[];          // [2][d]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int d = P.d;
-  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sm[c] = 0.f;
-  __syncthreads();
-  float as[NCH8][8], ab[NCH8][8], sc[NCH8][8];
+constexpr int SLAB_ROWS = 32;
+template <typename TI>
+__global__ void __launch_bounds__(256) ln_shift_bwd_param_kernel(db200_ln_shift_bwd_params P) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  const int n = P.n, d = P.d;
+  if (c >= d) return;
+  const int rows = P.batch * n;
+  const int r0 = blockIdx.y * SLAB_ROWS, r1 = min(rows, r0 + SLAB_ROWS);
+  const TI* __restrict__ dA = reinterpret_cast<const TI*>(P.d_out);
+  const float* __restrict__ x = P.x;
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int rb = r0; rb < r1; rb += 4) {
+    float2 a[4], bb[4];
+    float4 xv[4];
+    float mean[4], rstd[4];
 #pragma unroll
-  for (int k = 0; k < NCH8; ++k)
+    for (int i = 0; i < 4; ++i) {          // all loads of four rows first
+      const int r = rb + i;
+      a[i] = make_float2(0.f, 0.f); bb[i] = make_float2(0.f, 0.f); xv[i] = make_float4(0.f, 0.f, 0.f, 0.f); mean[i] = 0.f; rstd[i] = 0.f;
+      if (r < r1) {
+        const int b = r / n, p = r - b * n;
+        const int src = shift_row_dest(make_shift_row(p, n, P.text_len, P.fmap, P.do_shift), c, d);
+        if (src >= 0) {
+          const TI* gp = dA + ((long long)b * n + src) * d + c;
+          a[i] = load2<TI>(gp); bb[i] = load2<TI>(gp + 2);
+        }
+        xv[i] = *reinterpret_cast<const float4*>(x + (long long)r * d + c);
+        mean[i] = __ldg(P.mean + r); rstd[i] = __ldg(P.rstd + r);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ag.x += a[i].x * (xv[i].x - mean[i]) * rstd[i]; ag.y += a[i].y * (xv[i].y - mean[i]) * rstd[i];
+      ag.z += bb[i].x * (xv[i].z - mean[i]) * rstd[i]; ag.w += bb[i].y * (xv[i].w - mean[i]) * rstd[i];
+      ab.x += a[i].x; ab.y += a[i].y; ab.z += bb[i].x; ab.w += bb[i].y;
+    }
+  }
+  atomicAdd(P.dgamma + c, ag.x); atomicAdd(P.dgamma + c + 1, ag.y); atomicAdd(P.dgamma + c + 2, ag.z); atomicAdd(P.dgamma + c + 3, ag.w);
+  atomicAdd(P.dbeta + c, ab.x); atomicAdd(P.dbeta + c + 1, ab.y); atomicAdd(P.dbeta + c + 2, ab.z); atomicAdd(P.dbeta + c + 3, ab.w);
+}
+
+// scale_bwd, slab streaming: thread = 4 channels, block = 1024 channels x SLAB_ROWS rows; LayerScale value and the partial
+// sums live in 12 registers, so occupancy is high and four rows of loads are in flight per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) scale_bwd_slab_kernel(db200_scale_bwd_params P) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  const int d = P.d;
+  if (c >= d) return;
+  const int r0 = blockIdx.y * SLAB_ROWS, r1 = min(P.rows, r0 + SLAB_ROWS);
+  float4 sc = make_float4(P.sign, P.sign, P.sign, P.sign);
+  if (P.scale) { const float4 t = __ldg(reinterpret_cast<const float4*>(P.scale + c)); sc.x *= t.x; sc.y *= t.y; sc.z *= t.z; sc.w *= t.w; }
+  const T* __restrict__ y = reinterpret_cast<const T*>(P.y);
+  T* __restrict__ dy = reinterpret_cast<T*>(P.dy);
+  const float* __restrict__ dout = P.d_out;
+  const bool want_s = P.dscale != nullptr && y != nullptr;
+  float4 as = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int rb = r0; rb < r1; rb += 8) {
+    float4 g[8];
+    float2 y0[8], y1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {          // all loads of eight rows first
+      const long long off = (long long)(rb + i) * d + c;
+      g[i] = make_float4(0.f, 0.f, 0.f, 0.f); y0[i] = make_float2(0.f, 0.f); y1[i] = make_float2(0.f, 0.f);
+      if (rb + i < r1) {
+        g[i] = *reinterpret_cast<const float4*>(dout + off);
+        if (want_s) { y0[i] = load2<T>(y + off); y1[i] = load2<T>(y + off + 2); }
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      as[k][i] = 0.f; ab[k][i] = 0.f;
-      sc[k][i] = P.scale ? P.sign * __ldg(P.scale + k * 256 + lane * 8 + i) : P.sign;
-    }
-  const T* y = reinterpret_cast<const T*>(P.y);
-  T* dy = reinterpret_cast<T*>(P.dy);
-  const bool want_s = P.dscale != nullptr && y != nullptr;
-  for (int r = blockIdx.x * WR_WARPS + warp; r < P.rows; r += gridDim.x * WR_WARPS) {
-    const long long off = (long long)r * d;
-#pragma unroll
-    for (int k = 0; k < NCH8; ++k) {
-      const int c = k * 256 + lane * 8;
-      const float4 g0 = *reinterpret_cast<const float4*>(P.d_out + off + c);
-      const float4 g1 = *reinterpret_cast<const float4*>(P.d_out + off + c + 4);
-      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      float ov[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { ov[i] = sc[k][i] * gv[i]; ab[k][i] += ov[i]; }
-#pragma unroll
-      for (int i = 0; i < 8; i += 2) store2<T>(dy + off + c + i, ov[i], ov[i + 1]);
-      if (want_s) {
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          const float2 yy = load2<T>(y + off + c + i);
-          as[k][i] += P.sign * gv[i] * yy.x;
-          as[k][i + 1] += P.sign * gv[i + 1] * yy.y;
-        }
+      if (rb + i < r1) {
+        const long long off = (long long)(rb + i) * d + c;
+        const float o0 = sc.x * g[i].x, o1 = sc.y * g[i].y, o2 = sc.z * g[i].z, o3 = sc.w * g[i].w;
+        store2<T>(dy + off, o0, o1);
+        store2<T>(dy + off + 2, o2, o3);
+        ab.x += o0; ab.y += o1; ab.z += o2; ab.w += o3;
+        as.x += P.sign * g[i].x * y0[i].x; as.y += P.sign * g[i].y * y0[i].y; as.z += P.sign * g[i].z * y1[i].x; as.w += P.sign * g[i].w * y1[i].y;
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < NCH8; ++k)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = k * 256 + lane * 8 + i;
-      atomicAdd(sm + c, as[k][i]);
-      atomicAdd(sm + d + c, ab[k][i]);
-    }
-  __syncthreads();
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    if (P.dscale) atomicAdd(P.dscale + c, sm[c]);
-    if (P.dbias) atomicAdd(P.dbias + c, sm[d + c]);
-  }
+  if (P.dscale) { atomicAdd(P.dscale + c, as.x); atomicAdd(P.dscale + c + 1, as.y); atomicAdd(P.dscale + c + 2, as.z); atomicAdd(P.dscale + c + 3, as.w); }
+  if (P.dbias) { atomicAdd(P.dbias + c, ab.x); atomicAdd(P.dbias + c + 1, ab.y); atomicAdd(P.dbias + c + 2, ab.z); atomicAdd(P.dbias + c + 3, ab.w); }
 }
 
 template <typename T>
@@ -427,7 +474,7 @@ __global__ void __launch_bounds__(256) scale_bwd_kernel(db200_scale_bwd_params P
 // sums of du (= gradient of net.0.bias) accumulated on the fly.  Thread = 8 hidden columns, block = 2048 columns x GB_ROWS rows.
 constexpr int GB_ROWS = 64;
 template <typename T>
-__global__ void __launch_bounds__(256) geglu_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ u, T* __restrict__ du,
+__global__ void __launch_bounds__(256, 4) geglu_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ u, T* __restrict__ du,
                                                         float* __restrict__ dbias, int rows, int hidden) {
   const int j = (blockIdx.x * 256 + threadIdx.x) * 8;
   if (j >= hidden) return;
@@ -435,7 +482,7 @@ __global__ void __launch_bounds__(256) geglu_bwd_kernel(const T* __restrict__ dh
   float sa[8], sg[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { sa[i] = 0.f; sg[i] = 0.f; }
-#pragma unroll 2
+#pragma unroll 4
   for (int r = r0; r < r1; ++r) {
     float d[8], a[8], g[8], da[8], dg[8];
     Vec8<T>::load(dh + (long long)r * hidden + j, d);
@@ -602,20 +649,21 @@ int ln_shift_fwd_launch(const db200_ln_shift_fwd_params& P, cudaStream_t st) {
 int ln_shift_bwd_launch(const db200_ln_shift_bwd_params& P, cudaStream_t st) {
   const int rows = P.batch * P.n;
   if (rows == 0) return DB200_OK;
-  {
-    const int wgrid = ceil_div(rows, WR_WARPS) < sm_count() * 6 ? ceil_div(rows, WR_WARPS) : sm_count() * 6;
+  if (P.d == 256 || P.d == 512 || P.d == 1024) {
+    const int want = ceil_div(rows, WR_WARPS);
+    const int wgrid = want < sm_count() * 3 ? want : sm_count() * 3;
     const size_t wsmem = (size_t)2 * P.d * sizeof(float);
-#define DB200_LN_BWD_WARP(NCH)                                                                                              \
+#define DB200_LN_BWD_DX(NCH)                                                                                                \
   do {                                                                                                                      \
-    if (P.dout_dtype == DB200_F32) ln_shift_bwd_warp_kernel<float, NCH><<<wgrid, WR_WARPS * 32, wsmem, st>>>(P);           \
-    else ln_shift_bwd_warp_kernel<__nv_bfloat16, NCH><<<wgrid, WR_WARPS * 32, wsmem, st>>>(P);                             \
-    DB200_LAUNCH_OK("ln_shift_bwd_warp_kernel");                                                                           \
-    return DB200_OK;                                                                                                        \
+    if (P.dout_dtype == DB200_F32) ln_shift_bwd_dx_kernel<float, NCH><<<wgrid, WR_WARPS * 32, wsmem, st>>>(P);             \
+    else ln_shift_bwd_dx_kernel<__nv_bfloat16, NCH><<<wgrid, WR_WARPS * 32, wsmem, st>>>(P);                               \
   } while (0)
-    if (P.d == 256) DB200_LN_BWD_WARP(2);
-    if (P.d == 512) DB200_LN_BWD_WARP(4);
-    if (P.d == 1024) DB200_LN_BWD_WARP(8);
-#undef DB200_LN_BWD_WARP
+    if (P.d == 256) DB200_LN_BWD_DX(2);
+    else if (P.d == 512) DB200_LN_BWD_DX(4);
+    else DB200_LN_BWD_DX(8);
+#undef DB200_LN_BWD_DX
+    DB200_LAUNCH_OK("ln_shift_bwd_dx_kernel");
+    return DB200_OK;
   }
   const size_t smem = (size_t)4 * P.d * sizeof(float);
   const int grid = rows < sm_count() * 8 ? rows : sm_count() * 8;
@@ -628,19 +676,12 @@ int ln_shift_bwd_launch(const db200_ln_shift_bwd_params& P, cudaStream_t st) {
 int scale_bwd_launch(const db200_scale_bwd_params& P, cudaStream_t st) {
   if (P.rows == 0) return DB200_OK;
   const size_t smem = (size_t)2 * P.d * sizeof(float);
-  {
-    const int wgrid = ceil_div(P.rows, WR_WARPS) < sm_count() * 4 ? ceil_div(P.rows, WR_WARPS) : sm_count() * 4;
-#define DB200_SCALE_WARP(NCH8)                                                                                              \
-  do {                                                                                                                      \
-    if (P.dtype == DB200_F32) scale_bwd_warp_kernel<float, NCH8><<<wgrid, WR_WARPS * 32, smem, st>>>(P);                   \
-    else scale_bwd_warp_kernel<__nv_bfloat16, NCH8><<<wgrid, WR_WARPS * 32, smem, st>>>(P);                                \
-    DB200_LAUNCH_OK("scale_bwd_warp_kernel");                                                                              \
-    return DB200_OK;                                                                                                        \
-  } while (0)
-    if (P.d == 256) DB200_SCALE_WARP(1);
-    if (P.d == 512) DB200_SCALE_WARP(2);
-    if (P.d == 1024) DB200_SCALE_WARP(4);
-#undef DB200_SCALE_WARP
+  if ((P.d & 3) == 0) {
+    dim3 sgrid(ceil_div(P.d, 1024), ceil_div(P.rows, SLAB_ROWS));
+    if (P.dtype == DB200_F32) scale_bwd_slab_kernel<float><<<sgrid, 256, 0, st>>>(P);
+    else scale_bwd_slab_kernel<__nv_bfloat16><<<sgrid, 256, 0, st>>>(P);
+    DB200_LAUNCH_OK("scale_bwd_slab_kernel");
+    return DB200_OK;
   }
   const int grid = P.rows < sm_count() * 4 ? P.rows : sm_count() * 4;
   if (P.dtype == DB200_F32) scale_bwd_kernel<float><<<grid, 256, smem, st>>>(P);
