@@ -48,19 +48,64 @@ struct FwdArgs {
   bf16* out; float* lse; const uint8_t* key_mask; int heads, batch;
 };
 
-// smem map (after 1 KB alignment): Q | K0 | K1 | V0 | V1 | [P (SS mode only, 32 KB)] | barriers
+// Forward tiles are 128 queries x FK = 64 keys: S (fp32) needs 64 TMEM columns and P (bf16) is written over the first 32 of
+// them, O needs 64 -> 128 columns and 48 KB of smem per CTA, so up to FOUR CTAs are resident per SM and their softmax phases
+// overlap each other's MMAs (the per-tile MMA -> softmax -> MMA chain is latency-bound, not throughput-bound).
+constexpr int FK = 64;
+constexpr int FK_BYTES = FK * DH * 2;          // one [64 x 64] bf16 tile = 8 KB
+
+// P = exp2(S*log2e - m*log2e) for one 32-column chunk held in registers, packed to bf16x2; returns the chunk's row sum
+__device__ __forceinline__ float fwd_exp_pack(const uint32_t (&r)[32], uint32_t mb, bool skip, float mb2, uint32_t (&pk)[16]) {
+  float rs = 0.f;
+  if (skip) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pk[i] = 0u;
+  } else if (mb == 0xffffffffu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), LOG2E, -mb2));
+      const float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, -mb2));
+      rs += p0 + p1;
+      pk[i] = pack2(p0, p1);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float p0 = sel_bit(mb, 2 * i, ex2(fmaf(__uint_as_float(r[2 * i]), LOG2E, -mb2)), 0.f);
+      const float p1 = sel_bit(mb, 2 * i + 1, ex2(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, -mb2)), 0.f);
+      rs += p0 + p1;
+      pk[i] = pack2(p0, p1);
+    }
+  }
+  return rs;
+}
+template <bool P_TMEM>
+__device__ __forceinline__ void fwd_store_p(const uint32_t (&pk)[16], int c, uint32_t tP_lane, uint8_t* sP, int row) {
+  if constexpr (P_TMEM) {
+    tmem_st16(tP_lane + c * 16, pk);
+  } else {   // K-major [128 rows][64 keys] 128B-swizzled tile; this thread owns row `row`
+    uint8_t* prow = sP + row * 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int chunk = c * 4 + j;
+      *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+  }
+}
+
+// smem map (after 1 KB alignment): Q | K0 | K1 | V0 | V1 | [P (SS mode only, 16 KB)] | barriers
 template <bool P_TMEM>
 struct FwdSmem {
   static constexpr int Q_OFF = 0;
   static constexpr int K_OFF = TILE_BYTES;
-  static constexpr int V_OFF = 3 * TILE_BYTES;
-  static constexpr int P_OFF = 5 * TILE_BYTES;
-  static constexpr int BAR_OFF = P_OFF + (P_TMEM ? 0 : 2 * TILE_BYTES);
+  static constexpr int V_OFF = TILE_BYTES + 2 * FK_BYTES;
+  static constexpr int P_OFF = TILE_BYTES + 4 * FK_BYTES;
+  static constexpr int BAR_OFF = P_OFF + (P_TMEM ? 0 : TILE_BYTES);
   static constexpr int TOTAL = BAR_OFF + 128 + 1024;
 };
 
 template <bool P_TMEM>
-__global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+__global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                           const __grid_constant__ CUtensorMap tmV, FwdArgs P, AttnGeom g) {
   using L = FwdSmem<P_TMEM>;
   extern __shared__ uint8_t smem_raw[];
@@ -71,15 +116,15 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
   const uint32_t q_full = smem_u32(bars), kv_full = smem_u32(bars + 1), kv_empty = smem_u32(bars + 3);
   const uint32_t s_full = smem_u32(bars + 5), p_ready = smem_u32(bars + 6), o_done = smem_u32(bars + 7);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  constexpr uint32_t TMEM_COLS = 256;          // S [0,128) | O [128,192) | P [192,256)
+  constexpr uint32_t TMEM_COLS = 128;          // S [0,64) with P (bf16) aliased on [0,32) | O [64,128)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / P.heads, h = bh - b * P.heads;
   const int q0 = blockIdx.x * TQ;
   const int off = g.n_k - g.n_q;
   const int q_last = min(q0 + TQ, g.n_q) - 1;
-  const int nkt = (g.n_k + TK - 1) / TK;
-  auto needed = [&](int kt) { return attn_tile_needed(g, q0 + off, q_last + off, kt * TK, min(kt * TK + TK, g.n_k) - 1); };
+  const int nkt = (g.n_k + FK - 1) / FK;
+  auto needed = [&](int kt) { return attn_tile_needed(g, q0 + off, q_last + off, kt * FK, min(kt * FK + FK, g.n_k) - 1); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -93,7 +138,7 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tO = tmem + 128, tP = tmem + 192;
+  const uint32_t tS = tmem, tO = tmem + 64, tP = tmem;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -105,9 +150,9 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
         if (!needed(kt)) continue;
         const int s = it & 1;
         mbar_wait(kv_empty + 8 * s, ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(kv_full + 8 * s, 2 * TILE_BYTES);
-        tma_load_2d(sK + s * TILE_BYTES, &tmK, kv_full + 8 * s, 0, bh * g.n_k + kt * TK);
-        tma_load_2d(sV + s * TILE_BYTES, &tmV, kv_full + 8 * s, 0, bh * g.n_k + kt * TK);
+        mbar_expect_tx(kv_full + 8 * s, 2 * FK_BYTES);
+        tma_load_2d(sK + s * FK_BYTES, &tmK, kv_full + 8 * s, 0, bh * g.n_k + kt * FK);
+        tma_load_2d(sV + s * FK_BYTES, &tmV, kv_full + 8 * s, 0, bh * g.n_k + kt * FK);
         ++it;
       }
     }
@@ -115,7 +160,7 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     if (lane == 0) {
-      constexpr uint32_t IDESC_S = make_idesc_bf16(128, 128, false, false);   // S = Q K^T : both K-major
+      constexpr uint32_t IDESC_S = make_idesc_bf16(128, FK, false, false);    // S = Q K^T : both K-major
       constexpr uint32_t IDESC_O = make_idesc_bf16(128, 64, false, true);     // O = P V   : A K-major (TMEM / smem), B N-major
       mbar_wait(q_full, 0);
       const uint64_t dq = make_smem_desc(sQ, 16, 1024);
@@ -125,21 +170,23 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
         const int s = it & 1;
         mbar_wait(kv_full + 8 * s, (it >> 1) & 1);
         tc_fence_after();
-        const uint64_t dk = make_smem_desc(sK + s * TILE_BYTES, 16, 1024);
+        // (S of this tile overwrites the columns P of the previous tile was read from: safe, the tensor pipe executes the
+        //  previous O += P V before this S = Q K^T because both are issued in order by this thread)
+        const uint64_t dk = make_smem_desc(sK + s * FK_BYTES, 16, 1024);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
         umma_commit(s_full);
         mbar_wait(p_ready, it & 1);
         tc_fence_after();
-        // V tile image [128 keys][64 dh] read as the N-major B operand: K = keys (16 rows = 2048 B per step), N = dh
-        const uint64_t dv = make_smem_desc(sV + s * TILE_BYTES, TILE_BYTES, 1024);
+        // V tile image [64 keys][64 dh] read as the N-major B operand: K = keys (16 rows = 2048 B per step), N = dh
+        const uint64_t dv = make_smem_desc(sV + s * FK_BYTES, FK_BYTES, 1024);
 #pragma unroll
-        for (int k = 0; k < TK / 16; ++k) {
+        for (int k = 0; k < FK / 16; ++k) {
           if constexpr (P_TMEM) {
             umma_bf16_ts(tO, tP + 8 * k, dv + 128 * k, IDESC_O, (it | k) != 0);
           } else {
-            const uint64_t dp = make_smem_desc(sP + (k >> 2) * TILE_BYTES, 16, 1024);
-            umma_bf16(tO, dp + 2 * (k & 3), dv + 128 * k, IDESC_O, (it | k) != 0);
+            const uint64_t dp = make_smem_desc(sP, 16, 1024);
+            umma_bf16(tO, dp + 2 * k, dv + 128 * k, IDESC_O, (it | k) != 0);
           }
         }
         umma_commit(kv_empty + 8 * s);
@@ -159,21 +206,22 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
     int it = 0;
     for (int kt = 0; kt < nkt; ++kt) {
       if (!needed(kt)) continue;
-      const int k0 = kt * TK, k1 = min(k0 + TK, g.n_k) - 1;
-      const bool full = (k1 - k0 == TK - 1) && km == nullptr && attn_tile_full(g, q0 + off, q_last + off, k0, k1);
-      Mask128 mk = {{0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu}};
+      const int k0 = kt * FK, k1 = min(k0 + FK, g.n_k) - 1;
+      const bool full = (k1 - k0 == FK - 1) && km == nullptr && attn_tile_full(g, q0 + off, q_last + off, k0, k1);
+      Mask128 mk = {{0xffffffffu, 0xffffffffu, 0u, 0u}};
       if (!full) {
-        if (qi < g.n_q) mk = attn_row_bits(g, qi + off, k0, km);
-        else mk.w[0] = mk.w[1] = mk.w[2] = mk.w[3] = 0u;
+        if (qi < g.n_q) mk = attn_row_bits(g, qi + off, k0, km, FK);
+        else mk.w[0] = mk.w[1] = 0u;
       }
-      mbar_wait(s_full, it & 1);
+      mbar_wait(s_full, it & 1);                   // also implies the previous tile's O += P V has completed (in-order pipe)
       tc_fence_after();
-      // ---- pass 1: row max ----
+      // ---- pass 1: row max (32 columns at a time keeps the register footprint small enough for 3-4 CTAs per SM) ----
+      const bool skip0 = __all_sync(0xffffffffu, mk.w[0] == 0u), skip1 = __all_sync(0xffffffffu, mk.w[1] == 0u);
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t mb = c == 0 ? mk.w[0] : c == 1 ? mk.w[1] : c == 2 ? mk.w[2] : mk.w[3];
-        if (__all_sync(0xffffffffu, mb == 0u)) continue;            // whole 32x32 chunk masked (warp-uniform)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t mb = c == 0 ? mk.w[0] : mk.w[1];
+        if (c == 0 ? skip0 : skip1) continue;
         uint32_t r[32];
         tmem_ld32(tS + lane_off + c * 32, r);
         tmem_ld_wait();
@@ -188,52 +236,16 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
       const float m_new = (mx > m_run + RESCALE_TAU) ? mx : m_run;
       const float corr = ex2((m_run - m_new) * LOG2E);
       const float mb2 = m_new * LOG2E;
-      if (it > 0) {                                  // PV of the previous tile must be done: P buffer free, O final
-        mbar_wait(o_done, (it - 1) & 1);
-        tc_fence_after();
-      }
-      // ---- pass 2: P = exp2(S*log2e - m*log2e), row sum, P -> TMEM (or smem) as bf16 ----
+      // ---- pass 2: P = exp2(S*log2e - m*log2e) -> bf16 over the S columns already consumed ----
       float rs = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t mb = c == 0 ? mk.w[0] : c == 1 ? mk.w[1] : c == 2 ? mk.w[2] : mk.w[3];
-        uint32_t pk[16];
-        if (__all_sync(0xffffffffu, mb == 0u)) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = 0u;
-        } else {
-          uint32_t r[32];
-          tmem_ld32(tS + lane_off + c * 32, r);
-          tmem_ld_wait();
-          if (mb == 0xffffffffu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), LOG2E, -mb2));
-              const float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, -mb2));
-              rs += p0 + p1;
-              pk[i] = pack2(p0, p1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float p0 = sel_bit(mb, 2 * i, ex2(fmaf(__uint_as_float(r[2 * i]), LOG2E, -mb2)), 0.f);
-              const float p1 = sel_bit(mb, 2 * i + 1, ex2(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, -mb2)), 0.f);
-              rs += p0 + p1;
-              pk[i] = pack2(p0, p1);
-            }
-          }
-        }
-        if constexpr (P_TMEM) {
-          tmem_st16(tP + lane_off + c * 16, pk);
-        } else {
-          // K-major [128 rows][128 keys] as two 128B-swizzled [128 x 64] tiles; this thread owns row `row`
-          uint8_t* prow = smem + L::P_OFF + (c >> 1) * TILE_BYTES + row * 128;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int chunk = (c & 1) * 4 + j;
-            *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          }
-        }
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t mb = c == 0 ? mk.w[0] : mk.w[1];
+        const bool skip = c == 0 ? skip0 : skip1;
+        uint32_t r[32], pk[16];
+        if (!skip) { tmem_ld32(tS + lane_off + c * 32, r); tmem_ld_wait(); }
+        rs += fwd_exp_pack(r, mb, skip, mb2, pk);
+        fwd_store_p<P_TMEM>(pk, c, tP + lane_off, smem + L::P_OFF, row);
       }
       l_run = l_run * corr + rs;
       m_run = m_new;
@@ -292,7 +304,6 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_tc_kernel(const __grid_consta
     tmem_dealloc(tmem, TMEM_COLS);
   }
 }
-
 
 // =============================================== backward ====================================================
 __global__ void attn_delta_tc_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ delta, int batch, int heads,
@@ -716,8 +727,8 @@ int launch_fwd(const db200_attn_fwd_params& p, cudaStream_t st) {
   const uint64_t bh = (uint64_t)p.batch * p.heads;
   int rc = make_tensor_map_bf16(&tmQ, p.q, DH, bh * p.n_q, DH, DH, TQ);
   if (rc) return rc;
-  if ((rc = make_tensor_map_bf16(&tmK, p.k, DH, bh * p.n_k, DH, DH, TK))) return rc;
-  if ((rc = make_tensor_map_bf16(&tmV, p.v, DH, bh * p.n_k, DH, DH, TK))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmK, p.k, DH, bh * p.n_k, DH, DH, FK))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmV, p.v, DH, bh * p.n_k, DH, DH, FK))) return rc;
   auto kern = attn_fwd_tc_kernel<P_TMEM>;
   static bool attr_done = false;
   if (!attr_done) {
