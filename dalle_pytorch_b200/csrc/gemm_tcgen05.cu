@@ -123,8 +123,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mn = tile % num_mn, split = tile / num_mn;
-        const int m0 = (mn % num_m) * BLOCK_M;
-        const int n0 = (mn / num_m) * BLOCK_N;
+        const int m0 = (mn / num_n) * BLOCK_M;          // n-fastest: CTAs running together share the A tile through L2
+        const int n0 = (mn % num_n) * BLOCK_N;
         const int kb0 = split * kb_per, kb1 = min(total_kb, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + 8 * s, ph ^ 1);
@@ -201,8 +201,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int as = 0; uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mn = tile % num_mn;
-      const int m0 = (mn % num_m) * BLOCK_M;
-      const int n0 = (mn / num_m) * BLOCK_N;
+      const int m0 = (mn / num_n) * BLOCK_M;          // n-fastest: CTAs running together share the A tile through L2
+      const int n0 = (mn % num_n) * BLOCK_N;
       const int mbase = m0 + quarter * 32 + lrow;            // + 2*it
       mbar_wait(tfull_bar + 8 * as, aph);
       tc_fence_after();
