@@ -35,6 +35,9 @@ CONFIGS = {
     'c5': dict(dim=1024, depth=64, heads=16, text_seq_len=256, fmap=32, batch=32, attn_types=('axial_row', 'axial_col'), reversible=False, dtype='bf16'),
 }
 NUM_TEXT_TOKENS, NUM_IMAGE_TOKENS = 10000, 8192
+# measured with ncu on B200 (profiles/r01_gemm_ncu_summary.txt): 36.6 GB of DRAM traffic over the 150 tcgen05 GEMM launches of a C2 step
+# (algorithmic operand+result bytes of the same launches: 33.9 GB)
+GEMM_DRAM_BYTES_PER_LAUNCH = 244e6
 METRIC = 'DALL-E fwd+bwd tokens/sec at seq=1280, dim=1024'
 
 
@@ -294,6 +297,10 @@ def run_gpu_arm(args):
     tokens_per_step = batch * seq * world
     value = tokens_per_step * args.steps / (ms_dev / 1e3)
     e2e_value = tokens_per_step * args.steps / (ms_e2e / 1e3)
+    if world > 1:
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
     if rank != 0:
         return
 
@@ -302,7 +309,9 @@ def run_gpu_arm(args):
     if fam['ms'] > 0:
         ach = fam['flops'] / (fam['ms'] * 1e-3) / 1e12
         roof = {'bound': 'tensor', 'kernel': 'gemm_tcgen05_kernel (all fwd/dgrad/wgrad GEMMs of the block stack)', 'achieved': ach,
-                'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': GEMM_DRAM_BYTES_PER_LAUNCH if args.config == 'c2' else None,
+                'traffic_note': 'dram__bytes_read+write per launch averaged over the 150 GEMM launches of one C2 step, ncu --set full capture profiles/r01_gemm_ncu_summary.txt',
+                'peak_source': peak_src,
                 'launches_per_step': fam['launches'] / args.steps, 'share_of_step': fam['ms'] / ms_dev,
                 'by_shape': gemm_stats.get('by_shape', {})}
     else:
@@ -335,7 +344,7 @@ def run_gpu_arm(args):
            'dtype': 'bf16' if dtype == torch.bfloat16 else 'f32', 'data': 'synthetic',
            'config': {'workload': workload_name(args.config, c), 'global_batch': batch * world, 'seq_len': seq,
                       'parallelism': f'dp{world}', 'l2': 'activations and weights per step (GBs) exceed the 126 MB L2; no flush needed',
-                      'head': 'logits head + cross-entropy run in PyTorch (cuBLAS), block stack in libdalle_b200'},
+                      'head': 'block stack, logits head GEMMs and cross-entropy all run in libdalle_b200 (embedding lookup is torch)'},
            'e2e': {'value': e2e_value, 'unit': 'tokens/s', 'ms_per_step': ms_e2e / args.steps,
                    'h2d_bytes_per_step': int(text_h.numel() * 8 + image_h.numel() * 8) * world, 'd2h_bytes_per_step': 4 * world},
            'gpu_launches': launches, 'model_tflops_per_gpu': value / world * flops_tok / 1e12,
@@ -344,6 +353,7 @@ def run_gpu_arm(args):
     if cpu is not None:
         out['cpu_baseline'] = cpu
     print(json.dumps(out))
+    sys.stdout.flush()
 
 
 def main():
@@ -364,6 +374,12 @@ def main():
         run_reference_arm(args)
     else:
         run_gpu_arm(args)
+        try:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 if __name__ == '__main__':

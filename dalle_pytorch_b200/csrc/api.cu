@@ -42,6 +42,8 @@ int scale_bwd_launch(const db200_scale_bwd_params& P, cudaStream_t st);
 int colsum_launch(const void* x, int dtype, int rows, int cols, float* out, cudaStream_t st);
 int ce_fwd_launch(const void* logits, int dtype, int rows, int vocab, const long long* labels, float coef, float* row_lse, float* loss_acc, cudaStream_t st);
 int ce_bwd_launch(void* logits, int dtype, int rows, int vocab, const long long* labels, float coef, const float* row_lse, const float* upstream, cudaStream_t st);
+int qkv_rotary_launch(const void* qkv, void* q, void* k, void* v, const float* cos_t, const float* sin_t, int dtype, int rows, int seq_n, int heads,
+                      int dh, int pos_offset, float q_scale, cudaStream_t st);
 int geglu_bwd_launch(const void* dh, const void* u, void* du, float* dbias, int dtype, int rows, int hidden, cudaStream_t st);
 int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st);
 int axpby_launch(const float* a, const float* b, float alpha, float* y, int64_t count, cudaStream_t st);
@@ -239,6 +241,17 @@ int dalle_b200_geglu_bwd(const void* dh, const void* u, void* du, float* dbias, 
   DB200_CHECK_ARG(dh && u && du && rows >= 0 && hidden > 0 && (hidden & 7) == 0 && dtype_ok(dtype), "geglu_bwd: bad args (hidden must be a multiple of 8)");
   DB200_CHECK_ARG(aligned16(dh) && aligned16(u) && aligned16(du), "geglu_bwd: tensors must be 16-byte aligned");
   return geglu_bwd_launch(dh, u, du, dbias, dtype, rows, hidden, (cudaStream_t)stream);
+}
+
+int dalle_b200_qkv_rotary(const void* qkv, void* q, void* k, void* v, const float* cos_t, const float* sin_t, int dtype, int rows, int seq_n,
+                          int heads, int dim_head, int pos_offset, float q_scale, void* stream) {
+  DB200_CHECK_ARG(qkv && q && k && v && dtype_ok(dtype) && rows >= 0 && seq_n > 0 && heads > 0 && dim_head > 0 && (dim_head & 7) == 0 &&
+                      rows % seq_n == 0,
+                  "qkv_rotary: bad args (dim_head must be a multiple of 8, rows a multiple of seq_n)");
+  DB200_CHECK_ARG((cos_t == nullptr) == (sin_t == nullptr), "qkv_rotary: cos/sin tables must come together");
+  DB200_CHECK_ARG(aligned16(qkv) && aligned16(q) && aligned16(k) && aligned16(v) && (!cos_t || (aligned16(cos_t) && aligned16(sin_t))),
+                  "qkv_rotary: tensors must be 16-byte aligned");
+  return qkv_rotary_launch(qkv, q, k, v, cos_t, sin_t, dtype, rows, seq_n, heads, dim_head, pos_offset, q_scale, (cudaStream_t)stream);
 }
 
 int dalle_b200_ce_fwd(const void* logits, int dtype, int rows, int vocab, const int64_t* labels, float coef, float* row_lse, float* loss_acc,

@@ -568,6 +568,44 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(T* __restrict__ logits, con
   }
 }
 
+// Head split + rotary + q scale as a streaming pass over the plain to_qkv output (attention.py:63-69): qkv [rows, 3*h*dh] ->
+// q,k,v [b,h,n,dh].  Thread = 8 channels; the 8 lanes of a head read one 128-byte cos / sin table row and write one 128-byte
+// q/k/v row, so every access is a full line.  (Measured faster than doing the same in the tcgen05 epilogue, where a thread
+// owns a token row and its table loads are 32 different lines per instruction; profiles/r01_summary.md.)
+template <typename T>
+__global__ void __launch_bounds__(256) qkv_rotary_kernel(const T* __restrict__ qkv, T* __restrict__ q, T* __restrict__ k, T* __restrict__ v,
+                                                         const float* __restrict__ cos_t, const float* __restrict__ sin_t, int rows, int seq_n,
+                                                         int heads, int dh, int pos_offset, float q_scale) {
+  const int inner = heads * dh;
+  const int m = blockIdx.x;                                      // token row (block-uniform: its b / p split costs nothing)
+  const int c = (blockIdx.y * 256 + threadIdx.x) * 8;            // column in [0, 3*inner)
+  if (c >= 3 * inner) return;
+  const int which = c >= 2 * inner ? 2 : (c >= inner ? 1 : 0);
+  const int rem = c - which * inner;
+  const int head = rem / dh, d = rem - head * dh;
+  const int b = m / seq_n, p = m - b * seq_n;
+  float x[8];
+  Vec8<T>::load(qkv + (long long)m * (3 * inner) + c, x);
+  if (cos_t) {
+    const int ti = (p + pos_offset) * (dh >> 1) + (d >> 1);
+    const float4 cc = __ldg(reinterpret_cast<const float4*>(cos_t + ti));
+    const float4 ss = __ldg(reinterpret_cast<const float4*>(sin_t + ti));
+    const float cv[4] = {cc.x, cc.y, cc.z, cc.w}, sv[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float x0 = x[2 * i], x1 = x[2 * i + 1];
+      x[2 * i] = x0 * cv[i] + (-x1) * sv[i];
+      x[2 * i + 1] = x1 * cv[i] + x0 * sv[i];
+    }
+  }
+  if (which == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] *= q_scale;
+  }
+  T* base = which == 0 ? q : (which == 1 ? k : v);
+  Vec8<T>::store(base + (((long long)b * heads + head) * seq_n + p) * dh + d, x);
+}
+
 constexpr int CS_ROWS = 512;
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int rows, int cols, float* __restrict__ out) {
@@ -717,6 +755,21 @@ int ce_bwd_launch(void* logits, int dtype, int rows, int vocab, const long long*
   if (dtype == DB200_F32) ce_bwd_kernel<float><<<rows, 256, 0, st>>>(reinterpret_cast<float*>(logits), labels, vocab, coef, row_lse, upstream);
   else ce_bwd_kernel<__nv_bfloat16><<<rows, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(logits), labels, vocab, coef, row_lse, upstream);
   DB200_LAUNCH_OK("ce_bwd_kernel");
+  return DB200_OK;
+}
+
+int qkv_rotary_launch(const void* qkv, void* q, void* k, void* v, const float* cos_t, const float* sin_t, int dtype, int rows, int seq_n, int heads,
+                      int dh, int pos_offset, float q_scale, cudaStream_t st) {
+  if (rows == 0) return DB200_OK;
+  const dim3 grid(rows, ceil_div(3 * heads * dh / 8, 256));
+  if (dtype == DB200_F32)
+    qkv_rotary_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(q), reinterpret_cast<float*>(k),
+                                                   reinterpret_cast<float*>(v), cos_t, sin_t, rows, seq_n, heads, dh, pos_offset, q_scale);
+  else
+    qkv_rotary_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(q),
+                                                           reinterpret_cast<__nv_bfloat16*>(k), reinterpret_cast<__nv_bfloat16*>(v), cos_t, sin_t,
+                                                           rows, seq_n, heads, dh, pos_offset, q_scale);
+  DB200_LAUNCH_OK("qkv_rotary_kernel");
   return DB200_OK;
 }
 

@@ -64,7 +64,7 @@ def attn_sublayer_forward(g: SublayerGeom, x_in, resid, ln_w, ln_b, w_qkv, w_out
     shift = g.shift_active(n)
     a1, mean, rstd = ops.ln_shift_fwd(x_in, ln_w, ln_b, g.dtype, g.text_len, g.fmap, do_ln=g.do_ln, do_shift=shift, eps=g.eps)
     wq, wo = _w(w_qkv, g.dtype), _w(w_out, g.dtype)
-    q, k, v = ops.gemm_qkv(a1, wq, b, n, g.heads, g.dim_head, cos_t, sin_t, g.q_scale)
+    q, k, v = ops.gemm_qkv_auto(a1, wq, b, n, g.heads, g.dim_head, cos_t, sin_t, g.q_scale)
     o, lse = ops.attn_fwd(g.attn_spec, q, k, v, key_mask)
     keep_y = save and scale is not None
     out, y = ops.gemm_resid(o.view(b * n, -1), wo, b_out, None if resid is None else resid.contiguous().view(b * n, d),

@@ -172,6 +172,22 @@ def gemm_qkv(A, W, batch, seq_n, heads, dim_head, cos_t, sin_t, q_scale, pos_off
     return qkv[0], qkv[1], qkv[2]
 
 
+FUSE_QKV_EPILOGUE = False   # True: rotary + head split inside the GEMM epilogue (EPI_QKV); False (measured faster for bf16 on
+#                             B200): plain GEMM + dalle_b200_qkv_rotary streaming pass
+
+
+def gemm_qkv_auto(A, W, batch, seq_n, heads, dim_head, cos_t, sin_t, q_scale, pos_offset=0):
+    if FUSE_QKV_EPILOGUE or A.dtype != torch.bfloat16 or dim_head % 8:
+        return gemm_qkv(A, W, batch, seq_n, heads, dim_head, cos_t, sin_t, q_scale, pos_offset)
+    raw = gemm_store(A, W)                                      # [M, 3*h*dh]
+    M = raw.shape[0]
+    qkv = torch.empty(3, batch, heads, seq_n, dim_head, device=A.device, dtype=A.dtype)
+    _lib.check(_lib.lib().dalle_b200_qkv_rotary(_p(raw), _p(qkv[0]), _p(qkv[1]), _p(qkv[2]), _p(cos_t), _p(sin_t), dt_code(A.dtype), M, seq_n,
+                                                heads, dim_head, pos_offset, q_scale, _stream()), 'qkv_rotary')
+    _count()
+    return qkv[0], qkv[1], qkv[2]
+
+
 def gemm_resid(A, W, bias, resid, scale, sign=1.0, keep_y=False, backend=GEMM_AUTO):
     """out[M,N] fp32 = resid + sign*scale*(A W^T + bias); optionally also returns y = A W^T + bias (A.dtype)"""
     _c(A), _c(W)

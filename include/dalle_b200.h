@@ -199,6 +199,11 @@ int dalle_b200_scale_bwd(const db200_scale_bwd_params* p, void* stream);
 /* column sums: out[c] += sum_m x[m,c]  (bias gradient of net.0, transformer.py:114) */
 int dalle_b200_colsum(const void* x, int dtype, int rows, int cols, float* out, void* stream);
 
+/* Head split + rotary(q,k,v) + q scale as a streaming pass over the plain to_qkv output (the same math as EPI_QKV,
+ * attention.py:63-69): qkv [rows, 3*heads*dim_head] -> q,k,v [rows/seq_n, heads, seq_n, dim_head] (dtype) */
+int dalle_b200_qkv_rotary(const void* qkv, void* q, void* k, void* v, const float* cos_t, const float* sin_t, int dtype, int rows, int seq_n,
+                          int heads, int dim_head, int pos_offset, float q_scale, void* stream);
+
 /* GEGLU adjoint as a streaming pass: dh [rows, hidden], u = [a|g] [rows, 2*hidden] -> du [rows, 2*hidden] (dtype);
  * dbias [2*hidden] fp32 (optional, +=) receives the column sums of du = gradient of net.0.bias (transformer.py:106-115) */
 int dalle_b200_geglu_bwd(const void* dh, const void* u, void* du, float* dbias, int dtype, int rows, int hidden, void* stream);

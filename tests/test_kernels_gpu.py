@@ -112,6 +112,11 @@ def test_gemm_qkv_epilogue(dtype):
     report('q', q, wq * dh ** -0.5, **tol)
     report('k', k, wk, **tol)
     report('v', v, wv, **tol)
+    # same math as plain GEMM + streaming head-split/rotary pass (the bf16 default)
+    q2, k2, v2 = o.gemm_qkv_auto(A, W, b, n, h, dh, cos_t, sin_t, dh ** -0.5)
+    report('q (streaming)', q2, wq * dh ** -0.5, **tol)
+    report('k (streaming)', k2, wk, **tol)
+    report('v (streaming)', v2, wv, **tol)
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])

@@ -26,7 +26,7 @@ for stage in "$@"; do
     ncu_attn) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_.*tc_kernel -s 3 -c 3 -o gpurun_out/prof_attn -f python tools/attn_probe.py --backend tc --iters 1 > gpurun_out/ncu_attn.log 2>&1; tail -3 gpurun_out/ncu_attn.log ;;
     ncu_ew) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"bwd_dx|scale_bwd_slab|bwd_param|geglu_bwd_kernel" -c 4 -o gpurun_out/prof_ew -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_ew.log 2>&1; tail -2 gpurun_out/ncu_ew.log ;;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1; tail -3 gpurun_out/ncu_list.log ;;
-    ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 62 -c 14 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log ;;
+    ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 44 -c 20 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
