@@ -215,3 +215,90 @@ def test_module_api_standalone_and_cache():
             ref = full[:, cur] if cur < 24 else None
             live = ref > -1e30
             report(f'cached step {cur}', lg[:, -1][live], ref[live], RTOL, 2e-5)
+
+
+def test_c2_geometry_single_layer_fp32_vs_oracle():
+    """BASELINE.json configs[1] geometry (dim 1024, heads 16, text 256, image 32x32, n = 1280) at depth 1 / batch 1, fp32
+    mode against the CPU oracle: loss, sampled logits and a few gradients at rtol 1e-3 / atol 1e-5."""
+    import dalle_pytorch_b200 as D
+    cfg = OracleConfig(dim=1024, depth=1, heads=16, text_seq_len=256, fmap=32, num_text_tokens=10000, num_image_tokens=8192,
+                       attn_types=('full',))
+    sd = make_state_dict(cfg, seed=2, fast=True)
+    text, image = make_inputs(cfg, 1, seed=3)
+    params = {k: v.clone().requires_grad_(k != 'transformer.pos_emb') for k, v in sd.items()}
+    want = dalle_forward(text, image, params, cfg, return_loss=True)
+    want.backward()
+    with torch.no_grad():
+        want_logits = dalle_forward(text, image, sd, cfg)
+    m = build(cfg, sd).train()
+    with D.compute_dtype_ctx(torch.float32):
+        loss = m(text.cuda(), image.cuda(), return_loss=True)
+        loss.backward()
+        with torch.no_grad():
+            logits = m(text.cuda(), image.cuda()).cpu()
+    report('loss', loss, want, RTOL, ATOL)
+    live = want_logits > -1e30
+    assert torch.equal(logits[~live], want_logits[~live])
+    report('logits', logits[live][::97], want_logits[live][::97], RTOL, ATOL)
+    grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    for k in ('transformer.layers.layers.0.0.fn.fn.fn.fn.fn.to_qkv.weight', 'transformer.layers.layers.0.1.fn.fn.fn.fn.net.3.weight',
+              'transformer.layers.layers.0.0.scale', 'transformer.layers.layers.0.1.fn.norm.weight', 'to_logits.1.bias'):
+        report(f'grad {k}', grads[k], params[k].grad, RTOL, ATOL)
+
+
+def test_c2_geometry_bf16_consistent_with_fp32_mode():
+    """Same model, both precision modes of the library at the benchmark geometry (depth 2, batch 2, axial + full)."""
+    import dalle_pytorch_b200 as D
+    cfg = OracleConfig(dim=1024, depth=2, heads=16, text_seq_len=256, fmap=32, num_text_tokens=10000, num_image_tokens=8192,
+                       attn_types=('full', 'axial_col'))
+    sd = make_state_dict(cfg, seed=4, fast=True)
+    text, image = make_inputs(cfg, 2, seed=5)
+    out = {}
+    for dt in (torch.float32, torch.bfloat16):
+        m = build(cfg, sd).train()
+        with D.compute_dtype_ctx(dt):
+            loss = m(text.cuda(), image.cuda(), return_loss=True)
+            loss.backward()
+        out[dt] = (loss.detach(), m.transformer.layers.layers[0][1].fn.fn.fn.fn.net[0].weight.grad.clone())
+    report('loss bf16 vs fp32', out[torch.bfloat16][0], out[torch.float32][0], 1e-2, 1e-2)
+    g32, g16 = out[torch.float32][1], out[torch.bfloat16][1]
+    report('ff1 grad bf16 vs fp32', g16, g32, 0.0, 0.05 * float(g32.abs().max()))
+
+
+def test_generate_images_cached_and_uncached():
+    """generate_images (dalle_pytorch.py:506-562) with and without the KV cache on an optimize_for_inference model: both run
+    through the library kernels and, with the same Gumbel noise, produce the same image tokens."""
+    import dalle_pytorch_b200 as D
+    cfg = OracleConfig(dim=64, depth=2, heads=2, text_seq_len=8, fmap=4, num_text_tokens=50, num_image_tokens=32,
+                       attn_types=('axial_row', 'axial_col'))
+    sd = make_state_dict(cfg, seed=6)
+    vae = D.TokenVAE(image_size=32, num_layers=3, num_tokens=32)
+    m = D.DALLE(dim=64, vae=vae, num_text_tokens=50, text_seq_len=8, depth=2, heads=2, attn_types=('axial_row', 'axial_col'),
+                optimize_for_inference=True)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    text, _ = make_inputs(cfg, 2, seed=7, pad_tail=False)
+    toks = []
+    for use_cache in (False, True):
+        torch.manual_seed(123)
+        out = m.generate_images(text.cuda(), use_cache=use_cache, filter_thres=0.9)
+        assert out.shape == (2, 16) and out.min() >= 0 and out.max() < 32
+        toks.append(out.cpu())
+    assert (toks[0] == toks[1]).float().mean() > 0.9, (toks[0], toks[1])
+
+
+def test_edge_shapes():
+    """Ragged / degenerate shapes through the module API: batch 1, a text-only prefix shorter than text_len (no shift), one
+    image token, n not a multiple of any tile."""
+    import dalle_pytorch_b200 as D
+    torch.manual_seed(13)
+    t = D.Transformer(dim=64, depth=2, seq_len=24, heads=2, image_fmap_size=4, shift_tokens=True,
+                      attn_types=('full', 'axial_row')).cuda()
+    cfg = OracleConfig(dim=64, depth=2, heads=2, text_seq_len=8, fmap=4, num_text_tokens=50, num_image_tokens=32,
+                       attn_types=('full', 'axial_row'))
+    sd = {('transformer.' + k): v.detach().cpu() for k, v in t.state_dict().items()}
+    for n in (1, 5, 9, 10, 23):
+        x = torch.randn(1, n, 64)
+        got = t(x.cuda())
+        want = transformer_forward(x, sd, cfg)
+        report(f'transformer n={n}', got, want, RTOL, ATOL)
