@@ -15,6 +15,7 @@
 //   wgrad   : A MN-major (dY [rows, out]),    B MN-major (X [rows, in])     -> C = dW [out, in] fp32
 // (UMMA shared-memory descriptors support both majors for bf16; MN-major tiles are loaded as 64x64 boxes.)
 #include <cuda.h>
+#include <atomic>
 
 #include <cstdlib>
 #include <cstring>
@@ -35,6 +36,7 @@ constexpr int BLOCK_K = 64;          // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 320;          // 2 + 8 warps
 constexpr int NUM_EPI_WARPS = 8;
+constexpr int SCHED_DEPTH = 4;                 // tile-id ring between the producer and the MMA / epilogue roles
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;   // per epilogue warp
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr int BOX_MN_BYTES = 64 * BLOCK_K * 2;         // one 64(mn) x 64(k) MN-major box = 8 KB
@@ -63,17 +65,28 @@ struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * SCHED_DEPTH) * 8 + 16 + SCHED_DEPTH * 4 + 12;
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFFSET = EPI_OFFSET + NUM_EPI_WARPS * EPI_STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + BAR_BYTES + 1024;   // +1024: manual 1 KB alignment slack
 };
 
+// Dynamic tile scheduler: every tile is drawn with atomicAdd(counter).  A CTA that is not resident when the kernel starts
+// (an SM is held by a concurrent kernel, e.g. the NCCL all-reduce of the previous gradient bucket, whose shared memory
+// keeps a 200 KB GEMM CTA out) simply takes no tiles, instead of leaving its static share for the very end (measured:
+// the dgrad GEMM overlapped by the all-reduce went 0.14 -> 0.24 ms with the static schedule).  Exactly
+// num_tiles + gridDim.x draws happen per launch (one failing draw per CTA), so the thread that draws the last value
+// resets the counter for the next launch using the slot; the host rotates over SCHED_SLOTS counters so launches that run
+// concurrently on different streams never share one.
+constexpr int SCHED_SLOTS = 256;
+__device__ unsigned int g_sched_counter[SCHED_SLOTS];
+static std::atomic<unsigned int> g_launch_seq{0};
+
 template <int BLOCK_N, int EPI, bool A_MN, bool B_MN, bool EPI_COLS>
 // 320 threads are allocated as 12 warps of registers (4-warp granularity) -> 168 registers per thread at most
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, int k_splits,
-                    EpiArgs e) {
+                    int sched_slot, EpiArgs e) {
   using L = SmemLayout<BLOCK_N>;
   constexpr int STAGES = L::STAGES;
   constexpr int B_STAGE_BYTES = L::B_STAGE_BYTES;
@@ -90,15 +103,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t empty_bar = smem_u32(bars + STAGES);          // [STAGES]
   const uint32_t tfull_bar = smem_u32(bars + 2 * STAGES);      // [2]
   const uint32_t tempty_bar = smem_u32(bars + 2 * STAGES + 2); // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t sfull_bar = smem_u32(bars + 2 * STAGES + 4);                 // [SCHED_DEPTH] tile id published
+  const uint32_t sempty_bar = smem_u32(bars + 2 * STAGES + 4 + SCHED_DEPTH);  // [SCHED_DEPTH] tile id consumed by MMA + epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * SCHED_DEPTH);
+  volatile int* sched_tile = reinterpret_cast<volatile int*>(tmem_slot + 4);  // [SCHED_DEPTH]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  unsigned int first_draw = 0;
+  const bool dyn = sched_slot >= 0;                            // sched_slot < 0: static round-robin schedule (A/B switch)
+  if (threadIdx.x == 0) first_draw = dyn ? atomicAdd(&g_sched_counter[sched_slot], 1u) : blockIdx.x;   // latency hides behind the setup below
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, NUM_EPI_WARPS * 32); }
+    for (int s = 0; s < SCHED_DEPTH; ++s) { mbar_init(sfull_bar + 8 * s, 1); mbar_init(sempty_bar + 8 * s, 1 + NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -121,7 +141,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ================================ TMA producer ================================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int ss = 0; uint32_t sph = 0;
+      unsigned int* counter = &g_sched_counter[dyn ? sched_slot : 0];
+      const unsigned int last_draw = dyn ? static_cast<unsigned int>(num_tiles) + gridDim.x - 1u : 0xffffffffu;
+      if (first_draw == last_draw) atomicExch(counter, 0u);
+      int tile = static_cast<int>(first_draw);
+      while (true) {
+        mbar_wait(sempty_bar + 8 * ss, sph ^ 1);             // publish the tile id (or the end marker) to the other roles
+        sched_tile[ss] = tile;
+        mbar_arrive(sfull_bar + 8 * ss);
+        if (++ss == SCHED_DEPTH) { ss = 0; sph ^= 1; }
+        if (tile >= num_tiles) break;
+        const unsigned int drawn = dyn ? atomicAdd(counter, 1u) : static_cast<unsigned int>(tile) + gridDim.x;   // next tile; the latency hides behind this tile's loads
         const int mn = tile % num_mn, split = tile / num_mn;
         const int m0 = (mn / num_n) * BLOCK_M;          // n-fastest: CTAs running together share the A tile through L2
         const int n0 = (mn % num_n) * BLOCK_N;
@@ -152,6 +183,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+        if (drawn == last_draw) atomicExch(counter, 0u);    // last draw of this launch: leave the slot clean
+        tile = static_cast<int>(drawn);
       }
     }
     __syncwarp();
@@ -169,7 +202,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr uint32_t B_KSTEP = B_MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
       int s = 0; uint32_t ph = 0;
       int as = 0; uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int ss = 0; uint32_t sph = 0;
+      while (true) {
+        mbar_wait(sfull_bar + 8 * ss, sph);
+        const int tile = sched_tile[ss];
+        mbar_arrive(sempty_bar + 8 * ss);
+        if (++ss == SCHED_DEPTH) { ss = 0; sph ^= 1; }
+        if (tile >= num_tiles) break;
         mbar_wait(tempty_bar + 8 * as, aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + as * BLOCK_N;
@@ -199,7 +238,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* stage = reinterpret_cast<float*>(smem + L::EPI_OFFSET + ew * EPI_STAGE_BYTES);
     const int lrow = lane >> 4, lcol = (lane & 15) << 1;
     int as = 0; uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int ss = 0; uint32_t sph = 0;
+    while (true) {
+      mbar_wait(sfull_bar + 8 * ss, sph);
+      const int tile = sched_tile[ss];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sempty_bar + 8 * ss);
+      if (++ss == SCHED_DEPTH) { ss = 0; sph ^= 1; }
+      if (tile >= num_tiles) break;
       const int mn = tile % num_mn;
       const int m0 = (mn / num_n) * BLOCK_M;          // n-fastest: CTAs running together share the A tile through L2
       const int n0 = (mn % num_n) * BLOCK_N;
@@ -335,7 +381,9 @@ int launch_cfg_mode(const db200_gemm_params& p, cudaStream_t st) {
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
   EpiArgs e = make_epi_args(p);
   e.atomic_c = k_splits > 1;
-  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(tmA, tmB, p.M, p.N, p.K, k_splits, e);
+  static const bool static_sched = [] { const char* v = std::getenv("DALLE_B200_SCHED"); return v && !std::strcmp(v, "static"); }();
+  const int sched_slot = static_sched ? -1 : static_cast<int>(g_launch_seq.fetch_add(1, std::memory_order_relaxed) % SCHED_SLOTS);
+  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(tmA, tmB, p.M, p.N, p.K, k_splits, sched_slot, e);
   DB200_LAUNCH_OK("gemm_tcgen05_kernel");
   return DB200_OK;
 }

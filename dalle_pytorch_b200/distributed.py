@@ -147,17 +147,26 @@ class GradAllReducer:
         for bi, (_, _, ps) in enumerate(self.buckets):
             for p in ps:
                 self.bucket_of[p] = bi
+        self._has_avg = dist.get_backend(process_group) == 'nccl'
+        self._seen = set()
         self._pending = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
         self._works = []
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        for p in self.params:
+            p._b200_reducer = self
         self.zero_grad()
 
     # -- per-step protocol: zero_grad() -> forward/backward -> finish() -> optimizer.step() ----------------
     def zero_grad(self):
-        self.flat.zero_()
+        """Start of a step.  Gradients are NOT pre-zeroed views any more: autograd writes a fresh gradient tensor per
+        parameter and the post-accumulate hook moves it into the flat buffer (one copy instead of memset + read-modify-write),
+        then points .grad at the view."""
         for p in self.params:
-            p.grad = self.views[p]
+            p.grad = None
+            p._b200_uses = 0
+            p._b200_acc = 0
+        self._seen = set()
         for bi, (_, _, ps) in enumerate(self.buckets):
             self._pending[bi] = len(ps)
             self._launched[bi] = False
@@ -167,12 +176,39 @@ class GradAllReducer:
         s, e, _ = self.buckets[bi]
         self._launched[bi] = True
         if self.world > 1:
-            self._works.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+            # AVG folds the 1/world into the collective (NCCL); gloo (CPU tests) has no AVG -> SUM + scale in finish()
+            op = dist.ReduceOp.AVG if (self.average and self._has_avg) else dist.ReduceOp.SUM
+            self._works.append(dist.all_reduce(self.flat[s:e], op=op, group=self.pg, async_op=True))
+
+    def _adopt(self, p):
+        v = self.views[p]
+        if p.grad is None:
+            v.zero_()
+        elif p.grad.data_ptr() != v.data_ptr():
+            v.copy_(p.grad)
+        p.grad = v
+        self._seen.add(p)
+
+    # direct-write protocol used by the fused sub-layer backward (functional.py::_slot/_commit): the weight-gradient GEMM
+    # writes into the flat-buffer view itself, so neither a memset nor a copy of that gradient is ever made
+    def direct_slot(self, p):
+        if p in self._seen or p not in self.views:
+            return None
+        return self.views[p]
+
+    def direct_done(self, p):
+        p.grad = self.views[p]
+        self._seen.add(p)
+        self._count(p)
+
+    def _count(self, p):
+        bi = self.bucket_of[p]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0 and not self._launched[bi]:
+            self._launch(bi)
 
     def _on_grad(self, p):
-        if p.grad is not None and p.grad.data_ptr() != self.views[p].data_ptr():
-            self.views[p].copy_(p.grad)              # someone replaced .grad (e.g. zero_grad(set_to_none=True)): adopt it
-            p.grad = self.views[p]
+        self._adopt(p)
         bi = self.bucket_of[p]
         self._pending[bi] -= 1
         if self._pending[bi] == 0 and not self._launched[bi]:
@@ -184,19 +220,20 @@ class GradAllReducer:
         for bi, (_, _, ps) in enumerate(self.buckets):
             if not self._launched[bi]:
                 for p in ps:
-                    if p.grad is not None and p.grad.data_ptr() != self.views[p].data_ptr():
-                        self.views[p].copy_(p.grad)
-                        p.grad = self.views[p]
+                    if p not in self._seen:
+                        self._adopt(p)
                 self._launch(bi)
         for w in self._works:
             w.wait()
         self._works = []
-        if self.average and self.world > 1:
+        if self.average and self.world > 1 and not self._has_avg:
             self.flat.mul_(1.0 / self.world)
 
     def remove(self):
         for h in self._hooks:
             h.remove()
+        for p in self.params:
+            p._b200_reducer = None
 
 
 class NCCLBackend(DistributedBackend):

@@ -76,21 +76,23 @@ def attn_sublayer_forward(g: SublayerGeom, x_in, resid, ln_w, ln_b, w_qkv, w_out
     return out, ctx
 
 
-def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t, sin_t, key_mask=None, dres=None):
+def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t, sin_t, key_mask=None, dres=None, wslots=None):
     """d_out: gradient w.r.t. `out` [b,n,d] fp32.  Returns (dx_in, dln_w, dln_b, dw_qkv, dw_out, db_out, dscale).
     `dres` (optional, fp32) is added to dx_in inside the LayerNorm-backward kernel (sequential executor: the residual
-    branch gradient, which equals d_out)."""
+    branch gradient, which equals d_out).  `wslots` (optional) = (dw_qkv_out, dw_out_out): preallocated fp32 destinations
+    (views into the data-parallel flat gradient buffer) the weight-gradient GEMMs write straight into."""
     x_in, mean, rstd, a1, wq, wo, q, k, v, o, lse, y, shift = ctx
+    s_qkv, s_out = wslots if wslots is not None else (None, None)
     b, n, d = x_in.shape
     M = b * n
     d_out = d_out.contiguous().view(M, d)
     sc = None if scale is None else scale.detach().reshape(-1).contiguous()
     dy, dscale, db_out = ops.scale_bwd(d_out, y, sc, sign, g.dtype)
     d_o = ops.gemm_store(dy, wo, a_mn=False, b_mn=True)                                   # [M, inner]
-    dw_out = ops.gemm_store(dy, o.view(M, -1), a_mn=True, b_mn=True, out_dtype=torch.float32)   # [d, inner]
+    dw_out = ops.gemm_store(dy, o.view(M, -1), a_mn=True, b_mn=True, out_dtype=torch.float32, out=s_out)   # [d, inner]
     dqkv = ops.attn_bwd(g.attn_spec, q, k, v, o, lse, d_o.view(b, n, -1), cos_t, sin_t, g.q_scale, key_mask)
     da1 = ops.gemm_store(dqkv, wq, a_mn=False, b_mn=True)                                 # [M, d]
-    dw_qkv = ops.gemm_store(dqkv, a1, a_mn=True, b_mn=True, out_dtype=torch.float32)      # [3*inner, d]
+    dw_qkv = ops.gemm_store(dqkv, a1, a_mn=True, b_mn=True, out_dtype=torch.float32, out=s_qkv)      # [3*inner, d]
     dln_w = dln_b = None
     if g.do_ln:
         dln_w = torch.zeros(d, device=x_in.device, dtype=torch.float32)
@@ -122,9 +124,10 @@ def ff_sublayer_forward(g: SublayerGeom, x_in, resid, ln_w, ln_b, w1, b1, w2, b2
     return out, ctx
 
 
-def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=None):
-    """Returns (dx_in, dln_w, dln_b, dw1, db1, dw2, db2, dscale)."""
+def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=None, wslots=None):
+    """Returns (dx_in, dln_w, dln_b, dw1, db1, dw2, db2, dscale).  `wslots` = (dw1_out, dw2_out), see attn_sublayer_backward."""
     x_in, mean, rstd, a2, w1c, w2c, u, h, y, shift = ctx
+    s_w1, s_w2 = wslots if wslots is not None else (None, None)
     b, n, d = x_in.shape
     M = b * n
     d_out = d_out.contiguous().view(M, d)
@@ -136,9 +139,9 @@ def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=No
     else:   # measured faster on B200 (profiles/): plain dgrad GEMM + one streaming pass that also forms the bias gradient
         dh = ops.gemm_store(dy, w2c, a_mn=False, b_mn=True)                               # [M, H]
         du, db1 = ops.geglu_bwd(dh, u)
-    dw2 = ops.gemm_store(dy, h, a_mn=True, b_mn=True, out_dtype=torch.float32)            # [d, H]
+    dw2 = ops.gemm_store(dy, h, a_mn=True, b_mn=True, out_dtype=torch.float32, out=s_w2)            # [d, H]
     da2 = ops.gemm_store(du, w1c, a_mn=False, b_mn=True)                                  # [M, d]
-    dw1 = ops.gemm_store(du, a2, a_mn=True, b_mn=True, out_dtype=torch.float32)           # [2H, d]
+    dw1 = ops.gemm_store(du, a2, a_mn=True, b_mn=True, out_dtype=torch.float32, out=s_w1)           # [2H, d]
     dln_w = dln_b = None
     if g.do_ln:
         dln_w = torch.zeros(d, device=x_in.device, dtype=torch.float32)
@@ -153,6 +156,30 @@ def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=No
 # =====================================================================================================
 # autograd wrappers
 # =====================================================================================================
+def _note_use(*params):
+    """Forward-time use count per parameter (reset by GradAllReducer.zero_grad): a weight used by ONE sub-layer in the
+    step may have its gradient GEMM write directly into the flat data-parallel buffer; shared weights
+    (shared_attn_ids / shared_ff_ids, transformer.py:261-292) go through autograd's accumulation."""
+    for p in params:
+        if getattr(p, '_b200_reducer', None) is not None:
+            p._b200_uses = getattr(p, '_b200_uses', 0) + 1
+
+
+def _slot(p):
+    r = getattr(p, '_b200_reducer', None)
+    if r is None or getattr(p, '_b200_uses', 0) != 1:
+        return None
+    return r.direct_slot(p)
+
+
+def _commit(p, slot, grad):
+    """grad was written into `slot` (the flat-buffer view): tell the reducer and hand autograd nothing."""
+    if slot is None:
+        return grad
+    p._b200_reducer.direct_done(p)
+    return None
+
+
 class AttnSublayerFn(torch.autograd.Function):
     """out = resid + sign*scale*Attn(Shift(LN(x_in))).  If `resid_is_input`, resid := x_in and the residual-branch
     gradient is fused into the LayerNorm backward kernel."""
@@ -168,6 +195,8 @@ class AttnSublayerFn(torch.autograd.Function):
         ctx.saved = saved
         ctx.ln_w, ctx.scale = ln_w, scale
         ctx.has_resid = resid is not None
+        ctx.wparams = (w_qkv, w_out)
+        _note_use(w_qkv, w_out)
         return out
 
     @staticmethod
@@ -175,8 +204,11 @@ class AttnSublayerFn(torch.autograd.Function):
         g = ctx.g
         d_out = d_out.contiguous()
         dres = d_out if ctx.resid_is_input else None
+        slots = tuple(_slot(p) for p in ctx.wparams)
         dx, dln_w, dln_b, dw_qkv, dw_out, db_out, dscale = attn_sublayer_backward(
-            g, ctx.saved, d_out, ctx.ln_w, ctx.scale, ctx.sign, ctx.cos_t, ctx.sin_t, ctx.key_mask, dres=dres)
+            g, ctx.saved, d_out, ctx.ln_w, ctx.scale, ctx.sign, ctx.cos_t, ctx.sin_t, ctx.key_mask, dres=dres, wslots=slots)
+        dw_qkv = _commit(ctx.wparams[0], slots[0], dw_qkv)
+        dw_out = _commit(ctx.wparams[1], slots[1], dw_out)
         ctx.saved = None
         d_resid = d_out if (ctx.has_resid and not ctx.resid_is_input) else None
         return (None, None, None, None, None, None, dx, d_resid, dln_w, dln_b, dw_qkv, dw_out, db_out, dscale)
@@ -191,14 +223,19 @@ class FFSublayerFn(torch.autograd.Function):
         ctx.saved = saved
         ctx.ln_w, ctx.scale = ln_w, scale
         ctx.has_resid = resid is not None
+        ctx.wparams = (w1, w2)
+        _note_use(w1, w2)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         d_out = d_out.contiguous()
         dres = d_out if ctx.resid_is_input else None
+        slots = tuple(_slot(p) for p in ctx.wparams)
         dx, dln_w, dln_b, dw1, db1, dw2, db2, dscale = ff_sublayer_backward(ctx.g, ctx.saved, d_out, ctx.ln_w, ctx.scale, ctx.sign,
-                                                                              dres=dres)
+                                                                              dres=dres, wslots=slots)
+        dw1 = _commit(ctx.wparams[0], slots[0], dw1)
+        dw2 = _commit(ctx.wparams[1], slots[1], dw2)
         ctx.saved = None
         d_resid = d_out if (ctx.has_resid and not ctx.resid_is_input) else None
         return (None, None, None, dx, d_resid, dln_w, dln_b, dw1, db1, dw2, db2, dscale)

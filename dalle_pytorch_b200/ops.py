@@ -149,9 +149,11 @@ def gemm_store(A, B, a_mn=False, b_mn=False, out_dtype=None, bias=None, backend=
         out_dtype = out_dtype or A.dtype
         C = None
     # weight-gradient shapes (few output tiles, very long K): let the kernel split K; it needs a zeroed fp32 C
-    split_ok = out is None and out_dtype == torch.float32 and bias is None and A.dtype == torch.bfloat16 and M * N <= 4096 * 1024 and K >= 4096
+    split_ok = out_dtype == torch.float32 and bias is None and A.dtype == torch.bfloat16 and M * N <= 4096 * 1024 and K >= 4096
     if C is None:
         C = (torch.zeros if split_ok else torch.empty)(M, N, device=A.device, dtype=out_dtype)
+    elif split_ok:
+        C.zero_()
     P = _base(M, N, K, A, A.shape[1], a_mn, B, B.shape[1], b_mn, EPI_STORE, backend)
     P.C, P.ldc, P.c_dtype, P.bias, P.split_k_ok = _p(C), N, dt_code(out_dtype), _p(bias), int(split_ok)
     _gemm(P)

@@ -11,7 +11,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .functional import (attn_sublayer_forward, attn_sublayer_backward, ff_sublayer_forward, ff_sublayer_backward)
+from .functional import (attn_sublayer_forward, attn_sublayer_backward, ff_sublayer_forward, ff_sublayer_backward, _note_use)
 
 
 def route_args(router, args, depth):
@@ -65,6 +65,13 @@ def _accumulate(param, grad):
         param.grad = grad.contiguous()
     else:
         param.grad.add_(grad)
+    # data-parallel overlap: once every use of the parameter in this step has contributed, hand it to the reducer
+    # (it copies into the flat buffer and launches the bucket's all-reduce when the bucket is complete)
+    r = getattr(param, '_b200_reducer', None)
+    if r is not None:
+        param._b200_acc = getattr(param, '_b200_acc', 0) + 1
+        if param._b200_acc == getattr(param, '_b200_uses', 0):
+            r._on_grad(param)
 
 
 def _run_bwd(p, ctx, d_out, sign):
@@ -90,6 +97,8 @@ class _ReversibleFunction(torch.autograd.Function):
     def forward(ctx, x, plans):
         x1 = x2 = x                                             # cat([x, x]) then chunk (reversible.py:150, 61)
         for pf, pg in plans:
+            for pl in (pf, pg):
+                _note_use(*[t for t in pl.params.values() if t is not None])
             x1, _ = _run_fwd(pf, x2, x1, 1.0, save=False)       # y1 = x1 + f(x2)
             x2, _ = _run_fwd(pg, x1, x2, 1.0, save=False)       # y2 = x2 + g(y1)
         ctx.plans = plans

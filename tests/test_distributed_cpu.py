@@ -30,6 +30,8 @@ def _worker(rank, world, port, q):
     model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 4))
     extra = torch.nn.Parameter(torch.zeros(5))                     # receives its gradient outside autograd
     model.register_parameter('extra', extra)
+    direct = torch.nn.Parameter(torch.zeros(3, 2))                 # gradient written straight into the flat buffer (fused wgrad path)
+    model.register_parameter('direct', direct)
     opt = torch.optim.SGD(model.parameters(), lr=0.1)
     model, opt, _, _ = be.distribute(model=model, optimizer=opt)
     w0 = [p.detach().clone() for p in model.parameters()]
@@ -37,12 +39,21 @@ def _worker(rank, world, port, q):
     x = torch.randn(3, 8)
     loss = model(x).square().mean()
     loss.backward()
-    extra.grad.add_(torch.full((5,), float(rank + 1)))             # manual accumulation into the flat view
+    red = model.grad_reducer
+    direct._b200_uses = 1                                          # what functional._note_use records in forward
+    slot = red.direct_slot(direct)
+    assert slot is not None and slot.data_ptr() == red.views[direct].data_ptr()
+    slot.copy_(torch.full((3, 2), 10.0 * (rank + 1)))              # stands in for the weight-gradient GEMM
+    red.direct_done(direct)
+    assert red.direct_slot(direct) is None                         # a second use in the same step must go through autograd
+    assert extra.grad is None                                      # gradients start each step unset (no memset of the flat buffer)
+    extra.grad = torch.full((5,), float(rank + 1))                 # written outside autograd; finish() adopts it into the flat buffer
     model.grad_reducer.finish()
     grads = [p.grad.detach().clone() for p in model.parameters()]
     avg_loss = be.average_all(loss.detach())
-    opt.step()                                                     # pre-hook finish() is idempotent, post-hook re-zeros
-    assert all(float(p.grad.abs().sum()) == 0 for p in model.parameters())
+    assert all(p.grad.data_ptr() == model.grad_reducer.views[p].data_ptr() for p in model.parameters())
+    opt.step()                                                     # pre-hook finish() is idempotent, post-hook resets the step
+    assert all(p.grad is None for p in model.parameters())
     q.put((rank, [w.numpy() for w in w0], [g.numpy() for g in grads], float(avg_loss), float(loss.detach())))
     be.local_barrier()
     import torch.distributed as dist
@@ -67,6 +78,7 @@ def test_flat_allreduce_world2_gloo():
     for a, b in zip(g_a, g_b):
         assert np.allclose(a, b), 'ranks disagree on the reduced gradient'
     assert np.allclose(g_a[0], np.full(5, 1.5))                    # `extra` is registered on the container -> first; mean of 1 and 2
+    assert np.allclose(g_a[1], np.full((3, 2), 15.0))              # `direct`: mean of 10 and 20, written through direct_slot/direct_done
     assert abs(al_a - (l_a + l_b) / 2) < 1e-6 and abs(al_a - al_b) < 1e-7
     # cross-check against a single-process evaluation of the same two micro-batches
     torch.manual_seed(100)
@@ -79,5 +91,5 @@ def test_flat_allreduce_world2_gloo():
         model(x).square().mean().backward()
         for t, p in zip(tot, model.parameters()):
             t += p.grad / 2
-    for t, g in zip(tot, g_a[1:5]):
+    for t, g in zip(tot, g_a[2:6]):
         assert np.allclose(t.numpy(), g, atol=1e-6)

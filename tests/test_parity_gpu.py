@@ -302,3 +302,55 @@ def test_edge_shapes():
         got = t(x.cuda())
         want = transformer_forward(x, sd, cfg)
         report(f'transformer n={n}', got, want, RTOL, ATOL)
+
+
+@pytest.mark.parametrize('reversible', [False, True])
+def test_flat_gradient_buffer_direct_write_world1(reversible):
+    """Data-parallel plumbing on one GPU (NCCL world of 1): with NCCLBackend attached, the weight-gradient GEMMs write
+    straight into the flat all-reduce buffer (functional._slot/_commit), shared weights fall back to autograd
+    accumulation, the reversible executor hands gradients over as they complete; the gradients must equal the ones
+    computed without the reducer."""
+    import os
+    import torch.distributed as dist
+    import dalle_pytorch_b200 as D
+    from dalle_pytorch_b200.distributed import NCCLBackend
+    created = False
+    if not dist.is_initialized():
+        os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', '29617'
+        os.environ['RANK'], os.environ['WORLD_SIZE'], os.environ['LOCAL_RANK'] = '0', '1', '0'
+        created = True
+    try:
+        kw = dict(dim=256, num_text_tokens=200, text_seq_len=16, depth=4, heads=4, dim_head=64, reversible=reversible,
+                  attn_types=('full', 'axial_row'), shared_attn_ids=(0, 1, 0, 1), shared_ff_ids=(0, 1, 2, 3))
+        torch.manual_seed(3)
+        m = D.DALLE(vae=D.TokenVAE(image_size=64, num_layers=3, num_tokens=64), **kw).cuda().train()
+        text = torch.randint(1, 200, (2, 16)).cuda()
+        image = torch.randint(0, 64, (2, 64)).cuda()
+        for dt in (torch.float32, torch.bfloat16):
+            with D.compute_dtype_ctx(dt):
+                m.zero_grad(set_to_none=True)
+                m(text, image, return_loss=True).backward()
+                want = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+                be = NCCLBackend()
+                be.initialize()
+                be.distribute(model=m)
+                red = m.grad_reducer
+                for _ in range(2):                                           # two steps: the per-step reset must work
+                    red.zero_grad()
+                    m(text, image, return_loss=True).backward()
+                    red.finish()
+                direct = 0
+                for k, p in m.named_parameters():
+                    if k not in want:
+                        continue
+                    assert p.grad.data_ptr() == red.views[p].data_ptr(), k
+                    tol = 1e-5 if dt == torch.float32 else 2e-2
+                    report(f'{"rev" if reversible else "seq"} {dt} grad {k}', p.grad, want[k], tol, tol * float(want[k].abs().max()) + 1e-7)
+                    direct += int(getattr(p, '_b200_uses', 0) == 1 and p.dim() == 2)
+                assert direct >= 4
+                red.remove()
+                for p in m.parameters():
+                    p.grad = None
+    finally:
+        if created and dist.is_initialized():
+            dist.destroy_process_group()
