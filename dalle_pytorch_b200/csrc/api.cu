@@ -58,6 +58,7 @@ int attn_bwd_mma_launch(const db200_attn_bwd_params& p, cudaStream_t st);
 bool attn_tc_supported(const db200_attn_fwd_params& p);
 int attn_fwd_tc_launch(const db200_attn_fwd_params& p, cudaStream_t st);
 int attn_bwd_tc_launch(const db200_attn_bwd_params& p, cudaStream_t st);
+int attn_debug_timeline(long long* out, int count);
 
 static bool dtype_ok(int d) { return d == DB200_F32 || d == DB200_BF16; }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -78,6 +79,8 @@ using namespace db200;
 extern "C" {
 
 int dalle_b200_version(void) { return DALLE_B200_VERSION; }
+// debug probe (not part of the documented ABI): clock64() timeline of one dK/dV CTA, see attn_tc.cu
+int dalle_b200_debug_attn_timeline(long long* out, int count) { return db200::attn_debug_timeline(out, count); }
 
 const char* dalle_b200_last_error(void) { return last_error_slot().c_str(); }
 

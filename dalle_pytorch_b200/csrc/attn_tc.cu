@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / P.heads, h = bh - b * P.heads;
-  const int q0 = blockIdx.x * TQ;
+  // heaviest query tiles first: with a causal pattern the last tile of a head does the most key tiles; scheduling it first
+  // keeps the final partial wave short
+  const int q0 = (gridDim.x - 1 - blockIdx.x) * TQ;
   const int off = g.n_k - g.n_q;
   const int q_last = min(q0 + TQ, g.n_q) - 1;
   const int nkt = (g.n_k + FK - 1) / FK;
@@ -159,7 +161,8 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    // (whole warp converged; one elected lane issues each block of tcgen05 instructions, see elect_one())
+    {
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, FK, false, false);    // S = Q K^T : both K-major
       constexpr uint32_t IDESC_O = make_idesc_bf16(128, 64, false, true);     // O = P V   : A K-major (TMEM / smem), B N-major
       mbar_wait(q_full, 0);
@@ -173,28 +176,30 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
         // (S of this tile overwrites the columns P of the previous tile was read from: safe, the tensor pipe executes the
         //  previous O += P V before this S = Q K^T because both are issued in order by this thread)
         const uint64_t dk = make_smem_desc(sK + s * FK_BYTES, 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
-        umma_commit(s_full);
+          for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
+          umma_commit(s_full);
+        }
+        __syncwarp();
         mbar_wait(p_ready, it & 1);
         tc_fence_after();
         // V tile image [64 keys][64 dh] read as the N-major B operand: K = keys (16 rows = 2048 B per step), N = dh
         const uint64_t dv = make_smem_desc(sV + s * FK_BYTES, FK_BYTES, 1024);
+        const uint64_t dp = make_smem_desc(sP, 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < FK / 16; ++k) {
-          if constexpr (P_TMEM) {
-            umma_bf16_ts(tO, tP + 8 * k, dv + 128 * k, IDESC_O, (it | k) != 0);
-          } else {
-            const uint64_t dp = make_smem_desc(sP, 16, 1024);
-            umma_bf16(tO, dp + 2 * k, dv + 128 * k, IDESC_O, (it | k) != 0);
+          for (int k = 0; k < FK / 16; ++k) {
+            if constexpr (P_TMEM) umma_bf16_ts(tO, tP + 8 * k, dv + 128 * k, IDESC_O, (it | k) != 0);
+            else umma_bf16(tO, dp + 2 * k, dv + 128 * k, IDESC_O, (it | k) != 0);
           }
+          umma_commit(kv_empty + 8 * s);
+          umma_commit(o_done);
         }
-        umma_commit(kv_empty + 8 * s);
-        umma_commit(o_done);
+        __syncwarp();
         ++it;
       }
     }
-    __syncwarp();
   } else {
     // ===================================== softmax / epilogue =====================================
     const int quarter = warp & 3;
@@ -319,59 +324,107 @@ __global__ void attn_delta_tc_kernel(const bf16* __restrict__ O, const bf16* __r
   if (lane == 0) delta[(long long)bh * n + i] = s;
 }
 
+// Timeline probe (debug only, DALLE_B200_ATTN_WAIT bit 2): CTA (1,0) of the dK/dV kernel records clock64() at the hand-off
+// points of its first iterations; read back with dalle_b200_debug_attn_timeline().
+__device__ long long g_attn_dbg[256];
+#define ATTN_DBG(slot) do { if (dbg && it < 6) g_attn_dbg[(slot) * 6 + it] = clock64(); } while (0)
+
 struct BwdArgs {
   const float* lse; const float* delta; const uint8_t* key_mask; const float* cos_t; const float* sin_t; float q_scale;
-  bf16* dqkv; int heads, batch;
+  bf16* dqkv; int heads, batch; int wait_mode;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// 64 fp32 accumulator columns of this thread's row -> (rotary adjoint, optional scale) -> bf16 -> dst[0..63]
+// 32 fp32 accumulator columns [32c, 32c+32) of this thread's row -> (rotary adjoint, optional scale) -> bf16 -> dst[32c ..]
+__device__ __forceinline__ void store_grad_cols(uint32_t taddr, bf16* dst, const float* cos_row, const float* sin_row, float scale, bool valid,
+                                                int c) {
+  uint32_t r[32];
+  tmem_ld32(taddr + c * 32, r);
+  tmem_ld_wait();
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]) * scale;
+      if (cos_row) {
+        const int pi = (c * 32 + j * 8) >> 1;                      // pair index of the first pair of this granule
+        const float4 cc = *reinterpret_cast<const float4*>(cos_row + pi);
+        const float4 ss = *reinterpret_cast<const float4*>(sin_row + pi);
+        rotary_adjoint(cc.x, ss.x, v[0], v[1]); rotary_adjoint(cc.y, ss.y, v[2], v[3]);
+        rotary_adjoint(cc.z, ss.z, v[4], v[5]); rotary_adjoint(cc.w, ss.w, v[6], v[7]);
+      }
+      uint4 u;
+      u.x = pack2(v[0], v[1]); u.y = pack2(v[2], v[3]); u.z = pack2(v[4], v[5]); u.w = pack2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(dst + c * 32 + j * 8) = u;
+    }
+  }
+}
 __device__ __forceinline__ void store_grad_row(uint32_t taddr, bf16* dst, const float* cos_row, const float* sin_row, float scale, bool valid) {
 #pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
-    uint32_t r[32];
-    tmem_ld32(taddr + c * 32, r);
-    tmem_ld_wait();
-    if (valid) {
+  for (int c = 0; c < 2; ++c) store_grad_cols(taddr, dst, cos_row, sin_row, scale, valid, c);
+}
+
+// softmax-backward of 16 columns of one row: p = exp(s - lse), ds = p * (dp - delta); packs 8 bf16 pairs each.
+// kLseCol: lse/delta vary along the columns (dK/dV kernel, read from smem) instead of being per-row constants (dQ kernel).
+template <bool kLseCol, bool kWantP>
+__device__ __forceinline__ void bwd_softmax16(const uint32_t* rs, const uint32_t* rd, uint32_t mb16, const float* ls, const float* dl,
+                                              float lse_r, float delta_r, uint32_t* pk, uint32_t* dk_) {
+  float l2[16], dd[16];
+  if constexpr (kLseCol) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float v[8];
+    for (int j = 0; j < 4; ++j) {
+      const float4 a = reinterpret_cast<const float4*>(ls)[j], b = reinterpret_cast<const float4*>(dl)[j];
+      l2[4 * j] = a.x * LOG2E; l2[4 * j + 1] = a.y * LOG2E; l2[4 * j + 2] = a.z * LOG2E; l2[4 * j + 3] = a.w * LOG2E;
+      dd[4 * j] = b.x; dd[4 * j + 1] = b.y; dd[4 * j + 2] = b.z; dd[4 * j + 3] = b.w;
+    }
+  }
+  if (mb16 == 0xffffu) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]) * scale;
-        if (cos_row) {
-          const int pi = (c * 32 + j * 8) >> 1;                      // pair index of the first pair of this granule
-          const float4 cc = *reinterpret_cast<const float4*>(cos_row + pi);
-          const float4 ss = *reinterpret_cast<const float4*>(sin_row + pi);
-          rotary_adjoint(cc.x, ss.x, v[0], v[1]); rotary_adjoint(cc.y, ss.y, v[2], v[3]);
-          rotary_adjoint(cc.z, ss.z, v[4], v[5]); rotary_adjoint(cc.w, ss.w, v[6], v[7]);
-        }
-        uint4 u;
-        u.x = pack2(v[0], v[1]); u.y = pack2(v[2], v[3]); u.z = pack2(v[4], v[5]); u.w = pack2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(dst + c * 32 + j * 8) = u;
-      }
+    for (int i = 0; i < 8; ++i) {
+      const float la = kLseCol ? l2[2 * i] : lse_r, lb = kLseCol ? l2[2 * i + 1] : lse_r;
+      const float da = kLseCol ? dd[2 * i] : delta_r, db = kLseCol ? dd[2 * i + 1] : delta_r;
+      const float p0 = ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -la));
+      const float p1 = ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -lb));
+      if constexpr (kWantP) pk[i] = pack2(p0, p1);
+      dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - da), p1 * (__uint_as_float(rd[2 * i + 1]) - db));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float la = kLseCol ? l2[2 * i] : lse_r, lb = kLseCol ? l2[2 * i + 1] : lse_r;
+      const float da = kLseCol ? dd[2 * i] : delta_r, db = kLseCol ? dd[2 * i + 1] : delta_r;
+      const float p0 = sel_bit(mb16, 2 * i, ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -la)), 0.f);
+      const float p1 = sel_bit(mb16, 2 * i + 1, ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -lb)), 0.f);
+      if constexpr (kWantP) pk[i] = pack2(p0, p1);
+      dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - da), p1 * (__uint_as_float(rd[2 * i + 1]) - db));
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Backward tiles are 128 rows x BW = 64 columns so that each kernel needs only 256 TMEM columns and ~64 KB of smem: TWO CTAs
-// run per SM and one CTA's softmax-backward overlaps the other's MMAs.  P / dS (bf16) are written over the first half of the
-// S / dP columns they were computed from (each thread only overwrites columns of its own row that it has already read).
+// run per SM and one CTA's softmax-backward overlaps the other's MMAs.  Eight softmax warps per CTA: warps 2-5 own columns
+// [0,32) of the score tile, warps 6-9 columns [32,64) (a warp may only touch the TMEM lane quarter warp%4).  P / dS (bf16)
+// are written over the first half of the 32 columns each warp has itself read, i.e. packed columns [32c, 32c+16) for column
+// half c, so no warp overwrites scores another warp has not read yet; the TS-mode MMAs take their A operand from there.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int BW = 64;
 constexpr int HALF_TILE = BW * DH * 2;            // one [64 x 64] bf16 tile = 8 KB
+constexpr int BWD_THREADS = 320;                  // TMA warp, MMA warp, 8 softmax warps
+__device__ __forceinline__ uint32_t packed_kcol(int k) { return static_cast<uint32_t>(8 * k + (k >= 2 ? 16 : 0)); }   // A-operand column of k-step k
 
 // dK, dV : CTA = 128 keys; transposed score tile (rows = keys, columns = 64 queries) so that thread = key row.
-//   TMEM: S^T [0,64) (P^T bf16 aliased on [0,32)) | dP^T [64,128) (dS^T aliased on [64,96)) | dV [128,192) | dK [192,256)
+//   TMEM: S^T [0,64) (P^T bf16 aliased on [0,16)+[32,48)) | dP^T [64,128) (dS^T aliased on [64,80)+[96,112)) | dV [128,192) | dK [192,256)
 struct DkvSmem {
   static constexpr int K_OFF = 0, V_OFF = TILE_BYTES, Q_OFF = 2 * TILE_BYTES, DO_OFF = 2 * TILE_BYTES + 2 * HALF_TILE;
-  static constexpr int STAT_OFF = 2 * TILE_BYTES + 4 * HALF_TILE;   // lse*log2e [2][64], delta [2][64]
+  static constexpr int STAT_OFF = 2 * TILE_BYTES + 4 * HALF_TILE;   // lse [2][64], delta [2][64] (bulk-copied with the Q / dO tiles)
   static constexpr int BAR_OFF = STAT_OFF + 4 * BW * 4;
   static constexpr int TOTAL = BAR_OFF + 128 + 1024;
 };
 
-__global__ void __launch_bounds__(192, 2) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+__global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                                                                BwdArgs P, AttnGeom g) {
   using L = DkvSmem;
@@ -392,20 +445,24 @@ __global__ void __launch_bounds__(192, 2) attn_bwd_dkv_tc_kernel(const __grid_co
   const int k0 = blockIdx.x * TK, k1 = min(k0 + TK, n) - 1;
   const int nqt = (n + BW - 1) / BW;
   auto needed = [&](int qt) { return attn_tile_needed(g, qt * BW, min(qt * BW + BW, n) - 1, k0, k1); };
+  // per-query statistics ride along with the Q / dO tiles as two 1-D bulk copies when the rows are 16-byte aligned
+  const bool stats_tma = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.lse) | reinterpret_cast<uintptr_t>(P.delta)) & 15) == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(q_full + 8 * s, 1); mbar_init(q_empty + 8 * s, 1); }
-    mbar_init(st_full, 1); mbar_init(ps_ready, 128); mbar_init(acc_done, 1);
+    mbar_init(st_full, 1); mbar_init(ps_ready, BWD_THREADS - 64); mbar_init(acc_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x >= 64) s_lse[threadIdx.x - 64] = 0.f;      // [2][64] lse + [2][64] delta: stale entries must stay finite
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tSt = tmem, tdPt = tmem + 64, tdV = tmem + 128, tdK = tmem + 192, tPt = tmem, tdSt = tmem + 64;
+  const bool dbg = (P.wait_mode & 4) && blockIdx.x == 1 && blockIdx.y == 0 && (threadIdx.x == 32 || threadIdx.x == 64 || threadIdx.x == 192);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -417,15 +474,20 @@ __global__ void __launch_bounds__(192, 2) attn_bwd_dkv_tc_kernel(const __grid_co
         if (!needed(qt)) continue;
         const int s = it & 1;
         mbar_wait(q_empty + 8 * s, ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(q_full + 8 * s, 2 * HALF_TILE);
+        const uint32_t stat_bytes = stats_tma ? static_cast<uint32_t>(min(BW, n - qt * BW)) * 4u : 0u;
+        mbar_expect_tx(q_full + 8 * s, 2 * HALF_TILE + 2 * stat_bytes);
         tma_load_2d(sQ + s * HALF_TILE, &tmQ, q_full + 8 * s, 0, bh * n + qt * BW);
         tma_load_2d(sdO + s * HALF_TILE, &tmdO, q_full + 8 * s, h * DH, b * n + qt * BW);
+        if (stats_tma) {
+          bulk_load_1d(smem_u32(s_lse + s * BW), P.lse + (long long)bh * n + qt * BW, stat_bytes, q_full + 8 * s);
+          bulk_load_1d(smem_u32(s_delta + s * BW), P.delta + (long long)bh * n + qt * BW, stat_bytes, q_full + 8 * s);
+        }
         ++it;
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp converged; an elected lane issues (see elect_one())
       constexpr uint32_t IDESC_T = make_idesc_bf16(128, BW, false, false);    // S^T = K Q^T, dP^T = V dO^T
       constexpr uint32_t IDESC_G = make_idesc_bf16(128, 64, false, true);     // dV = P^T dO, dK = dS^T Q   (B N-major)
       mbar_wait(kv_full, 0);
@@ -436,27 +498,36 @@ __global__ void __launch_bounds__(192, 2) attn_bwd_dkv_tc_kernel(const __grid_co
         const int s = it & 1;
         mbar_wait(q_full + 8 * s, (it >> 1) & 1);
         tc_fence_after();
+        ATTN_DBG(0);                                         // MMA: Q/dO tile present
         const uint64_t dq = make_smem_desc(sQ + s * HALF_TILE, 16, 1024), ddo = make_smem_desc(sdO + s * HALF_TILE, 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16(tSt, dk + 2 * k, dq + 2 * k, IDESC_T, k != 0);
+          for (int k = 0; k < DH / 16; ++k) umma_bf16(tSt, dk + 2 * k, dq + 2 * k, IDESC_T, k != 0);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16(tdPt, dv + 2 * k, ddo + 2 * k, IDESC_T, k != 0);
-        umma_commit(st_full);
-        mbar_wait(ps_ready, it & 1);
+          for (int k = 0; k < DH / 16; ++k) umma_bf16(tdPt, dv + 2 * k, ddo + 2 * k, IDESC_T, k != 0);
+          umma_commit(st_full);
+        }
+        __syncwarp();
+        ATTN_DBG(1);                                         // MMA: S^T / dP^T issued
+        mbar_wait_mode(ps_ready, it & 1, (P.wait_mode >> 1) & 1);
         tc_fence_after();
+        ATTN_DBG(2);                                         // MMA: P^T / dS^T ready
         const uint64_t bq = make_smem_desc(sQ + s * HALF_TILE, HALF_TILE, 1024), bdo = make_smem_desc(sdO + s * HALF_TILE, HALF_TILE, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BW / 16; ++k) umma_bf16_ts(tdV, tPt + 8 * k, bdo + 128 * k, IDESC_G, (it | k) != 0);
+          for (int k = 0; k < BW / 16; ++k) umma_bf16_ts(tdV, tPt + packed_kcol(k), bdo + 128 * k, IDESC_G, (it | k) != 0);
 #pragma unroll
-        for (int k = 0; k < BW / 16; ++k) umma_bf16_ts(tdK, tdSt + 8 * k, bq + 128 * k, IDESC_G, (it | k) != 0);
-        umma_commit(q_empty + 8 * s);
-        umma_commit(acc_done);
+          for (int k = 0; k < BW / 16; ++k) umma_bf16_ts(tdK, tdSt + packed_kcol(k), bq + 128 * k, IDESC_G, (it | k) != 0);
+          umma_commit(q_empty + 8 * s);
+          umma_commit(acc_done);
+        }
+        __syncwarp();
+        ATTN_DBG(3);                                         // MMA: dV / dK issued
         ++it;
       }
     }
-    __syncwarp();
   } else {
-    const int quarter = warp & 3;
+    const int quarter = warp & 3, chunk = (warp - 2) >> 2;    // TMEM lane quarter; column half [32*chunk, 32*chunk+32)
     const int row = quarter * 32 + lane;
     const int kj = k0 + row;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
@@ -467,76 +538,70 @@ __global__ void __launch_bounds__(192, 2) attn_bwd_dkv_tc_kernel(const __grid_co
       if (!needed(qt)) continue;
       const int s = it & 1;
       const int qq0 = qt * BW, qq1 = min(qq0 + BW, n) - 1;
-      if (row < BW) {   // per-query statistics of this tile -> smem
-        const int qi = qq0 + row;
-        s_lse[s * BW + row] = qi < n ? P.lse[(long long)bh * n + qi] * LOG2E : 0.f;
-        s_delta[s * BW + row] = qi < n ? P.delta[(long long)bh * n + qi] : 0.f;
+      if (stats_tma) {
+        mbar_wait(q_full + 8 * s, (it >> 1) & 1);
+      } else {
+        if (chunk == 0 && row < BW) {   // per-query statistics of this tile -> smem
+          const int qi = qq0 + row;
+          s_lse[s * BW + row] = qi < n ? P.lse[(long long)bh * n + qi] : 0.f;
+          s_delta[s * BW + row] = qi < n ? P.delta[(long long)bh * n + qi] : 0.f;
+        }
+        named_bar_sync(1, BWD_THREADS - 64);
       }
-      named_bar_sync(1, 128);
       const bool full = (k1 - k0 == TK - 1) && (qq1 - qq0 == BW - 1) && km == nullptr && attn_tile_full(g, qq0, qq1, k0, k1);
-      Mask128 mk = {{0xffffffffu, 0xffffffffu, 0u, 0u}};
+      uint32_t mb = 0xffffffffu;
       if (!full) {
-        if (key_ok) mk = attn_col_bits(g, kj, qq0, n, BW);
-        else mk.w[0] = mk.w[1] = 0u;
+        if (key_ok) { const Mask128 mk = attn_col_bits(g, kj, qq0, n, BW); mb = chunk == 0 ? mk.w[0] : mk.w[1]; }
+        else mb = 0u;
       }
-      mbar_wait(st_full, it & 1);
+      ATTN_DBG(threadIdx.x == 64 ? 4 : 8);                   // softmax: masks ready, waiting for S^T / dP^T
+      mbar_wait_mode(st_full, it & 1, P.wait_mode & 1);
       tc_fence_after();
+      ATTN_DBG(threadIdx.x == 64 ? 5 : 9);                   // softmax: S^T / dP^T complete
       // (the MMAs of this tile were issued after the previous tile's dV/dK MMAs, which read P^T / dS^T from the columns
       //  written below: the tensor pipe executes in order, so st_full also means those reads are complete)
 #pragma unroll 1
-      for (int c = 0; c < BW / 32; ++c) {
-        const uint32_t mb = c == 0 ? mk.w[0] : mk.w[1];
-        uint32_t pk[16], dk_[16];
-        if (__all_sync(0xffffffffu, mb == 0u)) {
+      for (int sub = 0; sub < 2; ++sub) {
+        const uint32_t mb16 = (mb >> (16 * sub)) & 0xffffu;
+        const int col = chunk * 32 + sub * 16;
+        uint32_t pk[8], dk_[8];
+        if (__all_sync(0xffffffffu, mb16 == 0u)) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { pk[i] = 0u; dk_[i] = 0u; }
+          for (int i = 0; i < 8; ++i) { pk[i] = 0u; dk_[i] = 0u; }
         } else {
-          uint32_t rs[32], rd[32];
-          tmem_ld32(tSt + lane_off + c * 32, rs);
-          tmem_ld32(tdPt + lane_off + c * 32, rd);
-          tmem_ld_wait();
-          const float* ls = s_lse + s * BW + c * 32;
-          const float* dl = s_delta + s * BW + c * 32;
-          if (mb == 0xffffffffu) {
+          uint32_t rs[16], rd[16];
+          tmem_ld16(tSt + lane_off + col, rs);
+          if (!(P.wait_mode & 16)) tmem_ld16(tdPt + lane_off + col, rd);
+          else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float p0 = ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -ls[2 * i]));
-              const float p1 = ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -ls[2 * i + 1]));
-              pk[i] = pack2(p0, p1);
-              dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - dl[2 * i]), p1 * (__uint_as_float(rd[2 * i + 1]) - dl[2 * i + 1]));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float p0 = sel_bit(mb, 2 * i, ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -ls[2 * i])), 0.f);
-              const float p1 = sel_bit(mb, 2 * i + 1, ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -ls[2 * i + 1])), 0.f);
-              pk[i] = pack2(p0, p1);
-              dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - dl[2 * i]), p1 * (__uint_as_float(rd[2 * i + 1]) - dl[2 * i + 1]));
-            }
+            for (int i = 0; i < 16; ++i) rd[i] = rs[i];
           }
+          tmem_ld_wait();
+          bwd_softmax16<true, true>(rs, rd, mb16, s_lse + s * BW + col, s_delta + s * BW + col, 0.f, 0.f, pk, dk_);
         }
-        tmem_st16(tPt + lane_off + c * 16, pk);
-        tmem_st16(tdSt + lane_off + c * 16, dk_);
+        tmem_st8(tPt + lane_off + chunk * 32 + sub * 8, pk);
+        tmem_st8(tdSt + lane_off + chunk * 32 + sub * 8, dk_);
       }
+      ATTN_DBG(threadIdx.x == 64 ? 6 : 10);                  // softmax: both 16-column passes computed, stores issued
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(ps_ready);
+      ATTN_DBG(threadIdx.x == 64 ? 7 : 11);                  // softmax: arrived
       ++it;
     }
+    // warps 2-5 write dK, warps 6-9 write dV
+    const uint32_t tacc = chunk == 0 ? tdK : tdV;
+    const int sel = chunk == 0 ? 1 : 2;
     if (it > 0) {
       mbar_wait(acc_done, (it - 1) & 1);
       tc_fence_after();
       bf16* rowp = P.dqkv + ((long long)b * n + (kj < n ? kj : 0)) * (3 * inner) + h * DH;
       const float* cr = P.cos_t ? P.cos_t + (long long)(kj < n ? kj : 0) * (DH / 2) : nullptr;
       const float* sr = P.sin_t ? P.sin_t + (long long)(kj < n ? kj : 0) * (DH / 2) : nullptr;
-      store_grad_row(tdK + lane_off, rowp + inner, cr, sr, 1.0f, kj < n);
-      store_grad_row(tdV + lane_off, rowp + 2 * inner, cr, sr, 1.0f, kj < n);
+      store_grad_row(tacc + lane_off, rowp + sel * inner, cr, sr, 1.0f, kj < n);
     } else if (kj < n) {
       bf16* rowp = P.dqkv + ((long long)b * n + kj) * (3 * inner) + h * DH;
-      for (int d = 0; d < DH; d += 8) {
-        *reinterpret_cast<uint4*>(rowp + inner + d) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(rowp + 2 * inner + d) = make_uint4(0, 0, 0, 0);
-      }
+      for (int d = 0; d < DH; d += 8) *reinterpret_cast<uint4*>(rowp + sel * inner + d) = make_uint4(0, 0, 0, 0);
     }
   }
   tc_fence_before();
@@ -549,7 +614,7 @@ __global__ void __launch_bounds__(192, 2) attn_bwd_dkv_tc_kernel(const __grid_co
 
 // ---------------------------------------------------------------------------------------------------------------
 // dQ : CTA = 128 queries, thread = query row, 64-key tiles.
-//   TMEM: S [0,64) | dP [64,128) (dS bf16 aliased on [64,96)) | dQ [128,192)
+//   TMEM: S [0,64) | dP [64,128) (dS bf16 aliased on [64,80)+[96,112)) | dQ [128,192)
 // ---------------------------------------------------------------------------------------------------------------
 struct DqSmem {
   static constexpr int Q_OFF = 0, DO_OFF = TILE_BYTES, K_OFF = 2 * TILE_BYTES, V_OFF = 2 * TILE_BYTES + 2 * HALF_TILE;
@@ -557,7 +622,7 @@ struct DqSmem {
   static constexpr int TOTAL = BAR_OFF + 128 + 1024;
 };
 
-__global__ void __launch_bounds__(192, 2) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+__global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                                                               BwdArgs P, AttnGeom g) {
   using L = DqSmem;
@@ -573,7 +638,7 @@ __global__ void __launch_bounds__(192, 2) attn_bwd_dq_tc_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / P.heads, h = bh - b * P.heads;
   const int n = g.n_k, inner = P.heads * DH;
-  const int q0 = blockIdx.x * TQ, q1 = min(q0 + TQ, n) - 1;
+  const int q0 = (gridDim.x - 1 - blockIdx.x) * TQ, q1 = min(q0 + TQ, n) - 1;   // heaviest (causal) tiles first
   const int nkt = (n + BW - 1) / BW;
   auto needed = [&](int kt) { return attn_tile_needed(g, q0, q1, kt * BW, min(kt * BW + BW, n) - 1); };
 
@@ -581,7 +646,7 @@ __global__ void __launch_bounds__(192, 2) attn_bwd_dq_tc_kernel(const __grid_con
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
-    mbar_init(s_full, 1); mbar_init(ds_ready, 128); mbar_init(acc_done, 1);
+    mbar_init(s_full, 1); mbar_init(ds_ready, BWD_THREADS - 64); mbar_init(acc_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -609,7 +674,7 @@ __global__ void __launch_bounds__(192, 2) attn_bwd_dq_tc_kernel(const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp converged; an elected lane issues (see elect_one())
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, BW, false, false);
       constexpr uint32_t IDESC_G = make_idesc_bf16(128, 64, false, true);
       mbar_wait(q_full, 0);
@@ -621,24 +686,29 @@ __global__ void __launch_bounds__(192, 2) attn_bwd_dq_tc_kernel(const __grid_con
         mbar_wait(kv_full + 8 * s, (it >> 1) & 1);
         tc_fence_after();
         const uint64_t dk = make_smem_desc(sK + s * HALF_TILE, 16, 1024), dv = make_smem_desc(sV + s * HALF_TILE, 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
+          for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16(tdP, ddo + 2 * k, dv + 2 * k, IDESC_S, k != 0);
-        umma_commit(s_full);
-        mbar_wait(ds_ready, it & 1);
+          for (int k = 0; k < DH / 16; ++k) umma_bf16(tdP, ddo + 2 * k, dv + 2 * k, IDESC_S, k != 0);
+          umma_commit(s_full);
+        }
+        __syncwarp();
+        mbar_wait_mode(ds_ready, it & 1, (P.wait_mode >> 1) & 1);
         tc_fence_after();
         const uint64_t bk = make_smem_desc(sK + s * HALF_TILE, HALF_TILE, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BW / 16; ++k) umma_bf16_ts(tdQ, tdS + 8 * k, bk + 128 * k, IDESC_G, (it | k) != 0);
-        umma_commit(kv_empty + 8 * s);
-        umma_commit(acc_done);
+          for (int k = 0; k < BW / 16; ++k) umma_bf16_ts(tdQ, tdS + packed_kcol(k), bk + 128 * k, IDESC_G, (it | k) != 0);
+          umma_commit(kv_empty + 8 * s);
+          umma_commit(acc_done);
+        }
+        __syncwarp();
         ++it;
       }
     }
-    __syncwarp();
   } else {
-    const int quarter = warp & 3;
+    const int quarter = warp & 3, chunk = (warp - 2) >> 2;    // TMEM lane quarter; column half [32*chunk, 32*chunk+32)
     const int row = quarter * 32 + lane;
     const int qi = q0 + row;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
@@ -650,42 +720,29 @@ __global__ void __launch_bounds__(192, 2) attn_bwd_dq_tc_kernel(const __grid_con
       if (!needed(kt)) continue;
       const int k0 = kt * BW, k1 = min(k0 + BW, n) - 1;
       const bool full = (k1 - k0 == BW - 1) && km == nullptr && attn_tile_full(g, q0, q1, k0, k1);
-      Mask128 mk = {{0xffffffffu, 0xffffffffu, 0u, 0u}};
+      uint32_t mb = 0xffffffffu;
       if (!full) {
-        if (qi < n) mk = attn_row_bits(g, qi, k0, km, BW);
-        else mk.w[0] = mk.w[1] = 0u;
+        if (qi < n) { const Mask128 mk = attn_row_bits(g, qi, k0, km, BW); mb = chunk == 0 ? mk.w[0] : mk.w[1]; }
+        else mb = 0u;
       }
-      mbar_wait(s_full, it & 1);
+      mbar_wait_mode(s_full, it & 1, P.wait_mode & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BW / 32; ++c) {
-        const uint32_t mb = c == 0 ? mk.w[0] : mk.w[1];
-        uint32_t dk_[16];
-        if (__all_sync(0xffffffffu, mb == 0u)) {
+      for (int sub = 0; sub < 2; ++sub) {
+        const uint32_t mb16 = (mb >> (16 * sub)) & 0xffffu;
+        const int col = chunk * 32 + sub * 16;
+        uint32_t dk_[8];
+        if (__all_sync(0xffffffffu, mb16 == 0u)) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dk_[i] = 0u;
+          for (int i = 0; i < 8; ++i) dk_[i] = 0u;
         } else {
-          uint32_t rs[32], rd[32];
-          tmem_ld32(tS + lane_off + c * 32, rs);
-          tmem_ld32(tdP + lane_off + c * 32, rd);
+          uint32_t rs[16], rd[16];
+          tmem_ld16(tS + lane_off + col, rs);
+          tmem_ld16(tdP + lane_off + col, rd);
           tmem_ld_wait();
-          if (mb == 0xffffffffu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float p0 = ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -lse_r));
-              const float p1 = ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -lse_r));
-              dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - delta_r), p1 * (__uint_as_float(rd[2 * i + 1]) - delta_r));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float p0 = sel_bit(mb, 2 * i, ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -lse_r)), 0.f);
-              const float p1 = sel_bit(mb, 2 * i + 1, ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -lse_r)), 0.f);
-              dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - delta_r), p1 * (__uint_as_float(rd[2 * i + 1]) - delta_r));
-            }
-          }
+          bwd_softmax16<false, false>(rs, rd, mb16, nullptr, nullptr, lse_r, delta_r, nullptr, dk_);
         }
-        tmem_st16(tdS + lane_off + c * 16, dk_);
+        tmem_st8(tdS + lane_off + chunk * 32 + sub * 8, dk_);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -699,10 +756,10 @@ __global__ void __launch_bounds__(192, 2) attn_bwd_dq_tc_kernel(const __grid_con
       bf16* rowp = P.dqkv + ((long long)b * n + qs) * (3 * inner) + h * DH;
       const float* cr = P.cos_t ? P.cos_t + (long long)qs * (DH / 2) : nullptr;
       const float* sr = P.sin_t ? P.sin_t + (long long)qs * (DH / 2) : nullptr;
-      store_grad_row(tdQ + lane_off, rowp, cr, sr, P.q_scale, qi < n);    // q = rot(x) * scale (attention.py:69)
+      store_grad_cols(tdQ + lane_off, rowp, cr, sr, P.q_scale, qi < n, chunk);    // q = rot(x) * scale (attention.py:69)
     } else if (qi < n) {
-      bf16* rowp = P.dqkv + ((long long)b * n + qi) * (3 * inner) + h * DH;
-      for (int d = 0; d < DH; d += 8) *reinterpret_cast<uint4*>(rowp + d) = make_uint4(0, 0, 0, 0);
+      bf16* rowp = P.dqkv + ((long long)b * n + qi) * (3 * inner) + h * DH + chunk * 32;
+      for (int d = 0; d < 32; d += 8) *reinterpret_cast<uint4*>(rowp + d) = make_uint4(0, 0, 0, 0);
     }
   }
   tc_fence_before();
@@ -744,6 +801,11 @@ int launch_fwd(const db200_attn_fwd_params& p, cudaStream_t st) {
 
 }  // namespace
 
+int attn_debug_timeline(long long* out, int count) {
+  if (count > 256) count = 256;
+  return cudaMemcpyFromSymbol(out, g_attn_dbg, sizeof(long long) * count) == cudaSuccess ? 0 : -1;
+}
+
 bool attn_tc_supported(const db200_attn_fwd_params& p) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return false;
@@ -782,12 +844,13 @@ int attn_bwd_tc_launch(const db200_attn_bwd_params& p, cudaStream_t st) {
   attn_delta_tc_kernel<<<ceil_div(total_rows * 32, 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(f.out),
                                                                        reinterpret_cast<const bf16*>(p.d_out), p.delta, f.batch, f.heads, n);
   DB200_LAUNCH_OK("attn_delta_tc_kernel");
-  BwdArgs A{f.lse, p.delta, f.key_mask, p.cos_t, p.sin_t, p.q_scale, reinterpret_cast<bf16*>(p.dqkv), f.heads, f.batch};
+  static const int wait_mode = [] { const char* v = getenv("DALLE_B200_ATTN_WAIT"); return v ? atoi(v) : 0; }();
+  BwdArgs A{f.lse, p.delta, f.key_mask, p.cos_t, p.sin_t, p.q_scale, reinterpret_cast<bf16*>(p.dqkv), f.heads, f.batch, wait_mode};
   const AttnGeom g = make_geom(f);
   dim3 grid(ceil_div(n, TQ), f.batch * f.heads);
-  attn_bwd_dkv_tc_kernel<<<grid, 192, DkvSmem::TOTAL, st>>>(tmQ64, tmK128, tmV128, tmdO64, A, g);
+  attn_bwd_dkv_tc_kernel<<<grid, BWD_THREADS, DkvSmem::TOTAL, st>>>(tmQ64, tmK128, tmV128, tmdO64, A, g);
   DB200_LAUNCH_OK("attn_bwd_dkv_tc_kernel");
-  attn_bwd_dq_tc_kernel<<<grid, 192, DqSmem::TOTAL, st>>>(tmQ128, tmK64, tmV64, tmdO128, A, g);
+  attn_bwd_dq_tc_kernel<<<grid, BWD_THREADS, DqSmem::TOTAL, st>>>(tmQ128, tmK64, tmV64, tmdO128, A, g);
   DB200_LAUNCH_OK("attn_bwd_dq_tc_kernel");
   return DB200_OK;
 }

@@ -394,14 +394,14 @@ __global__ void __launch_bounds__(256) ln_shift_bwd_param_kernel(db200_ln_shift_
   atomicAdd(P.dbeta + c, ab.x); atomicAdd(P.dbeta + c + 1, ab.y); atomicAdd(P.dbeta + c + 2, ab.z); atomicAdd(P.dbeta + c + 3, ab.w);
 }
 
-// scale_bwd, slab streaming: thread = 4 channels, block = 1024 channels x SLAB_ROWS rows; LayerScale value and the partial
+// scale_bwd, slab streaming: thread = 4 channels, block = 1024 channels x rows_per_block rows; LayerScale value and the partial
 // sums live in 12 registers, so occupancy is high and four rows of loads are in flight per thread.
 template <typename T>
-__global__ void __launch_bounds__(256) scale_bwd_slab_kernel(db200_scale_bwd_params P) {
+__global__ void __launch_bounds__(256, 2) scale_bwd_slab_kernel(db200_scale_bwd_params P, int rows_per_block) {
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
   const int d = P.d;
   if (c >= d) return;
-  const int r0 = blockIdx.y * SLAB_ROWS, r1 = min(P.rows, r0 + SLAB_ROWS);
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(P.rows, r0 + rows_per_block);
   float4 sc = make_float4(P.sign, P.sign, P.sign, P.sign);
   if (P.scale) { const float4 t = __ldg(reinterpret_cast<const float4*>(P.scale + c)); sc.x *= t.x; sc.y *= t.y; sc.z *= t.z; sc.w *= t.w; }
   const T* __restrict__ y = reinterpret_cast<const T*>(P.y);
@@ -471,14 +471,14 @@ __global__ void __launch_bounds__(256) scale_bwd_kernel(db200_scale_bwd_params P
 }
 
 // GEGLU adjoint as one streaming pass (transformer.py:106-109 autograd): du = [dh*gelu(g) | dh*a*gelu'(g)], plus the column
-// sums of du (= gradient of net.0.bias) accumulated on the fly.  Thread = 8 hidden columns, block = 2048 columns x GB_ROWS rows.
-constexpr int GB_ROWS = 64;
+// sums of du (= gradient of net.0.bias) accumulated on the fly.  Thread = 8 hidden columns, block = 2048 columns x rows_per_block rows
+// (host-chosen so that the grid is whole waves of resident CTAs, see balanced_rows_per_block).
 template <typename T>
 __global__ void __launch_bounds__(256, 4) geglu_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ u, T* __restrict__ du,
-                                                        float* __restrict__ dbias, int rows, int hidden) {
+                                                        float* __restrict__ dbias, int rows, int hidden, int rows_per_block) {
   const int j = (blockIdx.x * 256 + threadIdx.x) * 8;
   if (j >= hidden) return;
-  const int r0 = blockIdx.y * GB_ROWS, r1 = min(rows, r0 + GB_ROWS);
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
   float sa[8], sg[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { sa[i] = 0.f; sg[i] = 0.f; }
@@ -711,13 +711,27 @@ int ln_shift_bwd_launch(const db200_ln_shift_bwd_params& P, cudaStream_t st) {
   return DB200_OK;
 }
 
+// Rows per CTA for the slab-streaming kernels: the grid must be whole waves of resident CTAs (148 SMs x `resident`), otherwise
+// the last partial wave runs at a fraction of the HBM bandwidth (measured: 640 CTAs on 592 slots = 2 waves for 1.08 waves of
+// work).  One wave, chunk rounded up to `quantum` rows.
+static int balanced_rows_per_block(int rows, int col_blocks, int resident, int quantum) {
+  const int slots = sm_count() * resident / (col_blocks > 0 ? col_blocks : 1);
+  if (slots <= 0) return rows;
+  int rpb = ceil_div(rows, slots);          // one wave; small inputs keep at least 32 rows per CTA (fewer CTAs than slots)
+  if (rpb < 32) rpb = 32;
+  rpb = ceil_div(rpb, quantum) * quantum;
+  return rpb;
+}
+
 int scale_bwd_launch(const db200_scale_bwd_params& P, cudaStream_t st) {
   if (P.rows == 0) return DB200_OK;
   const size_t smem = (size_t)2 * P.d * sizeof(float);
   if ((P.d & 3) == 0) {
-    dim3 sgrid(ceil_div(P.d, 1024), ceil_div(P.rows, SLAB_ROWS));
-    if (P.dtype == DB200_F32) scale_bwd_slab_kernel<float><<<sgrid, 256, 0, st>>>(P);
-    else scale_bwd_slab_kernel<__nv_bfloat16><<<sgrid, 256, 0, st>>>(P);
+    const int cb = ceil_div(P.d, 1024);
+    const int rpb = balanced_rows_per_block(P.rows, cb, 2, 8);
+    dim3 sgrid(cb, ceil_div(P.rows, rpb));
+    if (P.dtype == DB200_F32) scale_bwd_slab_kernel<float><<<sgrid, 256, 0, st>>>(P, rpb);
+    else scale_bwd_slab_kernel<__nv_bfloat16><<<sgrid, 256, 0, st>>>(P, rpb);
     DB200_LAUNCH_OK("scale_bwd_slab_kernel");
     return DB200_OK;
   }
@@ -730,13 +744,15 @@ int scale_bwd_launch(const db200_scale_bwd_params& P, cudaStream_t st) {
 
 int geglu_bwd_launch(const void* dh, const void* u, void* du, float* dbias, int dtype, int rows, int hidden, cudaStream_t st) {
   if (rows == 0) return DB200_OK;
-  dim3 grid(ceil_div(hidden, 2048), ceil_div(rows, GB_ROWS));
+  const int cb = ceil_div(hidden, 2048);
+  const int rpb = balanced_rows_per_block(rows, cb, 4, 4);
+  dim3 grid(cb, ceil_div(rows, rpb));
   if (dtype == DB200_F32)
     geglu_bwd_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(dh), reinterpret_cast<const float*>(u),
-                                                  reinterpret_cast<float*>(du), dbias, rows, hidden);
+                                                  reinterpret_cast<float*>(du), dbias, rows, hidden, rpb);
   else
     geglu_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dh), reinterpret_cast<const __nv_bfloat16*>(u),
-                                                          reinterpret_cast<__nv_bfloat16*>(du), dbias, rows, hidden);
+                                                          reinterpret_cast<__nv_bfloat16*>(du), dbias, rows, hidden, rpb);
   DB200_LAUNCH_OK("geglu_bwd_kernel");
   return DB200_OK;
 }

@@ -190,7 +190,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // Whole warp converged, one elected lane issues each k-block (see elect_one() in tc_common.cuh): descriptors stay in
+    // uniform registers instead of paying an R2UR + ELECT waterfall per tcgen05.mma.
+    {
       // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major bit15, b_major bit16,
       // N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u) |
@@ -206,7 +208,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       while (true) {
         mbar_wait(sfull_bar + 8 * ss, sph);
         const int tile = sched_tile[ss];
-        mbar_arrive(sempty_bar + 8 * ss);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sempty_bar + 8 * ss);
         if (++ss == SCHED_DEPTH) { ss = 0; sph ^= 1; }
         if (tile >= num_tiles) break;
         mbar_wait(tempty_bar + 8 * as, aph ^ 1);
@@ -219,17 +222,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES), A_LBO, 1024);
           const uint64_t db = make_smem_desc(smem_u32(smem_b + s * B_STAGE_BYTES), B_LBO, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_bf16(tmem_c, da + static_cast<uint64_t>(k * A_KSTEP), db + static_cast<uint64_t>(k * B_KSTEP), idesc, (kb > kb0) || (k != 0));
-          umma_commit(empty_bar + 8 * s);                    // smem stage free once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(tfull_bar + 8 * as);   // accumulator complete
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16(tmem_c, da + static_cast<uint64_t>(k * A_KSTEP), db + static_cast<uint64_t>(k * B_KSTEP), idesc, (kb > kb0) || (k != 0));
+            umma_commit(empty_bar + 8 * s);                    // smem stage free once these MMAs retire
+            if (kb == kb1 - 1) umma_commit(tfull_bar + 8 * as);   // accumulator complete
+          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
-    __syncwarp();
   } else {
     // ================================ epilogue (warps 2..9) ================================
     const int ew = warp - 2;

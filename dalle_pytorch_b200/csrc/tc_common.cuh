@@ -47,6 +47,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Latency-critical variant: plain try_wait (default, short hardware suspend) in a tight loop.  `mode` is an experiment switch:
+// 0 = parked wait (mbar_wait), 1 = spin.
+__device__ __forceinline__ void mbar_wait_mode(uint32_t bar, uint32_t parity, int mode) {
+  if (mode == 0) { mbar_wait(bar, parity); return; }
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
 // ---- TMA ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -116,6 +135,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// 1-D bulk copy global -> shared (bytes % 16 == 0, both addresses 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -128,6 +158,17 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// One lane of a fully converged warp.  The MMA-issuer warps keep all 32 lanes in the loop and elect the issuing lane per
+// block of tcgen05 instructions: operands computed in converged code are warp-uniform, so ptxas keeps the descriptors in
+// uniform registers.  Issuing from inside a long `if (lane == 0)` region instead makes every operand "divergent" and costs an
+// R2UR + ELECT waterfall loop per tcgen05.mma (~75 cycles per instruction, measured with the clock64 probe in attn_tc.cu) --
+// more than the 32 cycles a 128x64x16 MMA takes to execute.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 // D[tmem] (+)= A[tmem] * B[smem]   (A operand read from tensor memory: lane = row, packed bf16 pairs along columns)
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
