@@ -44,6 +44,36 @@ __device__ __forceinline__ float ex2(float x) {
 }
 __device__ __forceinline__ float sel_bit(uint32_t bits, int i, float a, float b) { return (bits >> i) & 1u ? a : b; }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2): one instruction per two elements on the fp32 pipe.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+
 struct FwdArgs {
   bf16* out; float* lse; const uint8_t* key_mask; int heads, batch;
 };
@@ -56,28 +86,29 @@ constexpr int FK_BYTES = FK * DH * 2;          // one [64 x 64] bf16 tile = 8 KB
 
 // P = exp2(S*log2e - m*log2e) for one 32-column chunk held in registers, packed to bf16x2; returns the chunk's row sum
 __device__ __forceinline__ float fwd_exp_pack(const uint32_t (&r)[32], uint32_t mb, bool skip, float mb2, uint32_t (&pk)[16]) {
-  float rs = 0.f;
+  float2 rs2 = make_float2(0.f, 0.f);
+  const float2 kLog2e = make_float2(LOG2E, LOG2E), nm = make_float2(-mb2, -mb2);
   if (skip) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) pk[i] = 0u;
   } else if (mb == 0xffffffffu) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), LOG2E, -mb2));
-      const float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, -mb2));
-      rs += p0 + p1;
-      pk[i] = pack2(p0, p1);
+      const float2 t = fma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), kLog2e, nm);
+      const float2 p = make_float2(ex2(t.x), ex2(t.y));
+      rs2 = add2(rs2, p);
+      pk[i] = pack2(p.x, p.y);
     }
   } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const float p0 = sel_bit(mb, 2 * i, ex2(fmaf(__uint_as_float(r[2 * i]), LOG2E, -mb2)), 0.f);
-      const float p1 = sel_bit(mb, 2 * i + 1, ex2(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, -mb2)), 0.f);
-      rs += p0 + p1;
-      pk[i] = pack2(p0, p1);
+      const float2 t = fma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), kLog2e, nm);
+      const float2 p = make_float2(sel_bit(mb, 2 * i, ex2(t.x), 0.f), sel_bit(mb, 2 * i + 1, ex2(t.y), 0.f));
+      rs2 = add2(rs2, p);
+      pk[i] = pack2(p.x, p.y);
     }
   }
-  return rs;
+  return rs2.x + rs2.y;
 }
 template <bool P_TMEM>
 __device__ __forceinline__ void fwd_store_p(const uint32_t (&pk)[16], int c, uint32_t tP_lane, uint8_t* sP, int row) {
@@ -311,17 +342,49 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
 }
 
 // =============================================== backward ====================================================
-__global__ void attn_delta_tc_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ delta, int batch, int heads,
-                                     int n) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int total = batch * heads * n;
-  if (warp >= total) return;
-  const int i = warp % n, bh = warp / n, h = bh % heads, b = bh / heads;
-  const long long off = ((long long)b * n + i) * heads * DH + h * DH + lane * 2;
-  const float2 o = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(O + off));
-  const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dO + off));
-  const float s = warp_sum(o.x * d.x + o.y * d.y);
-  if (lane == 0) delta[(long long)bh * n + i] = s;
+// delta[b,h,i] = sum_d O[b,i,h,d] * dO[b,i,h,d].  Rows of 64 bf16 (128 B) are contiguous in (b,i,h) order: 8 lanes per row,
+// one 16-byte load of O and dO per lane, 4 rows per warp per step, 4 steps in flight.
+__global__ void __launch_bounds__(256) attn_delta_tc_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ delta,
+                                                            int batch, int heads, int n) {
+  const long long total = (long long)batch * heads * n;
+  const int part = threadIdx.x & 7;
+  const long long stride = (long long)gridDim.x * 32 * 4;            // rows per grid step (32 rows per 256-thread block, x4 unroll)
+  // (loop bound is warp-uniform so that the full-mask shuffles below are always executed by all 32 lanes)
+  for (long long wb = (long long)blockIdx.x * 32 + (threadIdx.x >> 5) * 4; wb < total; wb += stride) {
+    const long long base = wb + ((threadIdx.x & 31) >> 3);
+    uint4 o[4], d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r = base + (long long)u * gridDim.x * 32;
+      o[u] = make_uint4(0, 0, 0, 0); d[u] = make_uint4(0, 0, 0, 0);
+      if (r < total) {
+        o[u] = *reinterpret_cast<const uint4*>(O + r * DH + part * 8);
+        d[u] = *reinterpret_cast<const uint4*>(dO + r * DH + part * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long r = base + (long long)u * gridDim.x * 32;
+      const __nv_bfloat162* po = reinterpret_cast<const __nv_bfloat162*>(&o[u]);
+      const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&d[u]);
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = __bfloat1622float2(po[k]), b2 = __bfloat1622float2(pd[k]);
+        acc = fmaf(a.x, b2.x, fmaf(a.y, b2.y, acc));
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (part == 0 && r < total) {
+        const long long bi = r / heads;                              // r = (b*n + i)*heads + h
+        const int h = static_cast<int>(r - bi * heads);
+        const long long b = bi / n;
+        const int i = static_cast<int>(bi - b * n);
+        delta[(b * heads + h) * n + i] = acc;
+      }
+    }
+  }
 }
 
 // Timeline probe (debug only, DALLE_B200_ATTN_WAIT bit 2): CTA (1,0) of the dK/dV kernel records clock64() at the hand-off
@@ -367,38 +430,36 @@ __device__ __forceinline__ void store_grad_row(uint32_t taddr, bf16* dst, const 
 }
 
 // softmax-backward of 16 columns of one row: p = exp(s - lse), ds = p * (dp - delta); packs 8 bf16 pairs each.
-// kLseCol: lse/delta vary along the columns (dK/dV kernel, read from smem) instead of being per-row constants (dQ kernel).
+// kLseCol: lse/delta vary along the columns (dK/dV kernel, read from smem at ls_addr / dl_addr) instead of being per-row
+// constants (dQ kernel; lse_r already carries the log2(e) factor).  Four packed fp32 instructions + two MUFU + two
+// conversions per element pair.
 template <bool kLseCol, bool kWantP>
-__device__ __forceinline__ void bwd_softmax16(const uint32_t* rs, const uint32_t* rd, uint32_t mb16, const float* ls, const float* dl,
+__device__ __forceinline__ void bwd_softmax16(const uint32_t* rs, const uint32_t* rd, uint32_t mb16, uint32_t ls_addr, uint32_t dl_addr,
                                               float lse_r, float delta_r, uint32_t* pk, uint32_t* dk_) {
-  float l2[16], dd[16];
-  if constexpr (kLseCol) {
+  const float2 kLog2e = make_float2(LOG2E, LOG2E), kNegLog2e = make_float2(-LOG2E, -LOG2E), kNegOne = make_float2(-1.f, -1.f);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 a = reinterpret_cast<const float4*>(ls)[j], b = reinterpret_cast<const float4*>(dl)[j];
-      l2[4 * j] = a.x * LOG2E; l2[4 * j + 1] = a.y * LOG2E; l2[4 * j + 2] = a.z * LOG2E; l2[4 * j + 3] = a.w * LOG2E;
-      dd[4 * j] = b.x; dd[4 * j + 1] = b.y; dd[4 * j + 2] = b.z; dd[4 * j + 3] = b.w;
+  for (int j = 0; j < 4; ++j) {                    // 4 columns per step
+    float2 nl0, nl1, d0, d1;                       // -lse*log2e and delta of columns (4j, 4j+1), (4j+2, 4j+3)
+    if constexpr (kLseCol) {
+      const float4 a = lds128(ls_addr + 16 * j), b = lds128(dl_addr + 16 * j);
+      nl0 = mul2(make_float2(a.x, a.y), kNegLog2e); nl1 = mul2(make_float2(a.z, a.w), kNegLog2e);
+      d0 = make_float2(b.x, b.y); d1 = make_float2(b.z, b.w);
+    } else {
+      nl0 = nl1 = make_float2(-lse_r, -lse_r);
+      d0 = d1 = make_float2(delta_r, delta_r);
     }
-  }
-  if (mb16 == 0xffffu) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float la = kLseCol ? l2[2 * i] : lse_r, lb = kLseCol ? l2[2 * i + 1] : lse_r;
-      const float da = kLseCol ? dd[2 * i] : delta_r, db = kLseCol ? dd[2 * i + 1] : delta_r;
-      const float p0 = ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -la));
-      const float p1 = ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -lb));
-      if constexpr (kWantP) pk[i] = pack2(p0, p1);
-      dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - da), p1 * (__uint_as_float(rd[2 * i + 1]) - db));
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float la = kLseCol ? l2[2 * i] : lse_r, lb = kLseCol ? l2[2 * i + 1] : lse_r;
-      const float da = kLseCol ? dd[2 * i] : delta_r, db = kLseCol ? dd[2 * i + 1] : delta_r;
-      const float p0 = sel_bit(mb16, 2 * i, ex2(fmaf(__uint_as_float(rs[2 * i]), LOG2E, -la)), 0.f);
-      const float p1 = sel_bit(mb16, 2 * i + 1, ex2(fmaf(__uint_as_float(rs[2 * i + 1]), LOG2E, -lb)), 0.f);
-      if constexpr (kWantP) pk[i] = pack2(p0, p1);
-      dk_[i] = pack2(p0 * (__uint_as_float(rd[2 * i]) - da), p1 * (__uint_as_float(rd[2 * i + 1]) - db));
+    for (int h = 0; h < 2; ++h) {
+      const int i = 2 * j + h;                     // pair index: columns 2i, 2i+1
+      const float2 sv = make_float2(__uint_as_float(rs[2 * i]), __uint_as_float(rs[2 * i + 1]));
+      const float2 dv = make_float2(__uint_as_float(rd[2 * i]), __uint_as_float(rd[2 * i + 1]));
+      const float2 t = fma2(sv, kLog2e, h == 0 ? nl0 : nl1);
+      float2 p = make_float2(ex2(t.x), ex2(t.y));
+      if (mb16 != 0xffffu) { p.x = sel_bit(mb16, 2 * i, p.x, 0.f); p.y = sel_bit(mb16, 2 * i + 1, p.y, 0.f); }
+      const float2 e = fma2(h == 0 ? d0 : d1, kNegOne, dv);      // dp - delta
+      const float2 ds = mul2(p, e);
+      if constexpr (kWantP) pk[i] = pack2(p.x, p.y);
+      dk_[i] = pack2(ds.x, ds.y);
     }
   }
 }
@@ -571,13 +632,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
         } else {
           uint32_t rs[16], rd[16];
           tmem_ld16(tSt + lane_off + col, rs);
-          if (!(P.wait_mode & 16)) tmem_ld16(tdPt + lane_off + col, rd);
-          else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) rd[i] = rs[i];
-          }
+          tmem_ld16(tdPt + lane_off + col, rd);
           tmem_ld_wait();
-          bwd_softmax16<true, true>(rs, rd, mb16, s_lse + s * BW + col, s_delta + s * BW + col, 0.f, 0.f, pk, dk_);
+          bwd_softmax16<true, true>(rs, rd, mb16, smem_u32(s_lse + s * BW + col), smem_u32(s_delta + s * BW + col), 0.f, 0.f, pk, dk_);
         }
         tmem_st8(tPt + lane_off + chunk * 32 + sub * 8, pk);
         tmem_st8(tdSt + lane_off + chunk * 32 + sub * 8, dk_);
@@ -740,7 +797,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
           tmem_ld16(tS + lane_off + col, rs);
           tmem_ld16(tdP + lane_off + col, rd);
           tmem_ld_wait();
-          bwd_softmax16<false, false>(rs, rd, mb16, nullptr, nullptr, lse_r, delta_r, nullptr, dk_);
+          bwd_softmax16<false, false>(rs, rd, mb16, 0u, 0u, lse_r, delta_r, nullptr, dk_);
         }
         tmem_st8(tdS + lane_off + chunk * 32 + sub * 8, dk_);
       }
@@ -841,8 +898,13 @@ int attn_bwd_tc_launch(const db200_attn_bwd_params& p, cudaStream_t st) {
     attr_done = true;
   }
   const int total_rows = f.batch * f.heads * n;
-  attn_delta_tc_kernel<<<ceil_div(total_rows * 32, 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(f.out),
-                                                                       reinterpret_cast<const bf16*>(p.d_out), p.delta, f.batch, f.heads, n);
+  {
+    int blocks = ceil_div(total_rows, 32 * 4);
+    const int cap = sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    attn_delta_tc_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(f.out), reinterpret_cast<const bf16*>(p.d_out), p.delta, f.batch,
+                                                 f.heads, n);
+  }
   DB200_LAUNCH_OK("attn_delta_tc_kernel");
   static const int wait_mode = [] { const char* v = getenv("DALLE_B200_ATTN_WAIT"); return v ? atoi(v) : 0; }();
   BwdArgs A{f.lse, p.delta, f.key_mask, p.cos_t, p.sin_t, p.q_scale, reinterpret_cast<bf16*>(p.dqkv), f.heads, f.batch, wait_mode};
