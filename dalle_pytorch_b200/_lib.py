@@ -9,7 +9,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdalle_b200.so')
+LIB_PATH = os.environ.get('DALLE_B200_LIB') or os.path.join(_HERE, 'libdalle_b200.so')   # env override: A/B builds only
 CSRC = os.path.join(_HERE, 'csrc')
 
 c_int, c_float, c_void_p, c_int64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_int64

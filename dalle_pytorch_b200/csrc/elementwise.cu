@@ -2,6 +2,7 @@
 // residual backward, column sums, casts.  Each is one pass over its tensor with 16-byte accesses.
 #include "common.cuh"
 #include "epilogue.cuh"
+#include "tc_common.cuh"
 
 namespace db200 {
 
@@ -353,6 +354,190 @@ __global__ void __launch_bounds__(WR_WARPS * 32, 3) ln_shift_bwd_dx_kernel(db200
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// LayerNorm(+shift) backward for d = 1024, bulk-copy staged.  The register-only kernel above tops out near 3 TB/s: a thread can
+// hold ~160 bytes of loads in flight, so an SM never has much more than 100 KB outstanding, and HBM3e needs about twice that
+// (its 64 shared-memory float atomics per row and lane also compile to ATOMS.CAST.SPIN compare-and-swap loops).
+// Here one producer warp streams batches of R token rows (dA row assembled from up to three source rows of the token shift,
+// x row, residual-gradient row) into a STAGES-deep shared-memory ring with cp.async.bulk + mbarrier transaction counts, so
+// ~160 KB per SM are always in flight; eight consumer warps (warp w = channels [128w, 128w+128)) read their slice with
+// conflict-free 8/16-byte LDS, keep dgamma / dbeta partials in registers for the whole kernel (a thread's channels never
+// change) and exchange the two row statistics through 2*R*8 floats of shared memory and one named barrier per batch.
+// ---------------------------------------------------------------------------------------------------------------------
+using namespace tc;
+constexpr int LT_R = 4;            // rows per stage
+constexpr int LT_NW = 8;           // consumer warps per group (d = 1024)
+constexpr int LT_GROUPS = 1;       // consumer groups taking alternate batches (2 measured no faster: the ring, not the consumers, paces the kernel)
+constexpr int LT_THREADS = (LT_GROUPS * LT_NW + 1) * 32;
+constexpr int LT_D = LT_NW * 128;
+template <typename TI>
+struct LnTmaSmem {
+  static constexpr int G_ROW = LT_D * (int)sizeof(TI), X_ROW = LT_D * 4;
+  static constexpr int STAGE = LT_R * (G_ROW + 2 * X_ROW);                  // dA | x | dres
+  static constexpr int STAGES = (sizeof(TI) == 2) ? 4 : 3;                  // 160 KB (bf16) / 144 KB (fp32)
+  static constexpr int FLAG_OFF = STAGES * STAGE;                           // [STAGES][R][4] ints: q1 present, q2 present, row valid, pad
+  static constexpr int PART_OFF = FLAG_OFF + STAGES * LT_R * 16;            // [GROUPS][2][2R][8] floats
+  static constexpr int BAR_OFF = PART_OFF + LT_GROUPS * 2 * 2 * LT_R * LT_NW * 4;   // full[STAGES], empty[STAGES]
+  static constexpr int TOTAL = BAR_OFF + 2 * STAGES * 8 + 16;
+};
+
+template <typename TI>
+__global__ void __launch_bounds__(LT_THREADS, 1) ln_shift_bwd_tma_kernel(db200_ln_shift_bwd_params P) {
+  using L = LnTmaSmem<TI>;
+  constexpr int R = LT_R, d = LT_D, STAGES = L::STAGES;
+  extern __shared__ __align__(128) uint8_t smem[];
+  int* flags = reinterpret_cast<int*>(smem + L::FLAG_OFF);
+  const uint32_t full_bar = smem_u32(smem + L::BAR_OFF), empty_bar = full_bar + 8 * STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = P.n, rows = P.batch * n;
+  const bool ln = P.do_ln != 0;
+  const bool has_res = P.dres != nullptr;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, LT_NW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int step = gridDim.x * R;
+
+  if (warp == LT_GROUPS * LT_NW) {
+    // ======================================= producer =======================================
+    // One lane per (row, copy): lane = 5*i + j handles copy j of row i (j: 0 dA quarter 1, 1 dA quarter 2, 2 dA upper half,
+    // 3 x, 4 dres).  A single issuing thread needs ~2-3 k cycles of dependent integer work per batch (divisions of the shift
+    // geometry, 20 address computations) and was the bottleneck of the whole kernel; spread over 20 lanes it is ~10x shorter.
+    // The transaction bytes are summed across the warp and posted by lane 0 (copies that complete before the expect_tx only
+    // drive the tx-count negative for a moment; the phase cannot complete before lane 0's arrival).
+    const TI* __restrict__ dA = reinterpret_cast<const TI*>(P.d_out);
+    const int i = lane / 5, j = lane - i * 5;
+    const bool active = lane < 5 * R;
+    int s = 0; uint32_t ph = 0;
+    for (int r0 = blockIdx.x * R; r0 < rows; r0 += step) {
+      mbar_wait(empty_bar + 8 * s, ph ^ 1);
+      uint8_t* st = smem + s * L::STAGE;
+      const uint32_t fb = full_bar + 8 * s;
+      uint32_t bytes = 0;
+      const int r = r0 + i;
+      if (active && r < rows) {
+        const int b = r / n, p = r - b * n;
+        const long long brow = (long long)b * n;
+        const ShiftRow sr = make_shift_row(p, n, P.text_len, P.fmap, P.do_shift);
+        const uint32_t gdst = smem_u32(st + i * L::G_ROW);
+        if (j == 0) {
+          int* fl = flags + (s * R + i) * 4;
+          fl[0] = sr.dest_q1 >= 0; fl[1] = sr.dest_q2 >= 0; fl[2] = 1;
+          if (sr.dest_q1 >= 0) { bytes = L::G_ROW / 4; bulk_load_1d(gdst, dA + (brow + sr.dest_q1) * d, bytes, fb); }
+        } else if (j == 1) {
+          if (sr.dest_q2 >= 0) { bytes = L::G_ROW / 4; bulk_load_1d(gdst + L::G_ROW / 4, dA + (brow + sr.dest_q2) * d + d / 4, bytes, fb); }
+        } else if (j == 2) {
+          bytes = L::G_ROW / 2; bulk_load_1d(gdst + L::G_ROW / 2, dA + (brow + p) * d + d / 2, bytes, fb);
+        } else if (j == 3) {
+          if (ln) { bytes = L::X_ROW; bulk_load_1d(smem_u32(st + R * L::G_ROW + i * L::X_ROW), P.x + (long long)r * d, bytes, fb); }
+        } else {
+          if (has_res) { bytes = L::X_ROW; bulk_load_1d(smem_u32(st + R * (L::G_ROW + L::X_ROW) + i * L::X_ROW), P.dres + (long long)r * d, bytes, fb); }
+        }
+      } else if (active && j == 0) {
+        flags[(s * R + i) * 4 + 2] = 0;                      // row past the end
+      }
+      const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+      __syncwarp();                                          // flag stores of all lanes are ordered before lane 0's (release) arrive
+      if (lane == 0) mbar_expect_tx(fb, total);
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
+    return;
+  }
+
+  // ======================================= consumers =======================================
+  // Two groups of eight warps take alternate batches (the per-batch chain LDS -> shuffles -> barrier -> LDS -> STG is mostly
+  // latency, so one group cannot drain the ring at HBM speed); each group has its own named barrier and statistics buffers.
+  const int grp = warp / LT_NW, cw = warp - grp * LT_NW;
+  float (*part)[2 * R][LT_NW] = reinterpret_cast<float (*)[2 * R][LT_NW]>(smem + L::PART_OFF) + grp * 2;
+  const int c = cw * 128 + lane * 4;
+  const bool want_p = ln && P.dgamma != nullptr;
+  const float4 ga = ln ? __ldg(reinterpret_cast<const float4*>(P.gamma + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int qsel = c >= (d >> 1) ? 2 : (c < (d >> 2) ? 0 : 1);      // flag index of this warp's channels (2 = always present)
+  int buf = 0;
+  for (int k = grp; ; k += LT_GROUPS, buf ^= 1) {
+    const int r0 = (blockIdx.x + k * (int)gridDim.x) * R;
+    if (r0 >= rows) break;
+    const int s = k % STAGES;
+    const uint32_t ph = (k / STAGES) & 1;
+    float mean[R], rstd[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {            // tiny broadcast loads, issued before the wait
+      const int r = r0 + i;
+      mean[i] = 0.f; rstd[i] = 1.f;
+      if (ln && r < rows) { mean[i] = __ldg(P.mean + r); rstd[i] = __ldg(P.rstd + r); }
+    }
+    mbar_wait(full_bar + 8 * s, ph);
+    const uint8_t* st = smem + s * L::STAGE;
+    const int* fl = flags + (s * R) * 4;
+    float4 g[R], h[R], e[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      g[i] = make_float4(0.f, 0.f, 0.f, 0.f); h[i] = g[i]; e[i] = g[i];
+      const bool valid = fl[i * 4 + 2] != 0;
+      const bool present = valid && (qsel == 2 || fl[i * 4 + qsel] != 0);
+      if (present) {
+        const TI* gp = reinterpret_cast<const TI*>(st + i * L::G_ROW) + c;
+        const float2 a = load2<TI>(gp), bq = load2<TI>(gp + 2);
+        g[i] = make_float4(a.x, a.y, bq.x, bq.y);
+      }
+      if (valid && ln) h[i] = *reinterpret_cast<const float4*>(st + R * L::G_ROW + i * L::X_ROW + c * 4);
+      if (valid && has_res) e[i] = *reinterpret_cast<const float4*>(st + R * (L::G_ROW + L::X_ROW) + i * L::X_ROW + c * 4);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar + 8 * s);       // stage consumed into registers
+    if (ln) {
+      float s1[R], s2[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        h[i] = make_float4((h[i].x - mean[i]) * rstd[i], (h[i].y - mean[i]) * rstd[i], (h[i].z - mean[i]) * rstd[i], (h[i].w - mean[i]) * rstd[i]);
+        if (want_p) {
+          ag.x += g[i].x * h[i].x; ag.y += g[i].y * h[i].y; ag.z += g[i].z * h[i].z; ag.w += g[i].w * h[i].w;
+          ab.x += g[i].x; ab.y += g[i].y; ab.z += g[i].z; ab.w += g[i].w;
+        }
+        g[i].x *= ga.x; g[i].y *= ga.y; g[i].z *= ga.z; g[i].w *= ga.w;
+        s1[i] = (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        s2[i] = (g[i].x * h[i].x + g[i].y * h[i].y) + (g[i].z * h[i].z + g[i].w * h[i].w);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+          s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+        }
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) { part[buf][i][cw] = s1[i]; part[buf][R + i][cw] = s2[i]; }
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(LT_NW * 32) : "memory");
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&part[buf][i][0]), a1 = *reinterpret_cast<const float4*>(&part[buf][i][4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&part[buf][R + i][0]), b1 = *reinterpret_cast<const float4*>(&part[buf][R + i][4]);
+        const float m1 = (((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w))) * (1.0f / d);
+        const float m2 = (((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w))) * (1.0f / d);
+        g[i].x = rstd[i] * (g[i].x - m1 - h[i].x * m2);
+        g[i].y = rstd[i] * (g[i].y - m1 - h[i].y * m2);
+        g[i].z = rstd[i] * (g[i].z - m1 - h[i].z * m2);
+        g[i].w = rstd[i] * (g[i].w - m1 - h[i].w * m2);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int r = r0 + i;
+      if (r < rows)
+        *reinterpret_cast<float4*>(P.dx + (long long)r * d + c) = make_float4(g[i].x + e[i].x, g[i].y + e[i].y, g[i].z + e[i].z, g[i].w + e[i].w);
+    }
+  }
+  if (want_p) {
+    atomicAdd(P.dgamma + c, ag.x); atomicAdd(P.dgamma + c + 1, ag.y); atomicAdd(P.dgamma + c + 2, ag.z); atomicAdd(P.dgamma + c + 3, ag.w);
+    atomicAdd(P.dbeta + c, ab.x); atomicAdd(P.dbeta + c + 1, ab.y); atomicAdd(P.dbeta + c + 2, ab.z); atomicAdd(P.dbeta + c + 3, ab.w);
+  }
+}
+
 constexpr int SLAB_ROWS = 32;
 template <typename TI>
 __global__ void __launch_bounds__(256) ln_shift_bwd_param_kernel(db200_ln_shift_bwd_params P) {
@@ -687,6 +872,23 @@ int ln_shift_fwd_launch(const db200_ln_shift_fwd_params& P, cudaStream_t st) {
 int ln_shift_bwd_launch(const db200_ln_shift_bwd_params& P, cudaStream_t st) {
   const int rows = P.batch * P.n;
   if (rows == 0) return DB200_OK;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(P.d_out) | reinterpret_cast<uintptr_t>(P.x) | reinterpret_cast<uintptr_t>(P.dres)) & 15) == 0;
+  static const bool no_tma = [] { const char* v = getenv("DALLE_B200_LN_BWD"); return v && !strcmp(v, "regs"); }();
+  if (P.d == 1024 && al16 && !no_tma) {
+    const int want = ceil_div(rows, LT_R);
+    const int grid = want < sm_count() ? want : sm_count();
+    if (P.dout_dtype == DB200_F32) {
+      static bool attr = false;
+      if (!attr) { DB200_CUDA_OK(cudaFuncSetAttribute(ln_shift_bwd_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, LnTmaSmem<float>::TOTAL)); attr = true; }
+      ln_shift_bwd_tma_kernel<float><<<grid, LT_THREADS, LnTmaSmem<float>::TOTAL, st>>>(P);
+    } else {
+      static bool attr = false;
+      if (!attr) { DB200_CUDA_OK(cudaFuncSetAttribute(ln_shift_bwd_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LnTmaSmem<__nv_bfloat16>::TOTAL)); attr = true; }
+      ln_shift_bwd_tma_kernel<__nv_bfloat16><<<grid, LT_THREADS, LnTmaSmem<__nv_bfloat16>::TOTAL, st>>>(P);
+    }
+    DB200_LAUNCH_OK("ln_shift_bwd_tma_kernel");
+    return DB200_OK;
+  }
   if (P.d == 256 || P.d == 512 || P.d == 1024) {
     const int want = ceil_div(rows, WR_WARPS);
     const int wgrid = want < sm_count() * 3 ? want : sm_count() * 3;

@@ -87,7 +87,8 @@ def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t
     M = b * n
     d_out = d_out.contiguous().view(M, d)
     sc = None if scale is None else scale.detach().reshape(-1).contiguous()
-    dy, dscale, db_out = ops.scale_bwd(d_out, y, sc, sign, g.dtype)
+    pool = torch.zeros(4, d, device=x_in.device, dtype=torch.float32)     # one fill for dscale, db_out, dln_w, dln_b
+    dy, dscale, db_out = ops.scale_bwd(d_out, y, sc, sign, g.dtype, zeroed=(pool[0], pool[1]))
     d_o = ops.gemm_store(dy, wo, a_mn=False, b_mn=True)                                   # [M, inner]
     dw_out = ops.gemm_store(dy, o.view(M, -1), a_mn=True, b_mn=True, out_dtype=torch.float32, out=s_out)   # [d, inner]
     dqkv = ops.attn_bwd(g.attn_spec, q, k, v, o, lse, d_o.view(b, n, -1), cos_t, sin_t, g.q_scale, key_mask)
@@ -95,8 +96,7 @@ def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t
     dw_qkv = ops.gemm_store(dqkv, a1, a_mn=True, b_mn=True, out_dtype=torch.float32, out=s_qkv)      # [3*inner, d]
     dln_w = dln_b = None
     if g.do_ln:
-        dln_w = torch.zeros(d, device=x_in.device, dtype=torch.float32)
-        dln_b = torch.zeros(d, device=x_in.device, dtype=torch.float32)
+        dln_w, dln_b = pool[2], pool[3]
     dx = ops.ln_shift_bwd(da1, x_in, mean, rstd, ln_w, None if dres is None else dres.contiguous(), g.text_len, g.fmap,
                           do_ln=g.do_ln, do_shift=shift, dgamma=dln_w, dbeta=dln_b)
     if dscale is not None:
@@ -132,20 +132,21 @@ def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=No
     M = b * n
     d_out = d_out.contiguous().view(M, d)
     sc = None if scale is None else scale.detach().reshape(-1).contiguous()
-    dy, dscale, db2 = ops.scale_bwd(d_out, y, sc, sign, g.dtype)
+    H2 = u.shape[1]
+    pool = torch.zeros(4 * d + H2, device=x_in.device, dtype=torch.float32)   # one fill for dscale, db2, dln_w, dln_b, db1
+    dy, dscale, db2 = ops.scale_bwd(d_out, y, sc, sign, g.dtype, zeroed=(pool[:d], pool[d:2 * d]))
     if FUSE_GEGLU_BWD:
         du = ops.gemm_geglu_bwd(dy, w2c, u)                                               # [M, 2H]
         db1 = ops.colsum(du)
     else:   # measured faster on B200 (profiles/): plain dgrad GEMM + one streaming pass that also forms the bias gradient
         dh = ops.gemm_store(dy, w2c, a_mn=False, b_mn=True)                               # [M, H]
-        du, db1 = ops.geglu_bwd(dh, u)
+        du, db1 = ops.geglu_bwd(dh, u, zeroed=pool[4 * d:])
     dw2 = ops.gemm_store(dy, h, a_mn=True, b_mn=True, out_dtype=torch.float32, out=s_w2)            # [d, H]
     da2 = ops.gemm_store(du, w1c, a_mn=False, b_mn=True)                                  # [M, d]
     dw1 = ops.gemm_store(du, a2, a_mn=True, b_mn=True, out_dtype=torch.float32, out=s_w1)           # [2H, d]
     dln_w = dln_b = None
     if g.do_ln:
-        dln_w = torch.zeros(d, device=x_in.device, dtype=torch.float32)
-        dln_b = torch.zeros(d, device=x_in.device, dtype=torch.float32)
+        dln_w, dln_b = pool[2 * d:3 * d], pool[3 * d:4 * d]
     dx = ops.ln_shift_bwd(da2, x_in, mean, rstd, ln_w, None if dres is None else dres.contiguous(), g.text_len, g.fmap,
                           do_ln=g.do_ln, do_shift=shift, dgamma=dln_w, dbeta=dln_b)
     if dscale is not None:

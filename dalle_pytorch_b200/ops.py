@@ -275,12 +275,18 @@ def attn_bwd(spec, q, k, v, out, lse, d_out, cos_t, sin_t, q_scale, key_mask=Non
 
 
 # ------------------------------------------------------------------------------------------------
-def scale_bwd(d_out, y, scale, sign, dtype, want_dscale=True, want_dbias=True):
-    """d_out [M,d] fp32 -> dy [M,d] dtype, dscale [d] fp32 | None, dbias [d] fp32 | None"""
+def scale_bwd(d_out, y, scale, sign, dtype, want_dscale=True, want_dbias=True, zeroed=None):
+    """d_out [M,d] fp32 -> dy [M,d] dtype, dscale [d] fp32 | None, dbias [d] fp32 | None.
+    `zeroed` (optional) = (dscale_buf, dbias_buf): pre-zeroed fp32 [d] accumulators (callers carve them out of one pooled
+    torch.zeros per sub-layer instead of launching a fill per gradient)."""
     M, d = d_out.shape
     dy = torch.empty(M, d, device=d_out.device, dtype=dtype)
-    dscale = torch.zeros(d, device=d_out.device, dtype=torch.float32) if (want_dscale and scale is not None) else None
-    dbias = torch.zeros(d, device=d_out.device, dtype=torch.float32) if want_dbias else None
+    if zeroed is not None:
+        dscale = zeroed[0] if (want_dscale and scale is not None) else None
+        dbias = zeroed[1] if want_dbias else None
+    else:
+        dscale = torch.zeros(d, device=d_out.device, dtype=torch.float32) if (want_dscale and scale is not None) else None
+        dbias = torch.zeros(d, device=d_out.device, dtype=torch.float32) if want_dbias else None
     P = _lib.ScaleBwdParams(rows=M, d=d, dtype=dt_code(dtype), sign=sign, d_out=_p(_c(d_out)), y=_p(y), scale=_p(scale), dy=_p(dy),
                             dscale=_p(dscale), dbias=_p(dbias))
     _lib.check(_lib.lib().dalle_b200_scale_bwd(ctypes.byref(P), _stream()), 'scale_bwd')
@@ -288,11 +294,12 @@ def scale_bwd(d_out, y, scale, sign, dtype, want_dscale=True, want_dbias=True):
     return dy, dscale, dbias
 
 
-def geglu_bwd(dh, u, want_dbias=True):
-    """dh [M,H], u [M,2H] -> (du [M,2H], db1 [2H] fp32 | None): streaming GEGLU adjoint + bias gradient in one pass"""
+def geglu_bwd(dh, u, want_dbias=True, zeroed=None):
+    """dh [M,H], u [M,2H] -> (du [M,2H], db1 [2H] fp32 | None): streaming GEGLU adjoint + bias gradient in one pass.
+    `zeroed`: optional pre-zeroed fp32 [2H] accumulator for the bias gradient."""
     M, H = dh.shape
     du = torch.empty_like(u)
-    db = torch.zeros(2 * H, device=dh.device, dtype=torch.float32) if want_dbias else None
+    db = (zeroed if zeroed is not None else torch.zeros(2 * H, device=dh.device, dtype=torch.float32)) if want_dbias else None
     _lib.check(_lib.lib().dalle_b200_geglu_bwd(_p(_c(dh)), _p(_c(u)), _p(du), _p(db), dt_code(dh.dtype), M, H, _stream()), 'geglu_bwd')
     _count()
     return du, db
