@@ -192,32 +192,40 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    // (whole warp converged; one elected lane issues each block of tcgen05 instructions, see elect_one())
+    // (whole warp converged; one elected lane issues each burst of tcgen05 instructions, see elect_one().  Software-pipelined:
+    //  S = Q K^T of tile i+1 is issued in the same burst as O += P V of tile i.)
     {
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, FK, false, false);    // S = Q K^T : both K-major
       constexpr uint32_t IDESC_O = make_idesc_bf16(128, 64, false, true);     // O = P V   : A K-major (TMEM / smem), B N-major
+      auto next_needed = [&](int kt) { while (kt < nkt && !needed(kt)) ++kt; return kt; };
       mbar_wait(q_full, 0);
       const uint64_t dq = make_smem_desc(sQ, 16, 1024);
-      int it = 0;
-      for (int kt = 0; kt < nkt; ++kt) {
-        if (!needed(kt)) continue;
-        const int s = it & 1;
-        mbar_wait(kv_full + 8 * s, (it >> 1) & 1);
+      const uint64_t dp = make_smem_desc(sP, 16, 1024);
+      int kt = next_needed(0);
+      if (kt < nkt) {
+        mbar_wait(kv_full, 0);
         tc_fence_after();
-        // (S of this tile overwrites the columns P of the previous tile was read from: safe, the tensor pipe executes the
-        //  previous O += P V before this S = Q K^T because both are issued in order by this thread)
-        const uint64_t dk = make_smem_desc(sK + s * FK_BYTES, 16, 1024);
+        const uint64_t dk = make_smem_desc(sK, 16, 1024);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
           umma_commit(s_full);
         }
         __syncwarp();
+      }
+      int it = 0;
+      while (kt < nkt) {
+        const int s = it & 1, sn = s ^ 1;
+        const int kn = next_needed(kt + 1);
+        const bool more = kn < nkt;
+        if (more) { mbar_wait(kv_full + 8 * sn, ((it + 1) >> 1) & 1); }
         mbar_wait(p_ready, it & 1);
         tc_fence_after();
         // V tile image [64 keys][64 dh] read as the N-major B operand: K = keys (16 rows = 2048 B per step), N = dh
         const uint64_t dv = make_smem_desc(sV + s * FK_BYTES, FK_BYTES, 1024);
-        const uint64_t dp = make_smem_desc(sP, 16, 1024);
+        // (S of the next tile overwrites the columns P of this tile is read from: safe, the tensor pipe executes this
+        //  O += P V before the next S = Q K^T because both are issued in order by the same thread)
+        const uint64_t dk = make_smem_desc(sK + sn * FK_BYTES, 16, 1024);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < FK / 16; ++k) {
@@ -226,8 +234,14 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
           }
           umma_commit(kv_empty + 8 * s);
           umma_commit(o_done);
+          if (more) {
+#pragma unroll
+            for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
+            umma_commit(s_full);
+          }
         }
         __syncwarp();
+        kt = kn;
         ++it;
       }
     }
@@ -549,18 +563,18 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
     __syncwarp();
   } else if (warp == 1) {
     {   // whole warp converged; an elected lane issues (see elect_one())
+      // Software-pipelined issue: the S^T / dP^T MMAs of tile i+1 go out in the same burst as the dV / dK MMAs of tile i (the
+      // in-order tensor pipe keeps the aliasing safe), so nothing but the softmax separates consecutive bursts.
       constexpr uint32_t IDESC_T = make_idesc_bf16(128, BW, false, false);    // S^T = K Q^T, dP^T = V dO^T
       constexpr uint32_t IDESC_G = make_idesc_bf16(128, 64, false, true);     // dV = P^T dO, dK = dS^T Q   (B N-major)
+      auto next_needed = [&](int qt) { while (qt < nqt && !needed(qt)) ++qt; return qt; };
       mbar_wait(kv_full, 0);
       const uint64_t dk = make_smem_desc(sK, 16, 1024), dv = make_smem_desc(sV, 16, 1024);
-      int it = 0;
-      for (int qt = 0; qt < nqt; ++qt) {
-        if (!needed(qt)) continue;
-        const int s = it & 1;
-        mbar_wait(q_full + 8 * s, (it >> 1) & 1);
+      int qt = next_needed(0);
+      if (qt < nqt) {
+        mbar_wait(q_full, 0);
         tc_fence_after();
-        ATTN_DBG(0);                                         // MMA: Q/dO tile present
-        const uint64_t dq = make_smem_desc(sQ + s * HALF_TILE, 16, 1024), ddo = make_smem_desc(sdO + s * HALF_TILE, 16, 1024);
+        const uint64_t dq = make_smem_desc(sQ, 16, 1024), ddo = make_smem_desc(sdO, 16, 1024);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k) umma_bf16(tSt, dk + 2 * k, dq + 2 * k, IDESC_T, k != 0);
@@ -569,11 +583,19 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
           umma_commit(st_full);
         }
         __syncwarp();
-        ATTN_DBG(1);                                         // MMA: S^T / dP^T issued
+      }
+      int it = 0;
+      while (qt < nqt) {
+        const int s = it & 1, sn = s ^ 1;
+        const int qn = next_needed(qt + 1);
+        const bool more = qn < nqt;
+        if (more) { mbar_wait(q_full + 8 * sn, ((it + 1) >> 1) & 1); }        // next Q / dO tile (prefetched long ago)
+        ATTN_DBG(1);
         mbar_wait_mode(ps_ready, it & 1, (P.wait_mode >> 1) & 1);
         tc_fence_after();
         ATTN_DBG(2);                                         // MMA: P^T / dS^T ready
         const uint64_t bq = make_smem_desc(sQ + s * HALF_TILE, HALF_TILE, 1024), bdo = make_smem_desc(sdO + s * HALF_TILE, HALF_TILE, 1024);
+        const uint64_t dq = make_smem_desc(sQ + sn * HALF_TILE, 16, 1024), ddo = make_smem_desc(sdO + sn * HALF_TILE, 16, 1024);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BW / 16; ++k) umma_bf16_ts(tdV, tPt + packed_kcol(k), bdo + 128 * k, IDESC_G, (it | k) != 0);
@@ -581,9 +603,17 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
           for (int k = 0; k < BW / 16; ++k) umma_bf16_ts(tdK, tdSt + packed_kcol(k), bq + 128 * k, IDESC_G, (it | k) != 0);
           umma_commit(q_empty + 8 * s);
           umma_commit(acc_done);
+          if (more) {
+#pragma unroll
+            for (int k = 0; k < DH / 16; ++k) umma_bf16(tSt, dk + 2 * k, dq + 2 * k, IDESC_T, k != 0);
+#pragma unroll
+            for (int k = 0; k < DH / 16; ++k) umma_bf16(tdPt, dv + 2 * k, ddo + 2 * k, IDESC_T, k != 0);
+            umma_commit(st_full);
+          }
         }
         __syncwarp();
-        ATTN_DBG(3);                                         // MMA: dV / dK issued
+        ATTN_DBG(3);                                         // MMA: burst issued
+        qt = qn;
         ++it;
       }
     }
@@ -731,18 +761,17 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
     }
     __syncwarp();
   } else if (warp == 1) {
-    {   // whole warp converged; an elected lane issues (see elect_one())
+    {   // whole warp converged; an elected lane issues (see elect_one()); software-pipelined like the dK/dV kernel
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, BW, false, false);
       constexpr uint32_t IDESC_G = make_idesc_bf16(128, 64, false, true);
+      auto next_needed = [&](int kt) { while (kt < nkt && !needed(kt)) ++kt; return kt; };
       mbar_wait(q_full, 0);
       const uint64_t dq = make_smem_desc(sQ, 16, 1024), ddo = make_smem_desc(sdO, 16, 1024);
-      int it = 0;
-      for (int kt = 0; kt < nkt; ++kt) {
-        if (!needed(kt)) continue;
-        const int s = it & 1;
-        mbar_wait(kv_full + 8 * s, (it >> 1) & 1);
+      int kt = next_needed(0);
+      if (kt < nkt) {
+        mbar_wait(kv_full, 0);
         tc_fence_after();
-        const uint64_t dk = make_smem_desc(sK + s * HALF_TILE, 16, 1024), dv = make_smem_desc(sV + s * HALF_TILE, 16, 1024);
+        const uint64_t dk = make_smem_desc(sK, 16, 1024), dv = make_smem_desc(sV, 16, 1024);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
@@ -751,16 +780,32 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
           umma_commit(s_full);
         }
         __syncwarp();
+      }
+      int it = 0;
+      while (kt < nkt) {
+        const int s = it & 1, sn = s ^ 1;
+        const int kn = next_needed(kt + 1);
+        const bool more = kn < nkt;
+        if (more) { mbar_wait(kv_full + 8 * sn, ((it + 1) >> 1) & 1); }
         mbar_wait_mode(ds_ready, it & 1, (P.wait_mode >> 1) & 1);
         tc_fence_after();
         const uint64_t bk = make_smem_desc(sK + s * HALF_TILE, HALF_TILE, 1024);
+        const uint64_t dk = make_smem_desc(sK + sn * HALF_TILE, 16, 1024), dv = make_smem_desc(sV + sn * HALF_TILE, 16, 1024);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BW / 16; ++k) umma_bf16_ts(tdQ, tdS + packed_kcol(k), bk + 128 * k, IDESC_G, (it | k) != 0);
           umma_commit(kv_empty + 8 * s);
           umma_commit(acc_done);
+          if (more) {
+#pragma unroll
+            for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
+#pragma unroll
+            for (int k = 0; k < DH / 16; ++k) umma_bf16(tdP, ddo + 2 * k, dv + 2 * k, IDESC_S, k != 0);
+            umma_commit(s_full);
+          }
         }
         __syncwarp();
+        kt = kn;
         ++it;
       }
     }
