@@ -139,20 +139,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    // Whole warp converged; the TMA instructions of a k-block are issued by one elected lane (operands stay warp-uniform, no
+    // R2UR / ELECT waterfall per cp.async.bulk.tensor -- see elect_one()).  Lane 0 owns the scheduler traffic.
+    {
       int s = 0; uint32_t ph = 0;
       int ss = 0; uint32_t sph = 0;
       unsigned int* counter = &g_sched_counter[dyn ? sched_slot : 0];
       const unsigned int last_draw = dyn ? static_cast<unsigned int>(num_tiles) + gridDim.x - 1u : 0xffffffffu;
-      if (first_draw == last_draw) atomicExch(counter, 0u);
-      int tile = static_cast<int>(first_draw);
+      if (lane == 0 && first_draw == last_draw) atomicExch(counter, 0u);
+      int tile = static_cast<int>(__shfl_sync(0xffffffffu, first_draw, 0));
       while (true) {
         mbar_wait(sempty_bar + 8 * ss, sph ^ 1);             // publish the tile id (or the end marker) to the other roles
-        sched_tile[ss] = tile;
-        mbar_arrive(sfull_bar + 8 * ss);
+        if (lane == 0) {
+          sched_tile[ss] = tile;
+          mbar_arrive(sfull_bar + 8 * ss);
+        }
+        __syncwarp();
         if (++ss == SCHED_DEPTH) { ss = 0; sph ^= 1; }
         if (tile >= num_tiles) break;
-        const unsigned int drawn = dyn ? atomicAdd(counter, 1u) : static_cast<unsigned int>(tile) + gridDim.x;   // next tile; the latency hides behind this tile's loads
+        unsigned int drawn = 0;
+        if (lane == 0) drawn = dyn ? atomicAdd(counter, 1u) : static_cast<unsigned int>(tile) + gridDim.x;   // next tile; latency hides behind the loads
         const int mn = tile % num_mn, split = tile / num_mn;
         const int m0 = (mn / num_n) * BLOCK_M;          // n-fastest: CTAs running together share the A tile through L2
         const int n0 = (mn % num_n) * BLOCK_N;
@@ -160,34 +166,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + 8 * s, ph ^ 1);
           const uint32_t fb = full_bar + 8 * s;
-          mbar_expect_tx(fb, L::STAGE_BYTES);
           const uint32_t sa = smem_u32(smem_a + s * A_STAGE_BYTES);
           const uint32_t sb = smem_u32(smem_b + s * B_STAGE_BYTES);
           const int k0 = kb * BLOCK_K;
-          if constexpr (!A_MN) {
-            tma_load_2d(sa, &tmA, fb, k0, m0);                                   // box {64 k, 128 m}
-          } else {
+          if (elect_one()) {
+            mbar_expect_tx(fb, L::STAGE_BYTES);
+            if constexpr (!A_MN) {
+              tma_load_2d(sa, &tmA, fb, k0, m0);                                   // box {64 k, 128 m}
+            } else {
 #pragma unroll
-            for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(sa + c * BOX_MN_BYTES, &tmA, fb, m0 + c * 64, k0);   // box {64 m, 64 k}
-          }
-          if constexpr (!B_MN) {
-#pragma unroll
-            for (int c = 0; c < BLOCK_N / 128; ++c) {
-              int row = n0 + c * 128;
-              if constexpr (EPI == DB200_EPI_GEGLU) row = (c == 0) ? (n0 >> 1) : e.hidden + (n0 >> 1);
-              tma_load_2d(sb + c * (128 * BLOCK_K * 2), &tmB, fb, k0, row);      // box {64 k, 128 n}
+              for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(sa + c * BOX_MN_BYTES, &tmA, fb, m0 + c * 64, k0);   // box {64 m, 64 k}
             }
-          } else {
+            if constexpr (!B_MN) {
 #pragma unroll
-            for (int c = 0; c < BLOCK_N / 64; ++c) tma_load_2d(sb + c * BOX_MN_BYTES, &tmB, fb, n0 + c * 64, k0);   // box {64 n, 64 k}
+              for (int c = 0; c < BLOCK_N / 128; ++c) {
+                int row = n0 + c * 128;
+                if constexpr (EPI == DB200_EPI_GEGLU) row = (c == 0) ? (n0 >> 1) : e.hidden + (n0 >> 1);
+                tma_load_2d(sb + c * (128 * BLOCK_K * 2), &tmB, fb, k0, row);      // box {64 k, 128 n}
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < BLOCK_N / 64; ++c) tma_load_2d(sb + c * BOX_MN_BYTES, &tmB, fb, n0 + c * 64, k0);   // box {64 n, 64 k}
+            }
           }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        if (drawn == last_draw) atomicExch(counter, 0u);    // last draw of this launch: leave the slot clean
+        drawn = __shfl_sync(0xffffffffu, drawn, 0);
+        if (lane == 0 && drawn == last_draw) atomicExch(counter, 0u);    // last draw of this launch: leave the slot clean
         tile = static_cast<int>(drawn);
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     // Whole warp converged, one elected lane issues each k-block (see elect_one() in tc_common.cuh): descriptors stay in
