@@ -83,12 +83,67 @@ __device__ __forceinline__ void gelu_fast(float g, float& gelu, float& dgelu) {
   gelu = g * cdf;
   dgelu = fmaf(g * 0.39894228040143267794f, ex, cdf);
 }
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): one instruction per two elements on the fp32 pipe.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+// gelu_fast for two elements at once: the same Abramowitz-Stegun evaluation with the polynomial and the products on packed
+// fp32 instructions (13 packed + 4 MUFU + 4 scalar per pair instead of ~19 scalar per element).
+__device__ __forceinline__ void gelu_fast2(float2 g, float2& gelu, float2& dgelu) {
+  const float2 x = mul2(g, splat2(0.70710678118654752440f));
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 den = fma2(ax, splat2(0.3275911f), splat2(1.0f));
+  float2 t, ex;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+  const float2 q = mul2(mul2(ax, ax), splat2(-1.4426950408889634f));        // -x^2 * log2(e)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.x) : "f"(q.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(q.y));
+  float2 poly = fma2(t, splat2(1.061405429f), splat2(-1.453152027f));
+  poly = fma2(t, poly, splat2(1.421413741f));
+  poly = fma2(t, poly, splat2(-0.284496736f));
+  poly = fma2(t, poly, splat2(0.254829592f));
+  const float2 m = mul2(mul2(poly, t), ex);
+  const float2 erf_abs = fma2(m, splat2(-1.0f), splat2(1.0f));
+  const float2 cs = make_float2(copysignf(erf_abs.x, x.x), copysignf(erf_abs.y, x.y));
+  const float2 cdf = fma2(cs, splat2(0.5f), splat2(0.5f));
+  gelu = mul2(g, cdf);
+  dgelu = fma2(mul2(g, splat2(0.39894228040143267794f)), ex, cdf);
+}
+
 template <typename T> __device__ __forceinline__ void gelu_pair(float g, float& gelu, float& dgelu);
 template <> __device__ __forceinline__ void gelu_pair<float>(float g, float& gelu, float& dgelu) { gelu = gelu_erf(g); dgelu = gelu_erf_grad(g); }
 template <> __device__ __forceinline__ void gelu_pair<__nv_bfloat16>(float g, float& gelu, float& dgelu) { gelu_fast(g, gelu, dgelu); }
 template <typename T> __device__ __forceinline__ float gelu_fwd(float g);
 template <> __device__ __forceinline__ float gelu_fwd<float>(float g) { return gelu_erf(g); }
 template <> __device__ __forceinline__ float gelu_fwd<__nv_bfloat16>(float g) { float a, b; gelu_fast(g, a, b); return a; }
+// two elements: fp32 mode stays on the exact scalar erf, bf16 mode uses the packed evaluation
+template <typename T> __device__ __forceinline__ void gelu_pair2(float2 g, float2& gelu, float2& dgelu);
+template <> __device__ __forceinline__ void gelu_pair2<float>(float2 g, float2& gelu, float2& dgelu) {
+  gelu = make_float2(gelu_erf(g.x), gelu_erf(g.y)); dgelu = make_float2(gelu_erf_grad(g.x), gelu_erf_grad(g.y));
+}
+template <> __device__ __forceinline__ void gelu_pair2<__nv_bfloat16>(float2 g, float2& gelu, float2& dgelu) { gelu_fast2(g, gelu, dgelu); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

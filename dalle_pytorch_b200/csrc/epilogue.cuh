@@ -374,7 +374,9 @@ __device__ __forceinline__ void epi_chunk_cols_geglu(const EpiArgs& e, int mbase
         store2<T>(u + j, a0, a1);
         store2<T>(u + e.hidden + j, g0, g1);
       }
-      store2<T>(reinterpret_cast<T*>(e.h_out) + (long long)m * e.hidden + j, a0 * gelu_fwd<T>(g0), a1 * gelu_fwd<T>(g1));
+      float2 f, df;
+      gelu_pair2<T>(make_float2(g0, g1), f, df);
+      store2<T>(reinterpret_cast<T*>(e.h_out) + (long long)m * e.hidden + j, a0 * f.x, a1 * f.y);
     }
   }
 }
