@@ -344,7 +344,7 @@ def run_gpu_arm(args):
            'dtype': 'bf16' if dtype == torch.bfloat16 else 'f32', 'data': 'synthetic',
            'config': {'workload': workload_name(args.config, c), 'global_batch': batch * world, 'seq_len': seq,
                       'parallelism': f'dp{world}', 'l2': 'activations and weights per step (GBs) exceed the 126 MB L2; no flush needed',
-                      'head': 'block stack, logits head GEMMs and cross-entropy all run in libdalle_b200 (embedding lookup is torch)'},
+                      'head': 'token embedding gather/scatter, block stack, logits head GEMMs and cross-entropy all run in libdalle_b200'},
            'e2e': {'value': e2e_value, 'unit': 'tokens/s', 'ms_per_step': ms_e2e / args.steps,
                    'h2d_bytes_per_step': int(text_h.numel() * 8 + image_h.numel() * 8) * world, 'd2h_bytes_per_step': 4 * world},
            'gpu_launches': launches, 'model_tflops_per_gpu': value / world * flops_tok / 1e12,

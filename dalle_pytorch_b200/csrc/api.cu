@@ -47,6 +47,7 @@ int qkv_rotary_launch(const void* qkv, void* q, void* k, void* v, const float* c
 int geglu_bwd_launch(const void* dh, const void* u, void* du, float* dbias, int dtype, int rows, int hidden, cudaStream_t st);
 int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st);
 int axpby_launch(const float* a, const float* b, float alpha, float* y, int64_t count, cudaStream_t st);
+int embed_launch(bool bwd, const long long* ids, const float* a, float* o, int batch, int seg_len, int n, int seg_off, int d, int vocab, cudaStream_t st);
 int gemm_simt_launch(const db200_gemm_params& p, cudaStream_t st);
 bool gemm_tcgen05_supported(const db200_gemm_params& p, const char** why);
 int gemm_tcgen05_launch(const db200_gemm_params& p, cudaStream_t st);
@@ -278,6 +279,20 @@ int dalle_b200_cast_bf16(const float* src, void* dst, int64_t count, void* strea
   return cast_bf16_launch(src, dst, count, (cudaStream_t)stream);
 }
 
+int dalle_b200_embed_fwd(const int64_t* ids, const float* weight, float* out, int batch, int seg_len, int n, int seg_off, int d, int vocab,
+                         void* stream) {
+  DB200_CHECK_ARG(ids && weight && out, "embed_fwd: null pointer");
+  DB200_CHECK_ARG(batch >= 0 && seg_len >= 0 && n > 0 && seg_off >= 0 && seg_off + seg_len <= n && vocab > 0, "embed_fwd: bad geometry");
+  DB200_CHECK_ARG(d > 0 && d % 4 == 0 && aligned16(weight) && aligned16(out), "embed_fwd: d must be a multiple of 4, pointers 16-byte aligned");
+  return embed_launch(false, reinterpret_cast<const long long*>(ids), weight, out, batch, seg_len, n, seg_off, d, vocab, (cudaStream_t)stream);
+}
+int dalle_b200_embed_bwd(const int64_t* ids, const float* d_out, float* dweight, int batch, int seg_len, int n, int seg_off, int d, int vocab,
+                         void* stream) {
+  DB200_CHECK_ARG(ids && d_out && dweight, "embed_bwd: null pointer");
+  DB200_CHECK_ARG(batch >= 0 && seg_len >= 0 && n > 0 && seg_off >= 0 && seg_off + seg_len <= n && vocab > 0, "embed_bwd: bad geometry");
+  DB200_CHECK_ARG(d > 0 && d % 4 == 0 && aligned16(d_out) && aligned16(dweight), "embed_bwd: d must be a multiple of 4, pointers 16-byte aligned");
+  return embed_launch(true, reinterpret_cast<const long long*>(ids), d_out, dweight, batch, seg_len, n, seg_off, d, vocab, (cudaStream_t)stream);
+}
 int dalle_b200_axpby(const float* a, const float* b, float alpha, float* y, int64_t count, void* stream) {
   DB200_CHECK_ARG(a && b && y && count >= 0, "axpby: bad args");
   DB200_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(y), "axpby: alignment");

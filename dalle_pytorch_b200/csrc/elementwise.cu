@@ -844,7 +844,44 @@ __global__ void axpby_kernel(const float* __restrict__ a, const float* __restric
   }
 }
 
+// token embedding gather / scatter-add: one warp per token row, 16 bytes per lane and step
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ w, float* __restrict__ out,
+                                                        int rows, int seg_len, int n, int seg_off, int d, int vocab) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int b = r / seg_len, l = r - b * seg_len;
+  long long id = ids[r];
+  if (id < 0 || id >= vocab) id = 0;                       // validated on the host side of the module; never index out of range
+  const float* src = w + id * d;
+  float* dst = out + ((long long)b * n + seg_off + l) * d;
+  for (int c = lane * 4; c < d; c += 128) *reinterpret_cast<float4*>(dst + c) = __ldg(reinterpret_cast<const float4*>(src + c));
+}
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ g, float* __restrict__ dw,
+                                                        int rows, int seg_len, int n, int seg_off, int d, int vocab) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int b = r / seg_len, l = r - b * seg_len;
+  const long long id = ids[r];
+  if (id < 0 || id >= vocab) return;
+  const float* src = g + ((long long)b * n + seg_off + l) * d;
+  float* dst = dw + id * d;
+  for (int c = lane * 4; c < d; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(src + c);
+    atomicAdd(dst + c, v.x); atomicAdd(dst + c + 1, v.y); atomicAdd(dst + c + 2, v.z); atomicAdd(dst + c + 3, v.w);
+  }
+}
+
 }  // namespace
+
+int embed_launch(bool bwd, const long long* ids, const float* a, float* o, int batch, int seg_len, int n, int seg_off, int d, int vocab,
+                 cudaStream_t st) {
+  const int rows = batch * seg_len;
+  if (rows == 0) return DB200_OK;
+  if (bwd) embed_bwd_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(ids, a, o, rows, seg_len, n, seg_off, d, vocab);
+  else embed_fwd_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(ids, a, o, rows, seg_len, n, seg_off, d, vocab);
+  DB200_LAUNCH_OK("embed_kernel");
+  return DB200_OK;
+}
 
 int ln_shift_fwd_launch(const db200_ln_shift_fwd_params& P, cudaStream_t st) {
   const int rows = P.batch * P.n;

@@ -214,9 +214,13 @@ class DALLE(nn.Module):
         text = torch.where(text == 0, text_range, text)
         text = F.pad(text, (1, 0), value=0)                      # <bos>
 
-        tokens = self.text_emb(text)
-        seq_len = tokens.shape[1]
-
+        # library path (plain nn.Embedding tables on the GPU): both lookups and the concatenation are one gather each into the
+        # [b, n, d] token buffer, and the table gradients are atomic scatter-adds (functional.EmbedTokensFn)
+        fused_embed = (text.is_cuda and type(self.text_emb) is nn.Embedding and type(self.image_emb) is nn.Embedding
+                       and self.text_emb.weight.dtype == torch.float32 and self.text_emb.weight.shape[1] % 4 == 0
+                       and self.text_emb.padding_idx is None and self.text_emb.max_norm is None)
+        img_ids = None
+        image_len = 0
         if exists(image) and not is_empty(image):
             if len(image.shape) == 4:
                 image_size = self.vae.image_size
@@ -227,9 +231,20 @@ class DALLE(nn.Module):
             image_len = image.shape[1]
             # dalle_pytorch.py:627-630 embeds every image token and then drops the last position when the sequence is one too
             # long; embedding only the tokens that survive gives the same tensor without a strided slice + 84 MB copy
-            drop = 1 if tokens.shape[1] + image_len > total_seq_len else 0
-            tokens = torch.cat((tokens, self.image_emb(image[:, :image_len - drop] if drop else image)), dim=1)
-            seq_len += image_len - drop
+            drop = 1 if text.shape[1] + image_len > total_seq_len else 0
+            img_ids = image[:, :image_len - drop] if drop else image
+            image_len -= drop
+        if fused_embed:
+            from .functional import EmbedTokensFn
+            # (ids are not range-checked on the host -- that would be a device sync per step; the kernels never index outside
+            #  the tables: an out-of-range id reads row 0 and receives no gradient)
+            tokens = EmbedTokensFn.apply(text.contiguous(), None if img_ids is None else img_ids.contiguous(),
+                                         self.text_emb.weight, self.image_emb.weight)
+        else:
+            tokens = self.text_emb(text)
+            if img_ids is not None:
+                tokens = torch.cat((tokens, self.image_emb(img_ids)), dim=1)
+        seq_len = text.shape[1] + image_len
 
         if tokens.shape[1] > total_seq_len:
             seq_len -= 1

@@ -242,6 +242,37 @@ class FFSublayerFn(torch.autograd.Function):
         return (None, None, None, dx, d_resid, dln_w, dln_b, dw1, db1, dw2, db2, dscale)
 
 
+class EmbedTokensFn(torch.autograd.Function):
+    """tokens = cat(text_emb(text_ids), image_emb(image_ids)) (dalle_pytorch.py:616-630) as two gathers writing one [b, n, d]
+    buffer; the backward scatter-adds the token gradients into the two tables with fp32 atomics."""
+
+    @staticmethod
+    def forward(ctx, text_ids, image_ids, w_text, w_image):
+        B, Lt = text_ids.shape
+        Li = 0 if image_ids is None else image_ids.shape[1]
+        d = w_text.shape[1]
+        out = torch.empty(B, Lt + Li, d, device=w_text.device, dtype=torch.float32)
+        ops.embed_fwd(text_ids, w_text.detach().float(), out, 0)
+        if Li:
+            ops.embed_fwd(image_ids, w_image.detach().float(), out, Lt)
+        ctx.save_for_backward(text_ids, image_ids)
+        ctx.shapes = (w_text.shape, None if w_image is None else w_image.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        text_ids, image_ids = ctx.saved_tensors
+        d_out = d_out.contiguous().float()
+        Lt = text_ids.shape[1]
+        dw_text = torch.zeros(ctx.shapes[0], device=d_out.device, dtype=torch.float32)
+        ops.embed_bwd(text_ids, d_out, dw_text, 0)
+        dw_image = None
+        if image_ids is not None and image_ids.shape[1] > 0:
+            dw_image = torch.zeros(ctx.shapes[1], device=d_out.device, dtype=torch.float32)
+            ops.embed_bwd(image_ids, d_out, dw_image, Lt)
+        return None, None, dw_text, dw_image
+
+
 class LayerNormFn(torch.autograd.Function):
     """Plain LayerNorm on the ln_shift kernels (used for sandwich norm, transformer.py:96,102)."""
 

@@ -339,6 +339,22 @@ def cast_bf16(src):
     return dst
 
 
+def embed_fwd(ids, weight, out, seg_off):
+    """out[b, seg_off + l, :] = weight[ids[b, l], :]   (ids [B, L] int64, out [B, n, d] fp32 contiguous, written in place)"""
+    B, L = ids.shape
+    _, n, d = out.shape
+    _lib.check(_lib.lib().dalle_b200_embed_fwd(_p(_c(ids)), _p(_c(weight)), _p(out), B, L, n, seg_off, d, weight.shape[0], _stream()), 'embed_fwd')
+    _count()
+
+
+def embed_bwd(ids, d_out, dweight, seg_off):
+    """dweight[ids[b, l], :] += d_out[b, seg_off + l, :]   (fp32 atomics)"""
+    B, L = ids.shape
+    _, n, d = d_out.shape
+    _lib.check(_lib.lib().dalle_b200_embed_bwd(_p(_c(ids)), _p(_c(d_out)), _p(dweight), B, L, n, seg_off, d, dweight.shape[0], _stream()), 'embed_bwd')
+    _count()
+
+
 def axpby(a, b, alpha):
     """a + alpha * b over fp32 tensors of equal shape"""
     _c(a), _c(b)

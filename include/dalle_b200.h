@@ -222,6 +222,15 @@ int dalle_b200_cast_bf16(const float* src, void* dst, int64_t count, void* strea
 /* y = a + alpha*b over fp32 (reversible stream arithmetic, reversible.py:83,86,96,99) */
 int dalle_b200_axpby(const float* a, const float* b, float alpha, float* y, int64_t count, void* stream);
 
+/* Token embedding written straight into the [batch, n, d] fp32 token stream (dalle_pytorch.py:616-630: text_emb / image_emb
+ * lookups + torch.cat): out[b, seg_off + l, :] = weight[ids[b, l], :] for l < seg_len.  ids are int64, 0 <= id < vocab.
+ * The backward adds d_out[b, seg_off + l, :] into dweight[ids[b, l], :] with fp32 atomics (dweight zero-initialised or
+ * carrying a previous accumulation), replacing nn.Embedding's sort-based gradient. */
+int dalle_b200_embed_fwd(const int64_t* ids, const float* weight, float* out, int batch, int seg_len, int n, int seg_off, int d, int vocab,
+                         void* stream);
+int dalle_b200_embed_bwd(const int64_t* ids, const float* d_out, float* dweight, int batch, int seg_len, int n, int seg_off, int d, int vocab,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -293,3 +293,30 @@ def test_attention_backends_bf16(backend, kind, code, n, T, fm, monkeypatch):
     dq, dk, dv = (dqkv.view(b, n, 3, h, dh)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
     for name, got, ref in (('dq', dq, qr.grad), ('dk', dk, kr.grad), ('dv', dv, vr.grad)):
         report(f'attn_bwd[{backend}] {name} {kind} n={n}', got, ref, 3e-2, 3e-2 * float(ref.abs().max()))
+
+
+@pytest.mark.gpu
+def test_token_embedding_gather_and_scatter():
+    """dalle_b200_embed_fwd / _bwd against nn.Embedding + cat (dalle_pytorch.py:616-630): bit-exact forward, fp32-atomic
+    backward (same sums, different order) within 1e-5."""
+    from dalle_pytorch_b200.functional import EmbedTokensFn
+    torch.manual_seed(0)
+    B, Lt, Li, d = 3, 9, 16, 64
+    wt = torch.randn(40, d, device='cuda', requires_grad=True)
+    wi = torch.randn(32, d, device='cuda', requires_grad=True)
+    text = torch.randint(0, 40, (B, Lt), device='cuda')
+    image = torch.randint(0, 32, (B, Li), device='cuda')
+    image[0, :4] = image[0, 0]                                   # repeated ids: the scatter must accumulate
+    out = EmbedTokensFn.apply(text, image, wt, wi)
+    ref = torch.cat((torch.nn.functional.embedding(text, wt), torch.nn.functional.embedding(image, wi)), dim=1)
+    assert torch.equal(out, ref)
+    g = torch.randn_like(out)
+    out.backward(g)
+    got = (wt.grad.clone(), wi.grad.clone())
+    wt.grad = wi.grad = None
+    ref.backward(g)
+    report('embed dW text', got[0], wt.grad, 1e-5, 1e-5)
+    report('embed dW image', got[1], wi.grad, 1e-5, 1e-5)
+    # text only (generation prefix)
+    out2 = EmbedTokensFn.apply(text, None, wt, wi)
+    assert torch.equal(out2, torch.nn.functional.embedding(text, wt))
