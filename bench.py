@@ -37,7 +37,7 @@ CONFIGS = {
 NUM_TEXT_TOKENS, NUM_IMAGE_TOKENS = 10000, 8192
 # measured with ncu on B200 (profiles/r01_gemm_ncu_summary.txt): 36.6 GB of DRAM traffic over the 150 tcgen05 GEMM launches of a C2 step
 # (algorithmic operand+result bytes of the same launches: 33.9 GB)
-GEMM_DRAM_BYTES_PER_LAUNCH = 244e6
+GEMM_DRAM_BYTES_PER_LAUNCH = 229e6
 METRIC = 'DALL-E fwd+bwd tokens/sec at seq=1280, dim=1024'
 
 
@@ -310,7 +310,7 @@ def run_gpu_arm(args):
         ach = fam['flops'] / (fam['ms'] * 1e-3) / 1e12
         roof = {'bound': 'tensor', 'kernel': 'gemm_tcgen05_kernel (all fwd/dgrad/wgrad GEMMs of the block stack)', 'achieved': ach,
                 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': GEMM_DRAM_BYTES_PER_LAUNCH if args.config == 'c2' else None,
-                'traffic_note': 'dram__bytes_read+write per launch averaged over the 150 GEMM launches of one C2 step, ncu --set full capture profiles/r01_gemm_ncu_summary.txt',
+                'traffic_note': 'dram__bytes_read+write per launch, mean of the 20 consecutive GEMM launches (last forward layer, head, first backward layer) of the ncu --set full capture summarised in profiles/r01_gemm_ncu_summary.txt; algorithmic bytes of the same 20 launches average 226 MB',
                 'peak_source': peak_src,
                 'launches_per_step': fam['launches'] / args.steps, 'share_of_step': fam['ms'] / ms_dev,
                 'by_shape': gemm_stats.get('by_shape', {})}

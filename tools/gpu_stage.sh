@@ -25,7 +25,7 @@ for stage in "$@"; do
     attn_probe) for be in tc mma; do for pat in full axial_row axial_col; do timeout 120 python tools/attn_probe.py --backend $be --pattern $pat; done; done 2>&1 | grep "^\[" | tee gpurun_out/attn_probe.log ;;
     ncu_attn) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_.*tc_kernel -s 3 -c 3 -o gpurun_out/prof_attn -f python tools/attn_probe.py --backend tc --iters 1 > gpurun_out/ncu_attn.log 2>&1; tail -3 gpurun_out/ncu_attn.log ;;
     ncu_ew) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"bwd_tma|scale_bwd_slab|geglu_bwd_kernel" -s 2 -c 4 -o gpurun_out/prof_ew -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_ew.log 2>&1; tail -2 gpurun_out/ncu_ew.log ;;
-    ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1; tail -3 gpurun_out/ncu_list.log ;;
+    ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1; tail -3 gpurun_out/ncu_list.log ;;
     ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 44 -c 20 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log ;;
     *) echo "unknown stage $stage" ;;
   esac
