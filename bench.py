@@ -35,8 +35,8 @@ CONFIGS = {
     'c5': dict(dim=1024, depth=64, heads=16, text_seq_len=256, fmap=32, batch=32, attn_types=('axial_row', 'axial_col'), reversible=False, dtype='bf16'),
 }
 NUM_TEXT_TOKENS, NUM_IMAGE_TOKENS = 10000, 8192
-# measured with ncu on B200 (profiles/r01_gemm_ncu_summary.txt): 36.6 GB of DRAM traffic over the 150 tcgen05 GEMM launches of a C2 step
-# (algorithmic operand+result bytes of the same launches: 33.9 GB)
+# measured with ncu on B200 (profiles/r01_gemm_ncu_summary.txt): mean dram__bytes_read+write of 20 consecutive tcgen05 GEMM launches
+# of a C2 step (algorithmic operand+result bytes of the same launches: 226 MB per launch)
 GEMM_DRAM_BYTES_PER_LAUNCH = 229e6
 METRIC = 'DALL-E fwd+bwd tokens/sec at seq=1280, dim=1024'
 
