@@ -10,5 +10,6 @@ from .transformer import (Transformer, FeedForward, GEGLU, LayerScale, PreNorm, 
 from .reversible import SequentialSequence, ReversibleSequence
 from .dalle import DALLE, TokenVAE
 from . import ops, functional
+from .optim import FusedAdam
 
 __version__ = '0.1.0'

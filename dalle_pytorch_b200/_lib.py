@@ -66,7 +66,13 @@ class ScaleBwdParams(ctypes.Structure):
                 ('dscale', c_void_p), ('dbias', c_void_p)]
 
 
-_STRUCTS = (LnShiftFwdParams, LnShiftBwdParams, GemmParams, AttnFwdParams, AttnBwdParams, ScaleBwdParams)
+class AdamParams(ctypes.Structure):
+    _fields_ = [('p', c_void_p), ('g', c_void_p), ('m', c_void_p), ('v', c_void_p), ('count', c_int64),
+                ('lr', c_float), ('beta1', c_float), ('beta2', c_float), ('eps', c_float), ('weight_decay', c_float),
+                ('step', c_int), ('max_norm', c_float), ('gnorm_sq', c_void_p)]
+
+
+_STRUCTS = (LnShiftFwdParams, LnShiftBwdParams, GemmParams, AttnFwdParams, AttnBwdParams, ScaleBwdParams, AdamParams)
 
 _lib = None
 _lock = threading.Lock()
@@ -106,6 +112,8 @@ def _declare(lib):
     lib.dalle_b200_ce_bwd.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p]
     lib.dalle_b200_cast_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     lib.dalle_b200_axpby.argtypes = [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p]
+    lib.dalle_b200_sumsq.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+    lib.dalle_b200_adam.argtypes = [ctypes.POINTER(AdamParams), c_void_p]
     lib.dalle_b200_embed_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.dalle_b200_embed_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
     sizes = (c_int * 8)()
@@ -140,4 +148,4 @@ def check(rc, what=''):
 EXPORTED = ['dalle_b200_version', 'dalle_b200_last_error', 'dalle_b200_device_ok', 'dalle_b200_abi_sizes',
             'dalle_b200_ln_shift_fwd', 'dalle_b200_ln_shift_bwd', 'dalle_b200_gemm', 'dalle_b200_gemm_select', 'dalle_b200_attn_fwd',
             'dalle_b200_attn_bwd', 'dalle_b200_scale_bwd', 'dalle_b200_colsum', 'dalle_b200_qkv_rotary', 'dalle_b200_geglu_bwd', 'dalle_b200_ce_fwd', 'dalle_b200_ce_bwd', 'dalle_b200_cast_bf16',
-            'dalle_b200_axpby', 'dalle_b200_embed_fwd', 'dalle_b200_embed_bwd']
+            'dalle_b200_axpby', 'dalle_b200_embed_fwd', 'dalle_b200_embed_bwd', 'dalle_b200_sumsq', 'dalle_b200_adam']

@@ -47,6 +47,8 @@ int qkv_rotary_launch(const void* qkv, void* q, void* k, void* v, const float* c
 int geglu_bwd_launch(const void* dh, const void* u, void* du, float* dbias, int dtype, int rows, int hidden, cudaStream_t st);
 int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st);
 int axpby_launch(const float* a, const float* b, float alpha, float* y, int64_t count, cudaStream_t st);
+int sumsq_launch(const float* x, int64_t count, float* out, cudaStream_t st);
+int adam_launch(const db200_adam_params& P, cudaStream_t st);
 int embed_launch(bool bwd, const long long* ids, const float* a, float* o, int batch, int seg_len, int n, int seg_off, int d, int vocab, cudaStream_t st);
 int gemm_simt_launch(const db200_gemm_params& p, cudaStream_t st);
 bool gemm_tcgen05_supported(const db200_gemm_params& p, const char** why);
@@ -92,10 +94,11 @@ int dalle_b200_device_ok(int dev) {
 }
 
 int dalle_b200_abi_sizes(int* out, int capacity) {
-  const int sizes[6] = {(int)sizeof(db200_ln_shift_fwd_params), (int)sizeof(db200_ln_shift_bwd_params), (int)sizeof(db200_gemm_params),
-                        (int)sizeof(db200_attn_fwd_params),     (int)sizeof(db200_attn_bwd_params),     (int)sizeof(db200_scale_bwd_params)};
-  for (int i = 0; i < 6 && i < capacity; ++i) out[i] = sizes[i];
-  return 6;
+  const int sizes[7] = {(int)sizeof(db200_ln_shift_fwd_params), (int)sizeof(db200_ln_shift_bwd_params), (int)sizeof(db200_gemm_params),
+                        (int)sizeof(db200_attn_fwd_params),     (int)sizeof(db200_attn_bwd_params),     (int)sizeof(db200_scale_bwd_params),
+                        (int)sizeof(db200_adam_params)};
+  for (int i = 0; i < 7 && i < capacity; ++i) out[i] = sizes[i];
+  return 7;
 }
 
 int dalle_b200_ln_shift_fwd(const db200_ln_shift_fwd_params* p, void* stream) {
@@ -279,6 +282,19 @@ int dalle_b200_cast_bf16(const float* src, void* dst, int64_t count, void* strea
   return cast_bf16_launch(src, dst, count, (cudaStream_t)stream);
 }
 
+int dalle_b200_sumsq(const float* x, int64_t count, float* out, void* stream) {
+  DB200_CHECK_ARG(x && out && count >= 0, "sumsq: bad args");
+  DB200_CHECK_ARG(aligned16(x), "sumsq: x must be 16-byte aligned");
+  return sumsq_launch(x, count, out, (cudaStream_t)stream);
+}
+int dalle_b200_adam(const db200_adam_params* p, void* stream) {
+  DB200_CHECK_ARG(p != nullptr, "adam: null params");
+  DB200_CHECK_ARG(p->p && p->g && p->m && p->v && p->count >= 0, "adam: null tensor / bad count");
+  DB200_CHECK_ARG(aligned16(p->p) && aligned16(p->g) && aligned16(p->m) && aligned16(p->v), "adam: buffers must be 16-byte aligned");
+  DB200_CHECK_ARG(p->step >= 1 && p->beta1 >= 0.f && p->beta1 < 1.f && p->beta2 >= 0.f && p->beta2 < 1.f && p->eps > 0.f, "adam: bad hyper-parameters");
+  DB200_CHECK_ARG(p->max_norm <= 0.f || p->gnorm_sq != nullptr, "adam: clipping needs the gradient-norm scalar");
+  return adam_launch(*p, (cudaStream_t)stream);
+}
 int dalle_b200_embed_fwd(const int64_t* ids, const float* weight, float* out, int batch, int seg_len, int n, int seg_off, int d, int vocab,
                          void* stream) {
   DB200_CHECK_ARG(ids && weight && out, "embed_fwd: null pointer");

@@ -1,5 +1,7 @@
 // HBM-bound glue kernels of the DALL-E block: LayerNorm + token-shift (forward and backward), LayerScale /
 // residual backward, column sums, casts.  Each is one pass over its tensor with 16-byte accesses.
+#include <cmath>
+
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "tc_common.cuh"
@@ -844,6 +846,57 @@ __global__ void axpby_kernel(const float* __restrict__ a, const float* __restric
   }
 }
 
+// ---- optimizer step (train_dalle.py:617-619) over flat buffers ----------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long count, float* __restrict__ out) {
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < count; i += stride) {
+    if (i + 3 < count) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i);
+      acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    } else {
+      for (long long j = i; j < count; ++j) acc += x[j] * x[j];
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(out, t);
+  }
+}
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float coef, float wd, float b1, float b2, float step_size,
+                                         float inv_sqrt_bc2, float eps) {
+  g = g * coef + wd * p;
+  m = m + (1.0f - b1) * (g - m);                       // exp_avg.lerp_(grad, 1 - beta1)
+  v = b2 * v + (1.0f - b2) * g * g;
+  p -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + eps);
+}
+__global__ void __launch_bounds__(256) adam_kernel(db200_adam_params P, float step_size, float inv_sqrt_bc2) {
+  float coef = 1.0f;
+  if (P.max_norm > 0.f) {
+    const float c = P.max_norm / (sqrtf(__ldg(P.gnorm_sq)) + 1e-6f);
+    coef = c < 1.0f ? c : 1.0f;
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < P.count; i += stride) {
+    if (i + 3 < P.count) {
+      float4 p = *reinterpret_cast<float4*>(P.p + i), m = *reinterpret_cast<float4*>(P.m + i), v = *reinterpret_cast<float4*>(P.v + i);
+      const float4 g = *reinterpret_cast<const float4*>(P.g + i);
+      adam_one(p.x, g.x, m.x, v.x, coef, P.weight_decay, P.beta1, P.beta2, step_size, inv_sqrt_bc2, P.eps);
+      adam_one(p.y, g.y, m.y, v.y, coef, P.weight_decay, P.beta1, P.beta2, step_size, inv_sqrt_bc2, P.eps);
+      adam_one(p.z, g.z, m.z, v.z, coef, P.weight_decay, P.beta1, P.beta2, step_size, inv_sqrt_bc2, P.eps);
+      adam_one(p.w, g.w, m.w, v.w, coef, P.weight_decay, P.beta1, P.beta2, step_size, inv_sqrt_bc2, P.eps);
+      *reinterpret_cast<float4*>(P.p + i) = p; *reinterpret_cast<float4*>(P.m + i) = m; *reinterpret_cast<float4*>(P.v + i) = v;
+    } else {
+      for (long long j = i; j < P.count; ++j) adam_one(P.p[j], P.g[j], P.m[j], P.v[j], coef, P.weight_decay, P.beta1, P.beta2, step_size, inv_sqrt_bc2, P.eps);
+    }
+  }
+}
+
 // token embedding gather / scatter-add: one warp per token row, 16 bytes per lane and step
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ w, float* __restrict__ out,
                                                         int rows, int seg_len, int n, int seg_off, int d, int vocab) {
@@ -872,6 +925,26 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restr
 }
 
 }  // namespace
+
+int sumsq_launch(const float* x, int64_t count, float* out, cudaStream_t st) {
+  if (count == 0) return DB200_OK;
+  int64_t blocks = ceil_div64(count, 256 * 4 * 4);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  if (blocks < 1) blocks = 1;
+  sumsq_kernel<<<(int)blocks, 256, 0, st>>>(x, count, out);
+  DB200_LAUNCH_OK("sumsq_kernel");
+  return DB200_OK;
+}
+int adam_launch(const db200_adam_params& P, cudaStream_t st) {
+  if (P.count == 0) return DB200_OK;
+  const double bc1 = 1.0 - pow((double)P.beta1, (double)P.step), bc2 = 1.0 - pow((double)P.beta2, (double)P.step);
+  int64_t blocks = ceil_div64(P.count, 256 * 4 * 2);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  if (blocks < 1) blocks = 1;
+  adam_kernel<<<(int)blocks, 256, 0, st>>>(P, (float)(P.lr / bc1), (float)(1.0 / sqrt(bc2)));
+  DB200_LAUNCH_OK("adam_kernel");
+  return DB200_OK;
+}
 
 int embed_launch(bool bwd, const long long* ids, const float* a, float* o, int batch, int seg_len, int n, int seg_off, int d, int vocab,
                  cudaStream_t st) {

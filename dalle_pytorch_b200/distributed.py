@@ -122,7 +122,8 @@ class GradAllReducer:
 
     def __init__(self, params, process_group=None, bucket_bytes=64 << 20, average=True):
         self.pg = process_group
-        self.world = dist.get_world_size(process_group)
+        # without an initialised process group this is just the flat gradient buffer of a single process (optim.FusedAdam)
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.average = average
         self.params = [p for p in params if p.requires_grad]
         assert self.params, 'no trainable parameters'
@@ -130,15 +131,20 @@ class GradAllReducer:
         # reverse order: the last layers' gradients are final first
         order = list(reversed(self.params))
         sizes = [p.numel() for p in order]
-        total = sum(sizes)
+        # every view starts on a 256-byte boundary: the kernels that read or write parameters and gradients (TMA operands,
+        # 16-byte vector loads of gamma / bias / embedding rows, the weight-gradient GEMM writing into its slot) need aligned
+        # pointers, and odd-sized tensors (a bias of 90 elements) would otherwise misalign everything behind them
+        ALIGN = 64
+        padded = [(n + ALIGN - 1) // ALIGN * ALIGN for n in sizes]
+        total = sum(padded)
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.views, self.bucket_of, self.buckets = {}, {}, []
         off, b_start, b_params = 0, 0, []
         limit = max(1, bucket_bytes // 4)
-        for p, n in zip(order, sizes):
+        for p, n, n_pad in zip(order, sizes, padded):
             self.views[p] = self.flat[off:off + n].view_as(p)
             b_params.append(p)
-            off += n
+            off += n_pad
             if off - b_start >= limit:
                 self.buckets.append((b_start, off, b_params))
                 b_start, b_params = off, []
@@ -147,7 +153,7 @@ class GradAllReducer:
         for bi, (_, _, ps) in enumerate(self.buckets):
             for p in ps:
                 self.bucket_of[p] = bi
-        self._has_avg = dist.get_backend(process_group) == 'nccl'
+        self._has_avg = dist.is_initialized() and dist.get_backend(process_group) == 'nccl'
         self._seen = set()
         self._pending = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)

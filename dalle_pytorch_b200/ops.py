@@ -355,6 +355,22 @@ def embed_bwd(ids, d_out, dweight, seg_off):
     _count()
 
 
+def sumsq_(x, out):
+    """out (fp32 device scalar) += sum(x^2) over a flat fp32 tensor"""
+    _lib.check(_lib.lib().dalle_b200_sumsq(_p(_c(x)), x.numel(), _p(out), _stream()), 'sumsq')
+    _count()
+
+
+def adam_(p, g, m, v, step, lr, beta1, beta2, eps, weight_decay=0.0, max_norm=0.0, gnorm_sq=None):
+    """In-place Adam update of the flat fp32 buffers p, m, v from g (see include/dalle_b200.h::dalle_b200_adam)."""
+    for t in (p, g, m, v):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
+    P = _lib.AdamParams(p=_p(p), g=_p(g), m=_p(m), v=_p(v), count=p.numel(), lr=lr, beta1=beta1, beta2=beta2, eps=eps,
+                        weight_decay=weight_decay, step=step, max_norm=max_norm, gnorm_sq=_p(gnorm_sq))
+    _lib.check(_lib.lib().dalle_b200_adam(ctypes.byref(P), _stream()), 'adam')
+    _count()
+
+
 def axpby(a, b, alpha):
     """a + alpha * b over fp32 tensors of equal shape"""
     _c(a), _c(b)

@@ -231,6 +231,24 @@ int dalle_b200_embed_fwd(const int64_t* ids, const float* weight, float* out, in
 int dalle_b200_embed_bwd(const int64_t* ids, const float* d_out, float* dweight, int batch, int seg_len, int n, int seg_off, int d, int vocab,
                          void* stream);
 
+/* Optimizer step of the reference trainer (train_dalle.py:617-619: clip_grad_norm_(params, 0.5); Adam.step()) over FLAT fp32
+ * buffers, two launches for the whole model:
+ *   dalle_b200_sumsq   : *out += sum(x[i]^2)                      (out: fp32 device scalar, caller zeroes it)
+ *   dalle_b200_adam    : coef = max_norm > 0 ? min(1, max_norm / (sqrt(*gnorm_sq) + 1e-6)) : 1     (clip_grad_norm_)
+ *                        g = coef * grad (+ weight_decay * p);  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *                        p -= (lr / (1 - b1^step)) * m / (sqrt(v) / sqrt(1 - b2^step) + eps)        (torch.optim.Adam)
+ * The clip coefficient is read on the device, so the step needs no host synchronisation. */
+int dalle_b200_sumsq(const float* x, int64_t count, float* out, void* stream);
+typedef struct {
+  float* p; const float* g; float* m; float* v;      /* [count] fp32 each */
+  int64_t count;
+  float lr, beta1, beta2, eps, weight_decay;
+  int step;                                          /* 1-based */
+  float max_norm;                                    /* <= 0: no clipping */
+  const float* gnorm_sq;                             /* device scalar from dalle_b200_sumsq (may be NULL when max_norm <= 0) */
+} db200_adam_params;
+int dalle_b200_adam(const db200_adam_params* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -320,3 +320,56 @@ def test_token_embedding_gather_and_scatter():
     # text only (generation prefix)
     out2 = EmbedTokensFn.apply(text, None, wt, wi)
     assert torch.equal(out2, torch.nn.functional.embedding(text, wt))
+
+
+@pytest.mark.gpu
+def test_fused_adam_matches_torch_adam_with_clipping():
+    """dalle_b200_sumsq + dalle_b200_adam over flat buffers vs clip_grad_norm_ + torch.optim.Adam (train_dalle.py:617-619),
+    three steps, with and without weight decay / clipping; sizes that are not multiples of 4 exercise the tails."""
+    from dalle_pytorch_b200 import ops
+    for n, max_norm, wd in ((1003, 0.5, 0.0), (4096 * 33 + 1, 0.0, 0.01), (7, 2.0, 0.0)):
+        torch.manual_seed(n)
+        p0 = torch.randn(n, device='cuda')
+        ref = torch.nn.Parameter(p0.clone())
+        opt = torch.optim.Adam([ref], lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+        p, m, v = p0.clone(), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+        gn = torch.zeros(1, device='cuda')
+        for step in range(1, 4):
+            g = torch.randn(n, device='cuda') * (3.0 if step == 2 else 0.01)      # one step clips hard, the others do not
+            ref.grad = g.clone()
+            if max_norm > 0:
+                torch.nn.utils.clip_grad_norm_([ref], max_norm)
+            opt.step()
+            gn.zero_()
+            ops.sumsq_(g, gn)
+            report(f'sumsq n={n} step {step}', gn, (g.double() ** 2).sum().float().reshape(1), 1e-5, 1e-6)
+            ops.adam_(p, g, m, v, step, 3e-4, 0.9, 0.999, 1e-8, wd, max_norm, gn if max_norm > 0 else None)
+            report(f'adam n={n} step {step}', p, ref.detach(), 1e-5, 1e-6)
+
+
+@pytest.mark.gpu
+def test_fused_adam_trains_the_model_like_torch_adam():
+    """FusedAdam (flat parameters + flat gradients, weight-gradient GEMMs writing straight into the flat buffer) against
+    clip_grad_norm_ + torch.optim.Adam on the same tiny DALLE for three steps."""
+    import copy
+    import dalle_pytorch_b200 as D
+    torch.manual_seed(5)
+    kw = dict(dim=64, num_text_tokens=50, text_seq_len=8, depth=2, heads=2, dim_head=64, attn_types=('full', 'axial_row'))
+    a = D.DALLE(vae=D.TokenVAE(image_size=32, num_layers=3, num_tokens=32), **kw).cuda().train()
+    b = copy.deepcopy(a)
+    text = torch.randint(1, 50, (2, 8)).cuda()
+    image = torch.randint(0, 32, (2, 16)).cuda()
+    opt_a = torch.optim.Adam(a.parameters(), lr=3e-4)
+    opt_b = D.FusedAdam(b.parameters(), lr=3e-4, max_grad_norm=0.5)
+    for _ in range(3):
+        opt_a.zero_grad(set_to_none=True)
+        la = a(text, image, return_loss=True)
+        la.backward()
+        torch.nn.utils.clip_grad_norm_(a.parameters(), 0.5)
+        opt_a.step()
+        lb = b(text, image, return_loss=True)
+        lb.backward()
+        opt_b.step()
+        report('loss', lb.detach(), la.detach(), 1e-4, 1e-5)
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        report(f'param {k}', pb.detach(), pa.detach(), 1e-3, 2e-5)
