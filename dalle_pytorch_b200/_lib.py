@@ -32,7 +32,9 @@ class LnShiftBwdParams(ctypes.Structure):
     _fields_ = [('batch', c_int), ('n', c_int), ('d', c_int), ('text_len', c_int), ('fmap', c_int),
                 ('do_ln', c_int), ('do_shift', c_int), ('dout_dtype', c_int),
                 ('d_out', c_void_p), ('x', c_void_p), ('mean', c_void_p), ('rstd', c_void_p), ('gamma', c_void_p),
-                ('dres', c_void_p), ('dx', c_void_p), ('dgamma', c_void_p), ('dbeta', c_void_p)]
+                ('dres', c_void_p), ('dx', c_void_p), ('dgamma', c_void_p), ('dbeta', c_void_p),
+                ('up_y', c_void_p), ('up_scale', c_void_p), ('up_sign', c_float), ('up_dy', c_void_p), ('up_dscale', c_void_p),
+                ('up_dbias', c_void_p)]
 
 
 class GemmParams(ctypes.Structure):

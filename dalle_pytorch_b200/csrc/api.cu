@@ -125,6 +125,12 @@ int dalle_b200_ln_shift_bwd(const db200_ln_shift_bwd_params* p, void* stream) {
   DB200_CHECK_ARG(p->d_out && p->dx, "ln_shift_bwd: null tensor");
   if (p->do_ln) DB200_CHECK_ARG(p->x && p->mean && p->rstd && p->gamma && p->dgamma && p->dbeta, "ln_shift_bwd: LayerNorm needs x/mean/rstd/gamma/dgamma/dbeta");
   if (p->do_shift) DB200_CHECK_ARG(p->fmap > 0 && p->n >= p->text_len && p->n <= p->text_len + p->fmap * p->fmap, "ln_shift_bwd: bad shift geometry");
+  if (p->up_dy) {
+    DB200_CHECK_ARG(p->d == 1024, "ln_shift_bwd: the fused upstream LayerScale adjoint needs d = 1024 (got %d)", p->d);
+    DB200_CHECK_ARG(aligned16(p->up_dy) && aligned16(p->up_y) && aligned16(p->d_out) && aligned16(p->x) && aligned16(p->dres),
+                    "ln_shift_bwd: fused path needs 16-byte aligned tensors");
+    DB200_CHECK_ARG(p->up_dscale == nullptr || p->up_y != nullptr, "ln_shift_bwd: up_dscale needs up_y");
+  }
   return ln_shift_bwd_launch(*p, (cudaStream_t)stream);
 }
 

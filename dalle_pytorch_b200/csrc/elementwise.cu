@@ -375,8 +375,9 @@ constexpr int LT_D = LT_NW * 128;
 template <typename TI>
 struct LnTmaSmem {
   static constexpr int G_ROW = LT_D * (int)sizeof(TI), X_ROW = LT_D * 4;
-  static constexpr int STAGE = LT_R * (G_ROW + 2 * X_ROW);                  // dA | x | dres
-  static constexpr int STAGES = (sizeof(TI) == 2) ? 4 : 3;                  // 160 KB (bf16) / 144 KB (fp32)
+  static constexpr int Y_OFF = LT_R * (G_ROW + 2 * X_ROW);                  // upstream branch output rows (fused LayerScale adjoint)
+  static constexpr int STAGE = LT_R * (2 * G_ROW + 2 * X_ROW);              // dA | x | dres | up_y
+  static constexpr int STAGES = (sizeof(TI) == 2) ? 4 : 3;                  // 192 KB either way
   static constexpr int FLAG_OFF = STAGES * STAGE;                           // [STAGES][R][4] ints: q1 present, q2 present, row valid, pad
   static constexpr int PART_OFF = FLAG_OFF + STAGES * LT_R * 16;            // [GROUPS][2][2R][8] floats
   static constexpr int BAR_OFF = PART_OFF + LT_GROUPS * 2 * 2 * LT_R * LT_NW * 4;   // full[STAGES], empty[STAGES]
@@ -403,14 +404,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1) ln_shift_bwd_tma_kernel(db200_l
 
   if (warp == LT_GROUPS * LT_NW) {
     // ======================================= producer =======================================
-    // One lane per (row, copy): lane = 5*i + j handles copy j of row i (j: 0 dA quarter 1, 1 dA quarter 2, 2 dA upper half,
-    // 3 x, 4 dres).  A single issuing thread needs ~2-3 k cycles of dependent integer work per batch (divisions of the shift
+    // One lane per (row, copy): lane = 6*i + j handles copy j of row i (j: 0 dA quarter 1, 1 dA quarter 2, 2 dA upper half,
+    // 3 x, 4 dres, 5 upstream y).  A single issuing thread needs ~2-3 k cycles of dependent integer work per batch (divisions of the shift
     // geometry, 20 address computations) and was the bottleneck of the whole kernel; spread over 20 lanes it is ~10x shorter.
     // The transaction bytes are summed across the warp and posted by lane 0 (copies that complete before the expect_tx only
     // drive the tx-count negative for a moment; the phase cannot complete before lane 0's arrival).
     const TI* __restrict__ dA = reinterpret_cast<const TI*>(P.d_out);
-    const int i = lane / 5, j = lane - i * 5;
-    const bool active = lane < 5 * R;
+    const int i = lane / 6, j = lane - i * 6;
+    const bool active = lane < 6 * R;
+    const bool has_up = P.up_dy != nullptr && P.up_y != nullptr;
     int s = 0; uint32_t ph = 0;
     for (int r0 = blockIdx.x * R; r0 < rows; r0 += step) {
       mbar_wait(empty_bar + 8 * s, ph ^ 1);
@@ -433,8 +435,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) ln_shift_bwd_tma_kernel(db200_l
           bytes = L::G_ROW / 2; bulk_load_1d(gdst + L::G_ROW / 2, dA + (brow + p) * d + d / 2, bytes, fb);
         } else if (j == 3) {
           if (ln) { bytes = L::X_ROW; bulk_load_1d(smem_u32(st + R * L::G_ROW + i * L::X_ROW), P.x + (long long)r * d, bytes, fb); }
-        } else {
+        } else if (j == 4) {
           if (has_res) { bytes = L::X_ROW; bulk_load_1d(smem_u32(st + R * (L::G_ROW + L::X_ROW) + i * L::X_ROW), P.dres + (long long)r * d, bytes, fb); }
+        } else {
+          if (has_up) { bytes = L::G_ROW; bulk_load_1d(smem_u32(st + L::Y_OFF + i * L::G_ROW), reinterpret_cast<const TI*>(P.up_y) + (long long)r * d, bytes, fb); }
         }
       } else if (active && j == 0) {
         flags[(s * R + i) * 4 + 2] = 0;                      // row past the end
@@ -457,6 +461,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1) ln_shift_bwd_tma_kernel(db200_l
   const float4 ga = ln ? __ldg(reinterpret_cast<const float4*>(P.gamma + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
   const int qsel = c >= (d >> 1) ? 2 : (c < (d >> 2) ? 0 : 1);      // flag index of this warp's channels (2 = always present)
+  // fused upstream LayerScale adjoint (see db200_ln_shift_bwd_params::up_*)
+  const bool up = P.up_dy != nullptr;
+  const bool up_has_y = up && P.up_y != nullptr;
+  float4 usc = make_float4(P.up_sign, P.up_sign, P.up_sign, P.up_sign);
+  if (up && P.up_scale) { const float4 t = __ldg(reinterpret_cast<const float4*>(P.up_scale + c)); usc.x *= t.x; usc.y *= t.y; usc.z *= t.z; usc.w *= t.w; }
+  float4 uds = make_float4(0.f, 0.f, 0.f, 0.f), udb = make_float4(0.f, 0.f, 0.f, 0.f);
+  TI* __restrict__ up_dy = reinterpret_cast<TI*>(P.up_dy);
   int buf = 0;
   for (int k = grp; ; k += LT_GROUPS, buf ^= 1) {
     const int r0 = (blockIdx.x + k * (int)gridDim.x) * R;
@@ -486,6 +497,16 @@ __global__ void __launch_bounds__(LT_THREADS, 1) ln_shift_bwd_tma_kernel(db200_l
       }
       if (valid && ln) h[i] = *reinterpret_cast<const float4*>(st + R * L::G_ROW + i * L::X_ROW + c * 4);
       if (valid && has_res) e[i] = *reinterpret_cast<const float4*>(st + R * (L::G_ROW + L::X_ROW) + i * L::X_ROW + c * 4);
+    }
+    float4 uy[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      uy[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (up_has_y && fl[i * 4 + 2] != 0) {
+        const TI* yp = reinterpret_cast<const TI*>(st + L::Y_OFF + i * L::G_ROW) + c;
+        const float2 a = load2<TI>(yp), bq = load2<TI>(yp + 2);
+        uy[i] = make_float4(a.x, a.y, bq.x, bq.y);
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar + 8 * s);       // stage consumed into registers
@@ -530,9 +551,26 @@ __global__ void __launch_bounds__(LT_THREADS, 1) ln_shift_bwd_tma_kernel(db200_l
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       const int r = r0 + i;
-      if (r < rows)
-        *reinterpret_cast<float4*>(P.dx + (long long)r * d + c) = make_float4(g[i].x + e[i].x, g[i].y + e[i].y, g[i].z + e[i].z, g[i].w + e[i].w);
+      if (r < rows) {
+        const float4 o = make_float4(g[i].x + e[i].x, g[i].y + e[i].y, g[i].z + e[i].z, g[i].w + e[i].w);
+        *reinterpret_cast<float4*>(P.dx + (long long)r * d + c) = o;
+        if (up) {
+          const float4 dy = make_float4(usc.x * o.x, usc.y * o.y, usc.z * o.z, usc.w * o.w);
+          TI* dst = up_dy + (long long)r * d + c;
+          store2<TI>(dst, dy.x, dy.y);
+          store2<TI>(dst + 2, dy.z, dy.w);
+          udb.x += dy.x; udb.y += dy.y; udb.z += dy.z; udb.w += dy.w;
+          uds.x += P.up_sign * o.x * uy[i].x; uds.y += P.up_sign * o.y * uy[i].y;
+          uds.z += P.up_sign * o.z * uy[i].z; uds.w += P.up_sign * o.w * uy[i].w;
+        }
+      }
     }
+  }
+  if (up && P.up_dbias) {
+    atomicAdd(P.up_dbias + c, udb.x); atomicAdd(P.up_dbias + c + 1, udb.y); atomicAdd(P.up_dbias + c + 2, udb.z); atomicAdd(P.up_dbias + c + 3, udb.w);
+  }
+  if (up && P.up_dscale) {
+    atomicAdd(P.up_dscale + c, uds.x); atomicAdd(P.up_dscale + c + 1, uds.y); atomicAdd(P.up_dscale + c + 2, uds.z); atomicAdd(P.up_dscale + c + 3, uds.w);
   }
   if (want_p) {
     atomicAdd(P.dgamma + c, ag.x); atomicAdd(P.dgamma + c + 1, ag.y); atomicAdd(P.dgamma + c + 2, ag.z); atomicAdd(P.dgamma + c + 3, ag.w);
@@ -984,7 +1022,8 @@ int ln_shift_bwd_launch(const db200_ln_shift_bwd_params& P, cudaStream_t st) {
   if (rows == 0) return DB200_OK;
   const bool al16 = ((reinterpret_cast<uintptr_t>(P.d_out) | reinterpret_cast<uintptr_t>(P.x) | reinterpret_cast<uintptr_t>(P.dres)) & 15) == 0;
   static const bool no_tma = [] { const char* v = getenv("DALLE_B200_LN_BWD"); return v && !strcmp(v, "regs"); }();
-  if (P.d == 1024 && al16 && !no_tma) {
+  if (P.up_dy && !(P.d == 1024 && al16)) return set_error(DB200_ERR_UNSUPPORTED, "ln_shift_bwd: fused upstream adjoint needs d = 1024 and aligned tensors");
+  if (P.d == 1024 && al16 && (!no_tma || P.up_dy)) {
     const int want = ceil_div(rows, LT_R);
     const int grid = want < sm_count() ? want : sm_count();
     if (P.dout_dtype == DB200_F32) {

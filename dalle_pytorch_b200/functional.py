@@ -20,12 +20,47 @@ feed-forward sub-layer:
   bwd  scale_bwd -> gemm dgrad(net.3)[GEGLU_BWD] , gemm wgrad(net.3) -> colsum (b1) -> gemm dgrad(net.0), gemm wgrad(net.0)
        -> ln_shift_bwd
 """
+import os
+import threading
+
 import torch
 
 from . import ops
 
 
 FUSE_GEGLU_BWD = False      # True: dgrad(net.3) with the GEGLU adjoint fused in its epilogue (EPI_GEGLU_BWD)
+# True: the LayerNorm/shift backward kernel of sub-layer k also forms the LayerScale adjoint of sub-layer k-1 (whose output is
+# this sub-layer's input) while dx is in registers, instead of a separate scale_bwd pass that re-reads dx (d = 1024 only).
+FUSE_UPSTREAM_SCALE_BWD = os.environ.get('DALLE_B200_FUSE_SCALE_BWD', '1') != '0'
+
+
+class _SubRec:
+    """What sub-layer k must know about sub-layer k-1 to run its LayerScale adjoint, plus the slot the results come back in."""
+    __slots__ = ('y', 'scale', 'sign', 'out_ptr', 'pre', 'pre_ptr')
+
+    def __init__(self, y, scale, sign, out):
+        self.y, self.scale, self.sign, self.out_ptr = y, scale, sign, out.data_ptr()
+        self.pre, self.pre_ptr = None, None
+
+
+_chain = threading.local()
+
+
+def chain_reset():
+    """Called at the start of every executor forward: a record must never match a tensor of an earlier pass whose address the
+    caching allocator has recycled."""
+    _chain.last = None
+
+
+def _chain_link(x_in, resid_is_input, rec):
+    """Returns the record of the sub-layer that produced `x_in` (if it is the immediately preceding fused sub-layer and x_in is
+    also the residual, i.e. the sequential executor) and makes `rec` the new tail."""
+    prev = getattr(_chain, 'last', None)
+    _chain.last = rec
+    if (FUSE_UPSTREAM_SCALE_BWD and prev is not None and resid_is_input and prev.out_ptr == x_in.data_ptr() and x_in.shape[-1] == 1024
+            and x_in.is_cuda):
+        return prev
+    return None
 
 
 class SublayerGeom:
@@ -54,6 +89,24 @@ def _w(weight, dtype):
     return ops.cast_bf16(weight.contiguous())
 
 
+def _up_args(up, da):
+    """(up_y, up_scale, up_sign) for ops.ln_shift_bwd, or None when the upstream record cannot be fused with this call."""
+    if up is None:
+        return None
+    if up.y is not None and up.y.dtype != da.dtype:
+        return None
+    return (up.y, up.scale, up.sign)
+
+
+def _up_store(up, res):
+    """Files the fused results in the upstream sub-layer's record; returns dx."""
+    if not isinstance(res, tuple):
+        return res
+    dx, up_dy, up_dscale, up_dbias = res
+    up.pre, up.pre_ptr = (up_dy, up_dscale, up_dbias), dx.data_ptr()
+    return dx
+
+
 # =====================================================================================================
 # attention sub-layer
 # =====================================================================================================
@@ -76,7 +129,8 @@ def attn_sublayer_forward(g: SublayerGeom, x_in, resid, ln_w, ln_b, w_qkv, w_out
     return out, ctx
 
 
-def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t, sin_t, key_mask=None, dres=None, wslots=None):
+def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t, sin_t, key_mask=None, dres=None, wslots=None,
+                           pre=None, up=None):
     """d_out: gradient w.r.t. `out` [b,n,d] fp32.  Returns (dx_in, dln_w, dln_b, dw_qkv, dw_out, db_out, dscale).
     `dres` (optional, fp32) is added to dx_in inside the LayerNorm-backward kernel (sequential executor: the residual
     branch gradient, which equals d_out).  `wslots` (optional) = (dw_qkv_out, dw_out_out): preallocated fp32 destinations
@@ -88,7 +142,10 @@ def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t
     d_out = d_out.contiguous().view(M, d)
     sc = None if scale is None else scale.detach().reshape(-1).contiguous()
     pool = torch.zeros(4, d, device=x_in.device, dtype=torch.float32)     # one fill for dscale, db_out, dln_w, dln_b
-    dy, dscale, db_out = ops.scale_bwd(d_out, y, sc, sign, g.dtype, zeroed=(pool[0], pool[1]))
+    if pre is not None:      # already formed by the downstream sub-layer's LayerNorm backward (FUSE_UPSTREAM_SCALE_BWD)
+        dy, dscale, db_out = pre
+    else:
+        dy, dscale, db_out = ops.scale_bwd(d_out, y, sc, sign, g.dtype, zeroed=(pool[0], pool[1]))
     d_o = ops.gemm_store(dy, wo, a_mn=False, b_mn=True)                                   # [M, inner]
     dw_out = ops.gemm_store(dy, o.view(M, -1), a_mn=True, b_mn=True, out_dtype=torch.float32, out=s_out)   # [d, inner]
     dqkv = ops.attn_bwd(g.attn_spec, q, k, v, o, lse, d_o.view(b, n, -1), cos_t, sin_t, g.q_scale, key_mask)
@@ -98,7 +155,9 @@ def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t
     if g.do_ln:
         dln_w, dln_b = pool[2], pool[3]
     dx = ops.ln_shift_bwd(da1, x_in, mean, rstd, ln_w, None if dres is None else dres.contiguous(), g.text_len, g.fmap,
-                          do_ln=g.do_ln, do_shift=shift, dgamma=dln_w, dbeta=dln_b)
+                          do_ln=g.do_ln, do_shift=shift, dgamma=dln_w, dbeta=dln_b, up=_up_args(up, da1))
+    if up is not None:
+        dx = _up_store(up, dx)
     if dscale is not None:
         dscale = dscale.view_as(scale)
     return dx, dln_w, dln_b, dw_qkv, dw_out, db_out, dscale
@@ -124,7 +183,7 @@ def ff_sublayer_forward(g: SublayerGeom, x_in, resid, ln_w, ln_b, w1, b1, w2, b2
     return out, ctx
 
 
-def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=None, wslots=None):
+def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=None, wslots=None, pre=None, up=None):
     """Returns (dx_in, dln_w, dln_b, dw1, db1, dw2, db2, dscale).  `wslots` = (dw1_out, dw2_out), see attn_sublayer_backward."""
     x_in, mean, rstd, a2, w1c, w2c, u, h, y, shift = ctx
     s_w1, s_w2 = wslots if wslots is not None else (None, None)
@@ -134,7 +193,10 @@ def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=No
     sc = None if scale is None else scale.detach().reshape(-1).contiguous()
     H2 = u.shape[1]
     pool = torch.zeros(4 * d + H2, device=x_in.device, dtype=torch.float32)   # one fill for dscale, db2, dln_w, dln_b, db1
-    dy, dscale, db2 = ops.scale_bwd(d_out, y, sc, sign, g.dtype, zeroed=(pool[:d], pool[d:2 * d]))
+    if pre is not None:
+        dy, dscale, db2 = pre
+    else:
+        dy, dscale, db2 = ops.scale_bwd(d_out, y, sc, sign, g.dtype, zeroed=(pool[:d], pool[d:2 * d]))
     if FUSE_GEGLU_BWD:
         du = ops.gemm_geglu_bwd(dy, w2c, u)                                               # [M, 2H]
         db1 = ops.colsum(du)
@@ -148,7 +210,9 @@ def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=No
     if g.do_ln:
         dln_w, dln_b = pool[2 * d:3 * d], pool[3 * d:4 * d]
     dx = ops.ln_shift_bwd(da2, x_in, mean, rstd, ln_w, None if dres is None else dres.contiguous(), g.text_len, g.fmap,
-                          do_ln=g.do_ln, do_shift=shift, dgamma=dln_w, dbeta=dln_b)
+                          do_ln=g.do_ln, do_shift=shift, dgamma=dln_w, dbeta=dln_b, up=_up_args(up, da2))
+    if up is not None:
+        dx = _up_store(up, dx)
     if dscale is not None:
         dscale = dscale.view_as(scale)
     return dx, dln_w, dln_b, dw1, db1, dw2, db2, dscale
@@ -198,6 +262,11 @@ class AttnSublayerFn(torch.autograd.Function):
         ctx.has_resid = resid is not None
         ctx.wparams = (w_qkv, w_out)
         _note_use(w_qkv, w_out)
+        ctx.rec = ctx.up = None
+        if any(ctx.needs_input_grad) and saved is not None:
+            y = saved[11]
+            ctx.rec = _SubRec(y, None if scale is None else scale.detach().reshape(-1).contiguous(), sign, out)
+            ctx.up = _chain_link(x_in, resid_is_input, ctx.rec)
         return out
 
     @staticmethod
@@ -206,8 +275,12 @@ class AttnSublayerFn(torch.autograd.Function):
         d_out = d_out.contiguous()
         dres = d_out if ctx.resid_is_input else None
         slots = tuple(_slot(p) for p in ctx.wparams)
+        rec = ctx.rec
+        pre = rec.pre if (rec is not None and rec.pre is not None and rec.pre_ptr == d_out.data_ptr()) else None
         dx, dln_w, dln_b, dw_qkv, dw_out, db_out, dscale = attn_sublayer_backward(
-            g, ctx.saved, d_out, ctx.ln_w, ctx.scale, ctx.sign, ctx.cos_t, ctx.sin_t, ctx.key_mask, dres=dres, wslots=slots)
+            g, ctx.saved, d_out, ctx.ln_w, ctx.scale, ctx.sign, ctx.cos_t, ctx.sin_t, ctx.key_mask, dres=dres, wslots=slots,
+            pre=pre, up=ctx.up)
+        ctx.rec = ctx.up = None
         dw_qkv = _commit(ctx.wparams[0], slots[0], dw_qkv)
         dw_out = _commit(ctx.wparams[1], slots[1], dw_out)
         ctx.saved = None
@@ -226,6 +299,11 @@ class FFSublayerFn(torch.autograd.Function):
         ctx.has_resid = resid is not None
         ctx.wparams = (w1, w2)
         _note_use(w1, w2)
+        ctx.rec = ctx.up = None
+        if any(ctx.needs_input_grad) and saved is not None:
+            y = saved[8]
+            ctx.rec = _SubRec(y, None if scale is None else scale.detach().reshape(-1).contiguous(), sign, out)
+            ctx.up = _chain_link(x_in, resid_is_input, ctx.rec)
         return out
 
     @staticmethod
@@ -233,8 +311,11 @@ class FFSublayerFn(torch.autograd.Function):
         d_out = d_out.contiguous()
         dres = d_out if ctx.resid_is_input else None
         slots = tuple(_slot(p) for p in ctx.wparams)
+        rec = ctx.rec
+        pre = rec.pre if (rec is not None and rec.pre is not None and rec.pre_ptr == d_out.data_ptr()) else None
         dx, dln_w, dln_b, dw1, db1, dw2, db2, dscale = ff_sublayer_backward(ctx.g, ctx.saved, d_out, ctx.ln_w, ctx.scale, ctx.sign,
-                                                                              dres=dres, wslots=slots)
+                                                                              dres=dres, wslots=slots, pre=pre, up=ctx.up)
+        ctx.rec = ctx.up = None
         dw1 = _commit(ctx.wparams[0], slots[0], dw1)
         dw2 = _commit(ctx.wparams[1], slots[1], dw2)
         ctx.saved = None

@@ -62,16 +62,28 @@ def ln_shift_fwd(x, gamma, beta, out_dtype, text_len, fmap, do_ln=True, do_shift
     return out, mean, rstd
 
 
-def ln_shift_bwd(d_out, x, mean, rstd, gamma, dres, text_len, fmap, do_ln=True, do_shift=True, dgamma=None, dbeta=None):
-    """-> dx [b,n,d] fp32 ; dgamma/dbeta accumulated in place (must be zero-initialised by the caller)"""
+def ln_shift_bwd(d_out, x, mean, rstd, gamma, dres, text_len, fmap, do_ln=True, do_shift=True, dgamma=None, dbeta=None, up=None):
+    """-> dx [b,n,d] fp32 ; dgamma/dbeta accumulated in place (must be zero-initialised by the caller).
+    `up` = (up_y | None, up_scale | None, up_sign): also form the upstream sub-layer's LayerScale adjoint from dx in the same pass
+    (d = 1024 only) and return (dx, up_dy, up_dscale, up_dbias)."""
     b, n, d = x.shape
     dx = torch.empty_like(x)
     P = _lib.LnShiftBwdParams(batch=b, n=n, d=d, text_len=text_len, fmap=fmap, do_ln=int(do_ln), do_shift=int(do_shift),
                               dout_dtype=dt_code(d_out.dtype), d_out=_p(_c(d_out)), x=_p(_c(x)), mean=_p(mean), rstd=_p(rstd),
                               gamma=_p(gamma), dres=_p(dres), dx=_p(dx), dgamma=_p(dgamma), dbeta=_p(dbeta))
+    res = None
+    if up is not None:
+        up_y, up_scale, up_sign = up
+        assert d == 1024 and (up_y is None or (up_y.dtype == d_out.dtype and up_y.is_contiguous()))
+        up_dy = torch.empty(b * n, d, device=x.device, dtype=d_out.dtype)
+        acc = torch.zeros(2, d, device=x.device, dtype=torch.float32)
+        want_scale = up_scale is not None and up_y is not None
+        P.up_y, P.up_scale, P.up_sign, P.up_dy = _p(up_y), _p(up_scale), up_sign, _p(up_dy)
+        P.up_dscale, P.up_dbias = (_p(acc[0]) if want_scale else None), _p(acc[1])
+        res = (up_dy, acc[0] if want_scale else None, acc[1])
     _lib.check(_lib.lib().dalle_b200_ln_shift_bwd(ctypes.byref(P), _stream()), 'ln_shift_bwd')
     _count()
-    return dx
+    return dx if res is None else (dx,) + res
 
 
 _gemm_events = None      # list of (start, end, flops, backend, shape-key) while gemm_timing is on

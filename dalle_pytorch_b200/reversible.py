@@ -11,7 +11,8 @@ import torch
 from torch import nn
 
 from . import ops
-from .functional import (attn_sublayer_forward, attn_sublayer_backward, ff_sublayer_forward, ff_sublayer_backward, _note_use)
+from .functional import (attn_sublayer_forward, attn_sublayer_backward, ff_sublayer_forward, ff_sublayer_backward, _note_use,
+                         chain_reset)
 
 
 def route_args(router, args, depth):
@@ -37,6 +38,7 @@ class SequentialSequence(nn.Module):
 
     def forward(self, x, **kwargs):
         args = route_args(self.args_route, kwargs, len(self.layers))
+        chain_reset()
         for (f, g), (f_args, g_args) in zip(self.layers, args):
             x = f.residual(x, **f_args)      # x + f(x): one fused sub-layer when possible
             x = g.residual(x, **g_args)

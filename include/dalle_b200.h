@@ -103,6 +103,15 @@ typedef struct {
   float* dx;                /* [rows, d] fp32 */
   float* dgamma;            /* [d] fp32, += */
   float* dbeta;             /* [d] fp32, += */
+  /* Optional fusion of the UPSTREAM sub-layer's LayerScale adjoint (what dalle_b200_scale_bwd would compute from this dx, which
+   * is that sub-layer's output gradient) while dx is still in registers; saves re-reading dx.  d = 1024 only; up_dy == NULL = off.
+   *   up_dy = up_sign * up_scale (.) dx  (dout_dtype);  up_dscale += up_sign * sum_rows dx (.) up_y;  up_dbias += sum_rows up_dy */
+  const void* up_y;         /* [rows, d] (dout_dtype) upstream branch output, needed for up_dscale; may be NULL */
+  const float* up_scale;    /* [d] fp32 or NULL (= 1) */
+  float up_sign;
+  void* up_dy;              /* [rows, d] (dout_dtype) out */
+  float* up_dscale;         /* [d] fp32, += ; may be NULL */
+  float* up_dbias;          /* [d] fp32, += ; may be NULL */
 } db200_ln_shift_bwd_params;
 int dalle_b200_ln_shift_bwd(const db200_ln_shift_bwd_params* p, void* stream);
 

@@ -373,3 +373,32 @@ def test_fused_adam_trains_the_model_like_torch_adam():
         report('loss', lb.detach(), la.detach(), 1e-4, 1e-5)
     for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
         report(f'param {k}', pb.detach(), pa.detach(), 1e-3, 2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_ln_shift_bwd_fused_upstream_scale_adjoint(dtype):
+    """ln_shift_bwd with the upstream LayerScale adjoint fused (db200_ln_shift_bwd_params::up_*) against the two separate
+    launches it replaces (ln_shift_bwd then scale_bwd on its dx); rows not a multiple of the 4-row stage."""
+    from dalle_pytorch_b200 import ops
+    torch.manual_seed(11)
+    b, n, d, T, fm = 2, 37, 1024, 8, 6
+    x = torch.randn(b, n, d, device='cuda')
+    da = torch.randn(b, n, d, device='cuda').to(dtype)
+    dres = torch.randn(b, n, d, device='cuda')
+    gamma = torch.randn(d, device='cuda')
+    mean, rstd = x.mean(-1).reshape(-1).contiguous(), (x.var(-1, unbiased=False) + 1e-5).rsqrt().reshape(-1).contiguous()
+    y_up = torch.randn(b * n, d, device='cuda').to(dtype)
+    sc_up = torch.randn(d, device='cuda') * 0.1
+    dg0, db0 = torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda')
+    dx0 = ops.ln_shift_bwd(da, x, mean, rstd, gamma, dres, T, fm, do_ln=True, do_shift=True, dgamma=dg0, dbeta=db0)
+    dy0, dsc0, dbi0 = ops.scale_bwd(dx0.view(b * n, d), y_up, sc_up, -1.0, dtype)
+    dg1, db1 = torch.zeros(d, device='cuda'), torch.zeros(d, device='cuda')
+    dx1, dy1, dsc1, dbi1 = ops.ln_shift_bwd(da, x, mean, rstd, gamma, dres, T, fm, do_ln=True, do_shift=True, dgamma=dg1, dbeta=db1,
+                                            up=(y_up, sc_up, -1.0))
+    assert torch.equal(dx1, dx0)
+    assert torch.equal(dy1, dy0)
+    tol = 1e-4 if dtype == torch.float32 else 2e-3
+    report('fused dscale', dsc1, dsc0, tol, tol * float(dsc0.abs().max()))
+    report('fused dbias', dbi1, dbi0, tol, tol * float(dbi0.abs().max()))
+    report('dgamma', dg1, dg0, 1e-4, 1e-4 * float(dg0.abs().max()))
