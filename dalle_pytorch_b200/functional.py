@@ -141,7 +141,7 @@ def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t
     M = b * n
     d_out = d_out.contiguous().view(M, d)
     sc = None if scale is None else scale.detach().reshape(-1).contiguous()
-    pool = torch.zeros(4, d, device=x_in.device, dtype=torch.float32)     # one fill for dscale, db_out, dln_w, dln_b
+    pool = torch.zeros(6, d, device=x_in.device, dtype=torch.float32)     # one fill for dscale, db_out, dln_w, dln_b (+ upstream dscale, dbias)
     if pre is not None:      # already formed by the downstream sub-layer's LayerNorm backward (FUSE_UPSTREAM_SCALE_BWD)
         dy, dscale, db_out = pre
     else:
@@ -155,7 +155,7 @@ def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t
     if g.do_ln:
         dln_w, dln_b = pool[2], pool[3]
     dx = ops.ln_shift_bwd(da1, x_in, mean, rstd, ln_w, None if dres is None else dres.contiguous(), g.text_len, g.fmap,
-                          do_ln=g.do_ln, do_shift=shift, dgamma=dln_w, dbeta=dln_b, up=_up_args(up, da1))
+                          do_ln=g.do_ln, do_shift=shift, dgamma=dln_w, dbeta=dln_b, up=_up_args(up, da1), up_zeroed=pool[4:6])
     if up is not None:
         dx = _up_store(up, dx)
     if dscale is not None:
@@ -192,7 +192,7 @@ def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=No
     d_out = d_out.contiguous().view(M, d)
     sc = None if scale is None else scale.detach().reshape(-1).contiguous()
     H2 = u.shape[1]
-    pool = torch.zeros(4 * d + H2, device=x_in.device, dtype=torch.float32)   # one fill for dscale, db2, dln_w, dln_b, db1
+    pool = torch.zeros(6 * d + H2, device=x_in.device, dtype=torch.float32)   # one fill for dscale, db2, dln_w, dln_b, upstream dscale/dbias, db1
     if pre is not None:
         dy, dscale, db2 = pre
     else:
@@ -202,7 +202,7 @@ def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=No
         db1 = ops.colsum(du)
     else:   # measured faster on B200 (profiles/): plain dgrad GEMM + one streaming pass that also forms the bias gradient
         dh = ops.gemm_store(dy, w2c, a_mn=False, b_mn=True)                               # [M, H]
-        du, db1 = ops.geglu_bwd(dh, u, zeroed=pool[4 * d:])
+        du, db1 = ops.geglu_bwd(dh, u, zeroed=pool[6 * d:])
     dw2 = ops.gemm_store(dy, h, a_mn=True, b_mn=True, out_dtype=torch.float32, out=s_w2)            # [d, H]
     da2 = ops.gemm_store(du, w1c, a_mn=False, b_mn=True)                                  # [M, d]
     dw1 = ops.gemm_store(du, a2, a_mn=True, b_mn=True, out_dtype=torch.float32, out=s_w1)           # [2H, d]
@@ -210,7 +210,8 @@ def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=No
     if g.do_ln:
         dln_w, dln_b = pool[2 * d:3 * d], pool[3 * d:4 * d]
     dx = ops.ln_shift_bwd(da2, x_in, mean, rstd, ln_w, None if dres is None else dres.contiguous(), g.text_len, g.fmap,
-                          do_ln=g.do_ln, do_shift=shift, dgamma=dln_w, dbeta=dln_b, up=_up_args(up, da2))
+                          do_ln=g.do_ln, do_shift=shift, dgamma=dln_w, dbeta=dln_b, up=_up_args(up, da2),
+                          up_zeroed=pool[4 * d:6 * d].view(2, d))
     if up is not None:
         dx = _up_store(up, dx)
     if dscale is not None:

@@ -62,7 +62,8 @@ def ln_shift_fwd(x, gamma, beta, out_dtype, text_len, fmap, do_ln=True, do_shift
     return out, mean, rstd
 
 
-def ln_shift_bwd(d_out, x, mean, rstd, gamma, dres, text_len, fmap, do_ln=True, do_shift=True, dgamma=None, dbeta=None, up=None):
+def ln_shift_bwd(d_out, x, mean, rstd, gamma, dres, text_len, fmap, do_ln=True, do_shift=True, dgamma=None, dbeta=None, up=None,
+                 up_zeroed=None):
     """-> dx [b,n,d] fp32 ; dgamma/dbeta accumulated in place (must be zero-initialised by the caller).
     `up` = (up_y | None, up_scale | None, up_sign): also form the upstream sub-layer's LayerScale adjoint from dx in the same pass
     (d = 1024 only) and return (dx, up_dy, up_dscale, up_dbias)."""
@@ -76,7 +77,7 @@ def ln_shift_bwd(d_out, x, mean, rstd, gamma, dres, text_len, fmap, do_ln=True, 
         up_y, up_scale, up_sign = up
         assert d == 1024 and (up_y is None or (up_y.dtype == d_out.dtype and up_y.is_contiguous()))
         up_dy = torch.empty(b * n, d, device=x.device, dtype=d_out.dtype)
-        acc = torch.zeros(2, d, device=x.device, dtype=torch.float32)
+        acc = up_zeroed if up_zeroed is not None else torch.zeros(2, d, device=x.device, dtype=torch.float32)   # [2, d] fp32, pre-zeroed
         want_scale = up_scale is not None and up_y is not None
         P.up_y, P.up_scale, P.up_sign, P.up_dy = _p(up_y), _p(up_scale), up_sign, _p(up_dy)
         P.up_dscale, P.up_dbias = (_p(acc[0]) if want_scale else None), _p(acc[1])
