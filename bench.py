@@ -76,13 +76,29 @@ def workload_name(name, c):
 # clocks sampling (B200_PROFILING.md recipe)
 # ------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / power / throttle reasons DURING the timed region.  NVML (nvidia_ml_py) polled every 10 ms from a thread -- the
+    timed region of a default run is a few hundred ms, too short for `nvidia-smi -lms` to deliver a sample reliably (its start-up
+    alone can take longer on an 8-GPU box); nvidia-smi is the fallback when NVML cannot be loaded."""
     Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    REASONS = ((0x8, 'hw_slowdown'), (0x40, 'hw_thermal_slowdown'), (0x20, 'sw_thermal_slowdown'), (0x4, 'sw_power_cap'))
 
     def __init__(self, gpu_index=0):
         self.proc, self.lines, self.gpu_index = None, [], gpu_index
+        self.nvml, self.samples, self.stop_flag, self.t = None, [], False, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
                                           '-i', str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -91,11 +107,37 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1e3
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((float(sm), float(pw), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=2)
+            if not self.samples:
+                return {'sm_mhz': None, 'sm_max_mhz': float(self.max_sm), 'reasons': ['no samples']}
+            sm = sorted(x[0] for x in self.samples)
+            bits = 0
+            for x in self.samples:
+                bits |= x[2]
+            return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.max_sm), 'power_w_max': max(x[1] for x in self.samples),
+                    'samples': len(sm), 'source': 'nvml, 10 ms period', 'reasons': sorted(name for bit, name in self.REASONS if bits & bit)}
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -118,7 +160,8 @@ class ClockSampler:
         if not sm:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
         sm.sort()
-        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'power_w_max': max(pw), 'samples': len(sm), 'reasons': sorted(reasons)}
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'power_w_max': max(pw), 'samples': len(sm), 'source': 'nvidia-smi -lms 200',
+                'reasons': sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------------------
