@@ -258,6 +258,10 @@ typedef struct {
 } db200_adam_params;
 int dalle_b200_adam(const db200_adam_params* p, void* stream);
 
+/* Debug export, NOT part of the contract (no reference counterpart): clock64() timeline of one dK/dV attention CTA recorded when
+ * DALLE_B200_ATTN_WAIT has bit 2 set; used by tools/attn_timeline.py. */
+int dalle_b200_debug_attn_timeline(long long* out, int count);
+
 #ifdef __cplusplus
 }
 #endif
