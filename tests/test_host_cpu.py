@@ -45,6 +45,13 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     A = _lib.AttnFwdParams(batch=1, heads=1, n_q=4, n_k=4, dim_head=32)
     rc = lib.dalle_b200_attn_fwd(ctypes.byref(A), None)
     assert rc == -2 and b'dim_head' in lib.dalle_b200_last_error()
+    # optimizer / embedding entry points validate before touching the device as well
+    O = _lib.AdamParams(count=16, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, step=1)
+    assert lib.dalle_b200_adam(ctypes.byref(O), None) == -1 and b'adam' in lib.dalle_b200_last_error()
+    assert lib.dalle_b200_sumsq(None, 4, None, None) == -1
+    assert lib.dalle_b200_embed_fwd(None, None, None, 1, 1, 1, 0, 4, 8, None) == -1 and b'embed_fwd' in lib.dalle_b200_last_error()
+    L = _lib.LnShiftBwdParams(batch=1, n=4, d=64, do_ln=0, do_shift=0, dout_dtype=0)
+    assert lib.dalle_b200_ln_shift_bwd(ctypes.byref(L), None) < 0
 
 
 @pytest.mark.parametrize('kw', [dict(), dict(reversible=True), dict(shift_tokens=False), dict(sandwich_norm=True),
