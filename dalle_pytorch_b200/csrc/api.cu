@@ -7,6 +7,10 @@
 #include "common.cuh"
 
 namespace db200 {
+bool pdl_enabled() {
+  static const bool on = [] { const char* v = std::getenv("DALLE_B200_PDL"); return !(v && v[0] == '0'); }();
+  return on;
+}
 
 std::string& last_error_slot() {
   static thread_local std::string s;

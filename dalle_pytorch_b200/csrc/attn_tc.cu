@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
                                                           const __grid_constant__ CUtensorMap tmV, FwdArgs P, AttnGeom g) {
   using L = FwdSmem<P_TMEM>;
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t sQ = smem_u32(smem + L::Q_OFF);
   const uint32_t sK = smem_u32(smem + L::K_OFF), sV = smem_u32(smem + L::V_OFF), sP = smem_u32(smem + L::P_OFF);
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                                   // set-up above overlapped the previous kernel's tail
   const uint32_t tS = tmem, tO = tmem + 64, tP = tmem;
 
   if (warp == 0) {
@@ -337,6 +339,8 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
 // one 16-byte load of O and dO per lane, 4 rows per warp per step, 4 steps in flight.
 __global__ void __launch_bounds__(256) attn_delta_tc_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ delta,
                                                             int batch, int heads, int n) {
+  pdl_launch();
+  pdl_wait();
   const long long total = (long long)batch * heads * n;
   const int part = threadIdx.x & 7;
   const long long stride = (long long)gridDim.x * 32 * 4;            // rows per grid step (32 rows per 256-thread block, x4 unroll)
@@ -481,6 +485,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
                                                                BwdArgs P, AttnGeom g) {
   using L = DkvSmem;
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t sK = smem_u32(smem + L::K_OFF), sV = smem_u32(smem + L::V_OFF), sQ = smem_u32(smem + L::Q_OFF), sdO = smem_u32(smem + L::DO_OFF);
   float* s_lse = reinterpret_cast<float*>(smem + L::STAT_OFF);      // [2][64]
@@ -513,6 +518,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                                   // set-up above overlapped the previous kernel's tail
   const uint32_t tSt = tmem, tdPt = tmem + 64, tdV = tmem + 128, tdK = tmem + 192, tPt = tmem, tdSt = tmem + 64;
   const bool dbg = (P.wait_mode & 4) && blockIdx.x == 1 && blockIdx.y == 0 && (threadIdx.x == 32 || threadIdx.x == 64 || threadIdx.x == 192);
 
@@ -691,6 +697,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
                                                               BwdArgs P, AttnGeom g) {
   using L = DqSmem;
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t sQ = smem_u32(smem + L::Q_OFF), sdO = smem_u32(smem + L::DO_OFF), sK = smem_u32(smem + L::K_OFF), sV = smem_u32(smem + L::V_OFF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -718,6 +725,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();                                   // set-up above overlapped the previous kernel's tail
   const uint32_t tS = tmem, tdP = tmem + 64, tdS = tmem + 64, tdQ = tmem + 128;
 
   if (warp == 0) {
@@ -873,7 +881,7 @@ int launch_fwd(const db200_attn_fwd_params& p, cudaStream_t st) {
   }
   FwdArgs A{reinterpret_cast<bf16*>(p.out), p.lse, p.key_mask, p.heads, p.batch};
   dim3 grid(ceil_div(p.n_q, TQ), p.batch * p.heads);
-  kern<<<grid, 192, L::TOTAL, st>>>(tmQ, tmK, tmV, A, make_geom(p));
+  DB200_CUDA_OK(launch_pdl(kern, grid, dim3(192), L::TOTAL, st, tmQ, tmK, tmV, A, make_geom(p)));
   DB200_LAUNCH_OK("attn_fwd_tc_kernel");
   return DB200_OK;
 }
@@ -924,17 +932,17 @@ int attn_bwd_tc_launch(const db200_attn_bwd_params& p, cudaStream_t st) {
     int blocks = ceil_div(total_rows, 32 * 4);
     const int cap = sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    attn_delta_tc_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(f.out), reinterpret_cast<const bf16*>(p.d_out), p.delta, f.batch,
-                                                 f.heads, n);
+    DB200_CUDA_OK(launch_pdl(attn_delta_tc_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const bf16*>(f.out),
+                             reinterpret_cast<const bf16*>(p.d_out), p.delta, f.batch, f.heads, n));
   }
   DB200_LAUNCH_OK("attn_delta_tc_kernel");
   static const int wait_mode = [] { const char* v = getenv("DALLE_B200_ATTN_WAIT"); return v ? atoi(v) : 0; }();
   BwdArgs A{f.lse, p.delta, f.key_mask, p.cos_t, p.sin_t, p.q_scale, reinterpret_cast<bf16*>(p.dqkv), f.heads, f.batch, wait_mode};
   const AttnGeom g = make_geom(f);
   dim3 grid(ceil_div(n, TQ), f.batch * f.heads);
-  attn_bwd_dkv_tc_kernel<<<grid, BWD_THREADS, DkvSmem::TOTAL, st>>>(tmQ64, tmK128, tmV128, tmdO64, A, g);
+  DB200_CUDA_OK(launch_pdl(attn_bwd_dkv_tc_kernel, grid, dim3(BWD_THREADS), DkvSmem::TOTAL, st, tmQ64, tmK128, tmV128, tmdO64, A, g));
   DB200_LAUNCH_OK("attn_bwd_dkv_tc_kernel");
-  attn_bwd_dq_tc_kernel<<<grid, BWD_THREADS, DqSmem::TOTAL, st>>>(tmQ128, tmK64, tmV64, tmdO128, A, g);
+  DB200_CUDA_OK(launch_pdl(attn_bwd_dq_tc_kernel, grid, dim3(BWD_THREADS), DqSmem::TOTAL, st, tmQ128, tmK64, tmV64, tmdO128, A, g));
   DB200_LAUNCH_OK("attn_bwd_dq_tc_kernel");
   return DB200_OK;
 }

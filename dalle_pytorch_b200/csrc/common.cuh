@@ -156,6 +156,25 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------
+// A kernel launched through launch_pdl() may be scheduled while its predecessor in the stream is still draining; it must
+// execute pdl_wait() before its first global-memory access (the wait returns once the predecessor grid has completed and its
+// writes are visible; it is a no-op for a normally launched kernel).  pdl_launch() lets OUR successor be scheduled early.
+// Net effect: the ~2 us launch gap and the kernel prologue (barrier init, TMEM allocation) overlap the previous kernel's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();      // DALLE_B200_PDL=0 turns the launch attribute off (kernels then serialise as usual)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -211,6 +211,8 @@ constexpr int WR_WARPS = 8;
 
 template <typename TO, int NCH>
 __global__ void __launch_bounds__(WR_WARPS * 32) ln_shift_fwd_warp_kernel(db200_ln_shift_fwd_params P) {
+  pdl_launch();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = P.batch * P.n;
   const int r = blockIdx.x * WR_WARPS + warp;
@@ -386,6 +388,7 @@ struct LnTmaSmem {
 
 template <typename TI>
 __global__ void __launch_bounds__(LT_THREADS, 1) ln_shift_bwd_tma_kernel(db200_ln_shift_bwd_params P) {
+  pdl_launch();
   using L = LnTmaSmem<TI>;
   constexpr int R = LT_R, d = LT_D, STAGES = L::STAGES;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -400,6 +403,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) ln_shift_bwd_tma_kernel(db200_l
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();
   const int step = gridDim.x * R;
 
   if (warp == LT_GROUPS * LT_NW) {
@@ -623,6 +627,8 @@ __global__ void __launch_bounds__(256) ln_shift_bwd_param_kernel(db200_ln_shift_
 // sums live in 12 registers, so occupancy is high and four rows of loads are in flight per thread.
 template <typename T>
 __global__ void __launch_bounds__(256, 2) scale_bwd_slab_kernel(db200_scale_bwd_params P, int rows_per_block) {
+  pdl_launch();
+  pdl_wait();
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
   const int d = P.d;
   if (c >= d) return;
@@ -701,6 +707,8 @@ __global__ void __launch_bounds__(256) scale_bwd_kernel(db200_scale_bwd_params P
 template <typename T>
 __global__ void __launch_bounds__(256, 4) geglu_bwd_kernel(const T* __restrict__ dh, const T* __restrict__ u, T* __restrict__ du,
                                                         float* __restrict__ dbias, int rows, int hidden, int rows_per_block) {
+  pdl_launch();
+  pdl_wait();
   const int j = (blockIdx.x * 256 + threadIdx.x) * 8;
   if (j >= hidden) return;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
@@ -801,6 +809,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) qkv_rotary_kernel(const T* __restrict__ qkv, T* __restrict__ q, T* __restrict__ k, T* __restrict__ v,
                                                          const float* __restrict__ cos_t, const float* __restrict__ sin_t, int rows, int seq_n,
                                                          int heads, int dh, int pos_offset, float q_scale) {
+  pdl_launch();
+  pdl_wait();
   const int inner = heads * dh;
   const int m = blockIdx.x;                                      // token row (block-uniform: its b / p split costs nothing)
   const int c = (blockIdx.y * 256 + threadIdx.x) * 8;            // column in [0, 3*inner)
@@ -858,6 +868,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, in
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long count) {
+  pdl_launch();
+  pdl_wait();
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < count; i += stride) {
     if (i + 3 < count) {
@@ -1000,8 +1012,8 @@ int ln_shift_fwd_launch(const db200_ln_shift_fwd_params& P, cudaStream_t st) {
   const int wgrid = ceil_div(rows, WR_WARPS);
 #define DB200_LN_FWD_WARP(NCH)                                                                                              \
   do {                                                                                                                      \
-    if (P.out_dtype == DB200_F32) ln_shift_fwd_warp_kernel<float, NCH><<<wgrid, WR_WARPS * 32, 0, st>>>(P);               \
-    else ln_shift_fwd_warp_kernel<__nv_bfloat16, NCH><<<wgrid, WR_WARPS * 32, 0, st>>>(P);                                 \
+    if (P.out_dtype == DB200_F32) DB200_CUDA_OK(launch_pdl(ln_shift_fwd_warp_kernel<float, NCH>, dim3(wgrid), dim3(WR_WARPS * 32), 0, st, P)); \
+    else DB200_CUDA_OK(launch_pdl(ln_shift_fwd_warp_kernel<__nv_bfloat16, NCH>, dim3(wgrid), dim3(WR_WARPS * 32), 0, st, P));              \
     DB200_LAUNCH_OK("ln_shift_fwd_warp_kernel");                                                                           \
     return DB200_OK;                                                                                                        \
   } while (0)
@@ -1029,11 +1041,11 @@ int ln_shift_bwd_launch(const db200_ln_shift_bwd_params& P, cudaStream_t st) {
     if (P.dout_dtype == DB200_F32) {
       static bool attr = false;
       if (!attr) { DB200_CUDA_OK(cudaFuncSetAttribute(ln_shift_bwd_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, LnTmaSmem<float>::TOTAL)); attr = true; }
-      ln_shift_bwd_tma_kernel<float><<<grid, LT_THREADS, LnTmaSmem<float>::TOTAL, st>>>(P);
+      DB200_CUDA_OK(launch_pdl(ln_shift_bwd_tma_kernel<float>, dim3(grid), dim3(LT_THREADS), LnTmaSmem<float>::TOTAL, st, P));
     } else {
       static bool attr = false;
       if (!attr) { DB200_CUDA_OK(cudaFuncSetAttribute(ln_shift_bwd_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LnTmaSmem<__nv_bfloat16>::TOTAL)); attr = true; }
-      ln_shift_bwd_tma_kernel<__nv_bfloat16><<<grid, LT_THREADS, LnTmaSmem<__nv_bfloat16>::TOTAL, st>>>(P);
+      DB200_CUDA_OK(launch_pdl(ln_shift_bwd_tma_kernel<__nv_bfloat16>, dim3(grid), dim3(LT_THREADS), LnTmaSmem<__nv_bfloat16>::TOTAL, st, P));
     }
     DB200_LAUNCH_OK("ln_shift_bwd_tma_kernel");
     return DB200_OK;
@@ -1081,8 +1093,8 @@ int scale_bwd_launch(const db200_scale_bwd_params& P, cudaStream_t st) {
     const int cb = ceil_div(P.d, 1024);
     const int rpb = balanced_rows_per_block(P.rows, cb, 2, 8);
     dim3 sgrid(cb, ceil_div(P.rows, rpb));
-    if (P.dtype == DB200_F32) scale_bwd_slab_kernel<float><<<sgrid, 256, 0, st>>>(P, rpb);
-    else scale_bwd_slab_kernel<__nv_bfloat16><<<sgrid, 256, 0, st>>>(P, rpb);
+    if (P.dtype == DB200_F32) DB200_CUDA_OK(launch_pdl(scale_bwd_slab_kernel<float>, sgrid, dim3(256), 0, st, P, rpb));
+    else DB200_CUDA_OK(launch_pdl(scale_bwd_slab_kernel<__nv_bfloat16>, sgrid, dim3(256), 0, st, P, rpb));
     DB200_LAUNCH_OK("scale_bwd_slab_kernel");
     return DB200_OK;
   }
@@ -1099,11 +1111,11 @@ int geglu_bwd_launch(const void* dh, const void* u, void* du, float* dbias, int 
   const int rpb = balanced_rows_per_block(rows, cb, 4, 4);
   dim3 grid(cb, ceil_div(rows, rpb));
   if (dtype == DB200_F32)
-    geglu_bwd_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(dh), reinterpret_cast<const float*>(u),
-                                                  reinterpret_cast<float*>(du), dbias, rows, hidden, rpb);
+    DB200_CUDA_OK(launch_pdl(geglu_bwd_kernel<float>, grid, dim3(256), 0, st, reinterpret_cast<const float*>(dh), reinterpret_cast<const float*>(u),
+                             reinterpret_cast<float*>(du), dbias, rows, hidden, rpb));
   else
-    geglu_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dh), reinterpret_cast<const __nv_bfloat16*>(u),
-                                                          reinterpret_cast<__nv_bfloat16*>(du), dbias, rows, hidden, rpb);
+    DB200_CUDA_OK(launch_pdl(geglu_bwd_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(dh),
+                             reinterpret_cast<const __nv_bfloat16*>(u), reinterpret_cast<__nv_bfloat16*>(du), dbias, rows, hidden, rpb));
   DB200_LAUNCH_OK("geglu_bwd_kernel");
   return DB200_OK;
 }
@@ -1130,12 +1142,12 @@ int qkv_rotary_launch(const void* qkv, void* q, void* k, void* v, const float* c
   if (rows == 0) return DB200_OK;
   const dim3 grid(rows, ceil_div(3 * heads * dh / 8, 256));
   if (dtype == DB200_F32)
-    qkv_rotary_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(q), reinterpret_cast<float*>(k),
-                                                   reinterpret_cast<float*>(v), cos_t, sin_t, rows, seq_n, heads, dh, pos_offset, q_scale);
+    DB200_CUDA_OK(launch_pdl(qkv_rotary_kernel<float>, grid, dim3(256), 0, st, reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(q),
+                             reinterpret_cast<float*>(k), reinterpret_cast<float*>(v), cos_t, sin_t, rows, seq_n, heads, dh, pos_offset, q_scale));
   else
-    qkv_rotary_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(q),
-                                                           reinterpret_cast<__nv_bfloat16*>(k), reinterpret_cast<__nv_bfloat16*>(v), cos_t, sin_t,
-                                                           rows, seq_n, heads, dh, pos_offset, q_scale);
+    DB200_CUDA_OK(launch_pdl(qkv_rotary_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
+                             reinterpret_cast<__nv_bfloat16*>(q), reinterpret_cast<__nv_bfloat16*>(k), reinterpret_cast<__nv_bfloat16*>(v), cos_t, sin_t,
+                             rows, seq_n, heads, dh, pos_offset, q_scale));
   DB200_LAUNCH_OK("qkv_rotary_kernel");
   return DB200_OK;
 }
@@ -1153,7 +1165,7 @@ int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st
   if (count == 0) return DB200_OK;
   int64_t blocks = ceil_div64(count, 256 * 4);
   if (blocks > sm_count() * 16) blocks = sm_count() * 16;
-  cast_bf16_kernel<<<(int)blocks, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), count);
+  DB200_CUDA_OK(launch_pdl(cast_bf16_kernel, dim3((int)blocks), dim3(256), 0, st, src, reinterpret_cast<__nv_bfloat16*>(dst), (long long)count));
   DB200_LAUNCH_OK("cast_bf16_kernel");
   return DB200_OK;
 }

@@ -110,6 +110,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  pdl_launch();
   unsigned int first_draw = 0;
   const bool dyn = sched_slot >= 0;                            // sched_slot < 0: static round-robin schedule (A/B switch)
   if (threadIdx.x == 0) first_draw = dyn ? atomicAdd(&g_sched_counter[sched_slot], 1u) : blockIdx.x;   // latency hides behind the setup below
@@ -129,6 +130,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                                 // everything above overlapped the previous kernel's tail
 
   const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
   const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
@@ -397,7 +399,7 @@ int launch_cfg_mode(const db200_gemm_params& p, cudaStream_t st) {
   e.atomic_c = k_splits > 1;
   static const bool static_sched = [] { const char* v = std::getenv("DALLE_B200_SCHED"); return v && !std::strcmp(v, "static"); }();
   const int sched_slot = static_sched ? -1 : static_cast<int>(g_launch_seq.fetch_add(1, std::memory_order_relaxed) % SCHED_SLOTS);
-  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(tmA, tmB, p.M, p.N, p.K, k_splits, sched_slot, e);
+  DB200_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, st, tmA, tmB, p.M, p.N, p.K, k_splits, sched_slot, e));
   DB200_LAUNCH_OK("gemm_tcgen05_kernel");
   return DB200_OK;
 }
