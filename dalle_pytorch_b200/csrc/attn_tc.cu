@@ -1,19 +1,21 @@
 // Fused attention on the 5th-generation tensor cores (tcgen05.mma, accumulators and P in tensor memory), for every
 // sparsity pattern of the reference.  bf16 operands, fp32 accumulation / softmax statistics.
 //
-// One CTA = 128 queries of one (batch, head); 128-key tiles stream through a 2-stage TMA ring.
+// One CTA = 128 queries of one (batch, head); 64-key tiles stream through a 2-stage TMA ring.
 //   warp 0     : TMA producer (Q once; K/V tiles)
-//   warp 1     : MMA issuer   S = Q K^T          (SS: both operands in 128B-swizzled smem, D in TMEM cols [0,128))
+//   warp 1     : MMA issuer   (converged warp + elect.sync, bursts software-pipelined: S of tile i+1 goes out with O += P V of tile i)
+//                             S = Q K^T          (SS: both operands in 128B-swizzled smem, D in TMEM cols [0,64))
 //                             O += P V           (TS: A = P read from TMEM, B = V tile read N-major from the same smem image)
 //   warps 2..5 : softmax      thread = query row (tcgen05.ld 32x32b): row max / sum need no shuffles; P is written back to
 //                             TMEM as packed bf16 (tcgen05.st) and O is rescaled in TMEM only when the running max moved by
 //                             more than 2^8 (lazy rescale); final O / l and the log-sum-exp are written by the same threads.
-// Two CTAs fit per SM (80 KB smem, 256 TMEM columns each), so one CTA's softmax overlaps the other's MMAs.
+// Three CTAs fit per SM (48 KB smem, 128 TMEM columns each), so one CTA's softmax overlaps the others' MMAs.
 //
 // Backward: delta = rowsum(dO*O), then a dK/dV kernel (CTA = 128 keys, loops over query tiles, works on the transposed
 // score tile so that thread = key row) and a dQ kernel (CTA = 128 queries, loops over key tiles); both recompute P from
 // the saved log-sum-exp, keep P / dS in TMEM as the A operand of the second-stage MMAs, and fold the rotary adjoint and
-// the q scale into their final stores (which write the [rows, 3*h*64] gradient of the to_qkv output directly).
+// the q scale into their final stores (which write the [rows, 3*h*64] gradient of the to_qkv output directly).  The backward
+// kernels run eight softmax warps (two per TMEM lane quarter, 32 score columns each) on 128 x 64 tiles, two CTAs per SM.
 #include <cstdlib>
 #include <cstring>
 

@@ -2,8 +2,10 @@
 // into 128B-swizzled shared memory, warp-specialised producer / MMA-issuer / epilogue roles, persistent CTAs
 // (one per SM) with a double-buffered TMEM accumulator so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
-//   warp 0      : TMA producer   (one elected lane; cp.async.bulk.tensor -> smem ring, mbarrier complete_tx)
-//   warp 1      : MMA issuer     (one elected lane; tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16;
+//   warp 0      : TMA producer + dynamic tile scheduler (whole warp converged, elect.sync picks the issuing lane per k-block;
+//                                 cp.async.bulk.tensor -> smem ring, mbarrier complete_tx; tile ids drawn with atomicAdd and
+//                                 published to the other roles through a small smem ring)
+//   warp 1      : MMA issuer     (converged warp + elect.sync; tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16;
 //                                 tcgen05.commit releases smem stages / publishes the accumulator)
 //   warps 2..9  : epilogue       (tcgen05.ld 32x32b gives thread = accumulator row; each 32x32 chunk is transposed through a
 //                                 private 4 KB smem buffer so that LANES RUN ALONG N: every global load/store of the fused
