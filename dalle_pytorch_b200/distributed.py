@@ -14,7 +14,15 @@ a post-accumulate hook counts parameters down and launches `all_reduce(bucket, a
 bucket is complete, so communication of layer i overlaps the backward kernels of layer i-1.  `finish()` waits for
 the outstanding work and applies 1/world.  NVSwitch gives every GPU full bandwidth to every peer, so buckets are
 sized for launch latency / overlap (default 64 MiB), not for link count.
+
+Validity contract (what makes the reference loop `loss.backward(); clip_grad_norm_(params); opt.step()`,
+train_dalle.py:612-622, safe): the first gradient of a backward pass queues an end-of-backward callback on the
+autograd engine which runs `finish()`, so when `backward()` returns every `.grad` is the reduced mean and no
+collective is still writing the flat buffer.  Gradient accumulation: wrap all but the last backward of a step in
+`reducer.no_sync()`; a gradient that arrives after the step's reduction raises instead of silently mixing
+averaged and local gradients.
 """
+import contextlib
 import os
 
 import torch
@@ -120,8 +128,10 @@ class DummyBackend(DistributedBackend):
 class GradAllReducer:
     """Flat-buffer bucketed gradient all-reduce (see module docstring)."""
 
-    def __init__(self, params, process_group=None, bucket_bytes=64 << 20, average=True):
+    def __init__(self, params, process_group=None, bucket_bytes=64 << 20, average=True, auto_finish=True):
         self.pg = process_group
+        self.auto_finish = auto_finish      # finish() runs as an autograd end-of-backward callback
+        self._sync, self._finished, self._cb_queued = True, False, False
         # without an initialised process group this is just the flat gradient buffer of a single process (optim.FusedAdam)
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.average = average
@@ -177,6 +187,38 @@ class GradAllReducer:
             self._pending[bi] = len(ps)
             self._launched[bi] = False
         self._works = []
+        self._finished = False
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Gradient accumulation: backward passes inside this context only accumulate into the flat buffer (no bucket is
+        launched, nothing is reduced); the first backward outside it reduces the accumulated sum."""
+        old, self._sync = self._sync, False
+        try:
+            yield self
+        finally:
+            self._sync = old
+
+    def _guard(self):
+        if self._finished:
+            raise RuntimeError('GradAllReducer: a gradient arrived after this step\'s all-reduce (second backward without '
+                               'zero_grad()).  For gradient accumulation run the earlier backward passes under reducer.no_sync(); '
+                               'otherwise call zero_grad() / optimizer.step() between steps.')
+
+    def _arm(self):
+        """Queue finish() to run when the current backward pass ends (once per pass)."""
+        if not self.auto_finish or self._cb_queued:
+            return
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(self._end_of_backward)
+            self._cb_queued = True
+        except RuntimeError:       # not inside a backward pass (gradient handed over by hand): the caller runs finish()
+            pass
+
+    def _end_of_backward(self):
+        self._cb_queued = False
+        if self._sync:
+            self.finish()
 
     def _launch(self, bi):
         s, e, _ = self.buckets[bi]
@@ -198,6 +240,7 @@ class GradAllReducer:
     # direct-write protocol used by the fused sub-layer backward (functional.py::_slot/_commit): the weight-gradient GEMM
     # writes into the flat-buffer view itself, so neither a memset nor a copy of that gradient is ever made
     def direct_slot(self, p):
+        self._guard()
         if p in self._seen or p not in self.views:
             return None
         return self.views[p]
@@ -208,21 +251,25 @@ class GradAllReducer:
         self._count(p)
 
     def _count(self, p):
+        self._arm()
+        if not self._sync:           # accumulation pass: nothing is launched
+            return
         bi = self.bucket_of[p]
         self._pending[bi] -= 1
         if self._pending[bi] == 0 and not self._launched[bi]:
             self._launch(bi)
 
     def _on_grad(self, p):
+        self._guard()
         self._adopt(p)
-        bi = self.bucket_of[p]
-        self._pending[bi] -= 1
-        if self._pending[bi] == 0 and not self._launched[bi]:
-            self._launch(bi)
+        self._count(p)
 
     def finish(self):
         """Reduce whatever has not been launched by the hooks (parameters whose gradients were written outside
-        autograd, e.g. by the reversible executor, or that received no gradient), wait, and average."""
+        autograd, or that received no gradient), wait, and average.  Idempotent within a step: a second call (explicit call +
+        the optimizer's step pre-hook) returns immediately; zero_grad() opens the next step."""
+        if self._finished:
+            return
         for bi, (_, _, ps) in enumerate(self.buckets):
             if not self._launched[bi]:
                 for p in ps:
@@ -234,6 +281,7 @@ class GradAllReducer:
         self._works = []
         if self.average and self.world > 1 and not self._has_avg:
             self.flat.mul_(1.0 / self.world)
+        self._finished = True
 
     def remove(self):
         for h in self._hooks:
@@ -286,7 +334,9 @@ class NCCLBackend(DistributedBackend):
     def _distribute(self, _args=None, model=None, optimizer=None, model_parameters=None, training_data=None, lr_scheduler=None,
                     **_kwargs):
         """Broadcast rank 0's parameters (Horovod analogue horovod_backend.py:49-52), attach the gradient reducer
-        and make `optimizer.step()` wait for it.  Returns (model, optimizer, training_data, lr_scheduler)."""
+        and make `optimizer.step()` wait for it (the reduction itself already completes inside `backward()`, see the
+        module docstring, so `clip_grad_norm_` between backward and step sees reduced gradients).
+        Returns (model, optimizer, training_data, lr_scheduler)."""
         with torch.no_grad():
             for t in list(model.parameters()) + list(model.buffers()):
                 dist.broadcast(t, src=self.ROOT_RANK)

@@ -35,20 +35,45 @@ FUSE_UPSTREAM_SCALE_BWD = os.environ.get('DALLE_B200_FUSE_SCALE_BWD', '1') != '0
 
 
 class _SubRec:
-    """What sub-layer k must know about sub-layer k-1 to run its LayerScale adjoint, plus the slot the results come back in."""
-    __slots__ = ('y', 'scale', 'sign', 'out_ptr', 'pre', 'pre_ptr')
+    """What sub-layer k must know about sub-layer k-1 to run its LayerScale adjoint, plus the slot the results come back in.
+
+    Identity of "the tensor sub-layer k-1 produced / the gradient sub-layer k wrote" is established with the tensor itself held
+    alive (so the caching allocator cannot hand its address to anything else) plus its version counter (so an in-place
+    accumulation by the autograd engine's input buffer -- a second consumer of the stream tensor -- is detected): a bare
+    data_ptr() comparison would accept a recycled address or `dx + other` sitting at dx's address."""
+    __slots__ = ('y', 'scale', 'sign', 'out', 'out_version', 'pre', 'pre_dx', 'pre_version')
 
     def __init__(self, y, scale, sign, out):
-        self.y, self.scale, self.sign, self.out_ptr = y, scale, sign, out.data_ptr()
-        self.pre, self.pre_ptr = None, None
+        self.y, self.scale, self.sign = y, scale, sign
+        self.out, self.out_version = out, out._version       # released as soon as the next sub-layer has linked (or chain_reset)
+        self.pre, self.pre_dx, self.pre_version = None, None, -1
+
+    def produced(self, x):
+        """Is `x` the (unmodified) output this record's sub-layer returned?"""
+        o = self.out
+        return (o is not None and x.data_ptr() == o.data_ptr() and x._version == self.out_version and x.shape == o.shape
+                and x.dtype == o.dtype)
+
+    def take_pre(self, d_out):
+        """The pre-computed LayerScale adjoint, if `d_out` is exactly the dx it was formed from."""
+        pre, dx = self.pre, self.pre_dx
+        self.pre = self.pre_dx = None
+        if pre is None or dx is None:
+            return None
+        if d_out.data_ptr() != dx.data_ptr() or d_out._version != self.pre_version or d_out.shape != dx.shape:
+            return None
+        return pre
 
 
 _chain = threading.local()
 
 
 def chain_reset():
-    """Called at the start of every executor forward: a record must never match a tensor of an earlier pass whose address the
-    caching allocator has recycled."""
+    """Called at the start and the end of every executor forward: drops the tail record's reference to its output (a record
+    is reachable from its own output through grad_fn -> ctx, so the reference must not outlive the link step)."""
+    last = getattr(_chain, 'last', None)
+    if last is not None:
+        last.out = None
     _chain.last = None
 
 
@@ -57,10 +82,11 @@ def _chain_link(x_in, resid_is_input, rec):
     also the residual, i.e. the sequential executor) and makes `rec` the new tail."""
     prev = getattr(_chain, 'last', None)
     _chain.last = rec
-    if (FUSE_UPSTREAM_SCALE_BWD and prev is not None and resid_is_input and prev.out_ptr == x_in.data_ptr() and x_in.shape[-1] == 1024
-            and x_in.is_cuda):
-        return prev
-    return None
+    if prev is None:
+        return None
+    ok = FUSE_UPSTREAM_SCALE_BWD and resid_is_input and x_in.shape[-1] == 1024 and x_in.is_cuda and prev.produced(x_in)
+    prev.out = None                  # the stream tensor is owned by the executor from here on
+    return prev if ok else None
 
 
 class SublayerGeom:
@@ -103,7 +129,7 @@ def _up_store(up, res):
     if not isinstance(res, tuple):
         return res
     dx, up_dy, up_dscale, up_dbias = res
-    up.pre, up.pre_ptr = (up_dy, up_dscale, up_dbias), dx.data_ptr()
+    up.pre, up.pre_dx, up.pre_version = (up_dy, up_dscale, up_dbias), dx, dx._version
     return dx
 
 
@@ -277,7 +303,7 @@ class AttnSublayerFn(torch.autograd.Function):
         dres = d_out if ctx.resid_is_input else None
         slots = tuple(_slot(p) for p in ctx.wparams)
         rec = ctx.rec
-        pre = rec.pre if (rec is not None and rec.pre is not None and rec.pre_ptr == d_out.data_ptr()) else None
+        pre = rec.take_pre(d_out) if rec is not None else None
         dx, dln_w, dln_b, dw_qkv, dw_out, db_out, dscale = attn_sublayer_backward(
             g, ctx.saved, d_out, ctx.ln_w, ctx.scale, ctx.sign, ctx.cos_t, ctx.sin_t, ctx.key_mask, dres=dres, wslots=slots,
             pre=pre, up=ctx.up)
@@ -313,7 +339,7 @@ class FFSublayerFn(torch.autograd.Function):
         dres = d_out if ctx.resid_is_input else None
         slots = tuple(_slot(p) for p in ctx.wparams)
         rec = ctx.rec
-        pre = rec.pre if (rec is not None and rec.pre is not None and rec.pre_ptr == d_out.data_ptr()) else None
+        pre = rec.take_pre(d_out) if rec is not None else None
         dx, dln_w, dln_b, dw1, db1, dw2, db2, dscale = ff_sublayer_backward(ctx.g, ctx.saved, d_out, ctx.ln_w, ctx.scale, ctx.sign,
                                                                               dres=dres, wslots=slots, pre=pre, up=ctx.up)
         ctx.rec = ctx.up = None

@@ -42,6 +42,7 @@ class SequentialSequence(nn.Module):
         for (f, g), (f_args, g_args) in zip(self.layers, args):
             x = f.residual(x, **f_args)      # x + f(x): one fused sub-layer when possible
             x = g.residual(x, **g_args)
+        chain_reset()
         return x
 
 
