@@ -11,5 +11,6 @@ from .reversible import SequentialSequence, ReversibleSequence
 from .dalle import DALLE, TokenVAE
 from . import ops, functional
 from .optim import FusedAdam
+from .patch import patch_dalle_pytorch
 
 __version__ = '0.1.0'

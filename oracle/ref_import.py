@@ -1,9 +1,10 @@
-"""Import the UNMODIFIED reference (lucidrains/DALLE-pytorch @ /root/reference) in the dev container.
+"""Import the UNMODIFIED reference (lucidrains/DALLE-pytorch) from /root/reference (dev container) or from the
+offline install under baseline/_ref (`pip install --no-deps --target baseline/_ref`, which travels to the GPU box).
 
-TEST INFRASTRUCTURE ONLY.  /root/reference does not exist on the GPU box; nothing under tests -m gpu,
-smoke() or bench.py may call this at run time.  It is used by oracle/make_golden.py (to generate the
-committed fixtures under tests/golden/) and by the `not gpu` tests that pin oracle/dalle_oracle.py
-against the live reference when it is present.
+TEST / MEASUREMENT INFRASTRUCTURE ONLY -- never imported by the product package.  Users: oracle/make_golden.py (generates
+the committed fixtures under tests/golden/), the `not gpu` tests that pin oracle/dalle_oracle.py against the live
+reference, the drop-in test of `patch_dalle_pytorch()`, and bench.py's reference legs (`--impl reference`, `cpu_baseline`,
+`gpu_eager_baseline`), which time the reference's own `DALLE(...)` stock code path.
 
 Mechanism: register a synthetic package object `dalle_pytorch` whose __path__ points
 at /root/reference/dalle_pytorch so that its __init__.py (which pulls tokenizers / vae deps that are not
@@ -15,12 +16,23 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get('DALLE_REFERENCE_ROOT', '/root/reference')
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'shims')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIMS = os.path.join(_HERE, 'shims')
+
+
+def _find_root():
+    cands = [os.environ.get('DALLE_REFERENCE_ROOT'), '/root/reference', os.path.join(os.path.dirname(_HERE), 'baseline', '_ref')]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, 'dalle_pytorch', 'dalle_pytorch.py')):
+            return c
+    return cands[1]
+
+
+REF_ROOT = _find_root()
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REF_ROOT, 'dalle_pytorch'))
+    return os.path.isfile(os.path.join(REF_ROOT, 'dalle_pytorch', 'dalle_pytorch.py'))
 
 
 def import_reference():

@@ -119,3 +119,35 @@ def test_ops_refuse_cpu_tensors():
     from dalle_pytorch_b200 import ops
     with pytest.raises(AssertionError):
         ops.colsum(torch.zeros(4, 4))
+
+
+def test_patch_dalle_pytorch_rebinds_the_live_reference():
+    """`patch_dalle_pytorch()` (SURVEY.md §7 drop-in installer): an UNMODIFIED reference DALLE built after patching carries this
+    package's modules with the reference's state-dict keys; undo() restores the reference classes."""
+    import ref_import
+    if not ref_import.reference_available():
+        pytest.skip('reference not present')
+    ref = ref_import.import_reference()
+    undo = D.patch_dalle_pytorch()
+    try:
+        vae = ref.DiscreteVAE(image_size=32, num_layers=3, num_tokens=32, codebook_dim=16, hidden_dim=8)
+        kw = dict(dim=64, num_text_tokens=50, text_seq_len=8, depth=4, heads=2, dim_head=64,
+                  attn_types=('full', 'axial_row', 'axial_col', 'conv_like'))
+        for rev in (False, True):
+            m = ref.DALLE(vae=vae, reversible=rev, **kw)
+            ours = D.DALLE(vae=D.TokenVAE(image_size=32, num_layers=3, num_tokens=32), reversible=rev, **kw)
+            assert type(m).__module__.startswith('dalle_pytorch.')                 # the reference's own DALLE / Transformer ...
+            assert type(m.transformer).__module__ == 'dalle_pytorch.transformer'
+            assert type(m.transformer.layers).__module__ == 'dalle_pytorch_b200.reversible'   # ... around this package's blocks
+            kinds = {type(x).__name__: type(x).__module__ for x in m.transformer.modules()}
+            for name in ('Attention', 'SparseAxialCausalAttention', 'SparseConvCausalAttention', 'FeedForward', 'LayerScale', 'PreNorm',
+                         'PreShiftToken'):
+                assert kinds[name].startswith('dalle_pytorch_b200.'), (name, kinds[name])
+            own = {k: v.shape for k, v in ours.state_dict().items()}
+            got = {k: v.shape for k, v in m.state_dict().items() if not k.startswith('vae.')}
+            assert own == got
+            ours.load_state_dict({k: v for k, v in m.state_dict().items() if not k.startswith('vae.')})
+    finally:
+        undo()
+    m = ref.DALLE(vae=vae, **kw)
+    assert type(m.transformer.layers).__module__ == 'dalle_pytorch.reversible'
