@@ -52,7 +52,7 @@ class GemmParams(ctypes.Structure):
 class AttnFwdParams(ctypes.Structure):
     _fields_ = [('batch', c_int), ('heads', c_int), ('n_q', c_int), ('n_k', c_int), ('dim_head', c_int),
                 ('dtype', c_int), ('pattern', c_int), ('causal', c_int), ('stable', c_int),
-                ('text_len', c_int), ('fmap', c_int), ('kernel_size', c_int), ('dilation', c_int),
+                ('text_len', c_int), ('fmap', c_int), ('kernel_size', c_int), ('dilation', c_int), ('gather', c_int),
                 ('key_mask', c_void_p), ('static_mask', c_void_p), ('static_ld', c_int64),
                 ('q', c_void_p), ('k', c_void_p), ('v', c_void_p), ('out', c_void_p), ('lse', c_void_p)]
 
@@ -108,7 +108,7 @@ def _declare(lib):
     lib.dalle_b200_gemm_select.argtypes = [ctypes.POINTER(GemmParams)]
     lib.dalle_b200_gemm_select.restype = c_int
     lib.dalle_b200_colsum.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
-    lib.dalle_b200_qkv_rotary.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]
+    lib.dalle_b200_qkv_rotary.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]
     lib.dalle_b200_geglu_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.dalle_b200_ce_fwd.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p]
     lib.dalle_b200_ce_bwd.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p]

@@ -28,7 +28,7 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 int sm_count() {
-  static int cached[64] = {0};
+  static std::atomic<int> cached[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
   if (cached[dev] == 0) {
@@ -47,7 +47,7 @@ int colsum_launch(const void* x, int dtype, int rows, int cols, float* out, cuda
 int ce_fwd_launch(const void* logits, int dtype, int rows, int vocab, const long long* labels, float coef, float* row_lse, float* loss_acc, cudaStream_t st);
 int ce_bwd_launch(void* logits, int dtype, int rows, int vocab, const long long* labels, float coef, const float* row_lse, const float* upstream, cudaStream_t st);
 int qkv_rotary_launch(const void* qkv, void* q, void* k, void* v, const float* cos_t, const float* sin_t, int dtype, int rows, int seq_n, int heads,
-                      int dh, int pos_offset, float q_scale, cudaStream_t st);
+                      int dh, int pos_offset, float q_scale, int n_alloc, cudaStream_t st);
 int geglu_bwd_launch(const void* dh, const void* u, void* du, float* dbias, int dtype, int rows, int hidden, cudaStream_t st);
 int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st);
 int axpby_launch(const float* a, const float* b, float alpha, float* y, int64_t count, cudaStream_t st);
@@ -63,6 +63,7 @@ bool attn_mma_supported(const db200_attn_fwd_params& p);
 int attn_fwd_mma_launch(const db200_attn_fwd_params& p, cudaStream_t st);
 int attn_bwd_mma_launch(const db200_attn_bwd_params& p, cudaStream_t st);
 bool attn_tc_supported(const db200_attn_fwd_params& p);
+bool attn_gather_ok(const db200_attn_fwd_params& p, const char** why);
 int attn_fwd_tc_launch(const db200_attn_fwd_params& p, cudaStream_t st);
 int attn_bwd_tc_launch(const db200_attn_bwd_params& p, cudaStream_t st);
 int attn_debug_timeline(long long* out, int count);
@@ -197,6 +198,7 @@ int dalle_b200_gemm_select(const db200_gemm_params* p) {
 static int attn_backend(const db200_attn_fwd_params& f) {
   const char* v = getenv("DALLE_B200_ATTN");
   int want = 2;                                   // tcgen05 kernels (attn_tc.cu) whenever the problem qualifies
+  if (f.gather) return 2;                         // validated by check_attn
   if (v) want = !strcmp(v, "simt") ? 0 : !strcmp(v, "tc") ? 2 : 1;
   if (want == 2 && !attn_tc_supported(f)) want = 1;
   if (want == 1 && !attn_mma_supported(f)) want = 0;
@@ -213,6 +215,11 @@ static int check_attn(const db200_attn_fwd_params& f, const char* who) {
   if (f.pattern == DB200_ATTN_AXIAL_ROW || f.pattern == DB200_ATTN_AXIAL_COL || f.pattern == DB200_ATTN_CONV_LIKE)
     DB200_CHECK_ARG(f.fmap > 0 && f.text_len > 0, "%s: sparse pattern needs text_len / fmap", who);
   if (f.pattern == DB200_ATTN_CONV_LIKE) DB200_CHECK_ARG(f.kernel_size > 0 && (f.kernel_size & 1) && f.dilation > 0, "%s: conv_like kernel_size must be odd", who);
+  if (f.gather) {      // the caller has laid q/k/v/lse out for the gathered kernels: there is no other backend to fall back to
+    const char* why = nullptr;
+    if (!attn_gather_ok(f, &why)) return set_error(DB200_ERR_UNSUPPORTED, "%s: %s", who, why);
+    if (!attn_tc_supported(f)) return set_error(DB200_ERR_UNSUPPORTED, "%s: gathered axial attention needs the tcgen05 path (sm_100, 16-byte aligned tensors)", who);
+  }
   return DB200_OK;
 }
 
@@ -261,14 +268,16 @@ int dalle_b200_geglu_bwd(const void* dh, const void* u, void* du, float* dbias, 
 }
 
 int dalle_b200_qkv_rotary(const void* qkv, void* q, void* k, void* v, const float* cos_t, const float* sin_t, int dtype, int rows, int seq_n,
-                          int heads, int dim_head, int pos_offset, float q_scale, void* stream) {
+                          int heads, int dim_head, int pos_offset, float q_scale, int n_alloc, void* stream) {
+  if (n_alloc == 0) n_alloc = seq_n;
+  DB200_CHECK_ARG(n_alloc >= seq_n, "qkv_rotary: n_alloc must be >= seq_n");
   DB200_CHECK_ARG(qkv && q && k && v && dtype_ok(dtype) && rows >= 0 && seq_n > 0 && heads > 0 && dim_head > 0 && (dim_head & 7) == 0 &&
                       rows % seq_n == 0,
                   "qkv_rotary: bad args (dim_head must be a multiple of 8, rows a multiple of seq_n)");
   DB200_CHECK_ARG((cos_t == nullptr) == (sin_t == nullptr), "qkv_rotary: cos/sin tables must come together");
   DB200_CHECK_ARG(aligned16(qkv) && aligned16(q) && aligned16(k) && aligned16(v) && (!cos_t || (aligned16(cos_t) && aligned16(sin_t))),
                   "qkv_rotary: tensors must be 16-byte aligned");
-  return qkv_rotary_launch(qkv, q, k, v, cos_t, sin_t, dtype, rows, seq_n, heads, dim_head, pos_offset, q_scale, (cudaStream_t)stream);
+  return qkv_rotary_launch(qkv, q, k, v, cos_t, sin_t, dtype, rows, seq_n, heads, dim_head, pos_offset, q_scale, n_alloc, (cudaStream_t)stream);
 }
 
 int dalle_b200_ce_fwd(const void* logits, int dtype, int rows, int vocab, const int64_t* labels, float coef, float* row_lse, float* loss_acc,

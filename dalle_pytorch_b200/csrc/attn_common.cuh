@@ -9,14 +9,77 @@ struct AttnGeom {
   int pattern, causal, text_len, fmap, ksize, dil;
   int n_q, n_k;                       // queries are the last n_q of the n_k key positions
   const uint8_t* static_mask; long long static_ld;
+  // Gathered axial mode (tcgen05 kernels only, see "gathered axial tiling" below): `pattern` is AXIAL_ROW in VIRTUAL
+  // coordinates, `col` says the virtual image order is column-major (axis = 1), rows per (b,h) of q/k/v = n_alloc,
+  // entries per (b,h) of lse / delta = n_stat, t_pad = text_len rounded up to 64.
+  int gather, col, n_alloc, n_stat, t_pad;
 };
+
+// layout constants of the gathered mode, shared with the host (ops.py mirrors them)
+__host__ __device__ inline int gather_n_alloc(int text_len, int fmap) { return text_len + fmap * fmap; }
+__host__ __device__ inline int gather_t_pad(int text_len) { return (text_len + 63) / 64 * 64; }
+__host__ __device__ inline int gather_n_stat(int text_len, int fmap) { return gather_t_pad(text_len) + fmap * fmap; }
 
 inline AttnGeom make_geom(const db200_attn_fwd_params& p) {
   AttnGeom g;
   g.pattern = p.pattern; g.causal = p.causal; g.text_len = p.text_len; g.fmap = p.fmap > 0 ? p.fmap : 1;
   g.ksize = p.kernel_size; g.dil = p.dilation > 0 ? p.dilation : 1;
   g.n_q = p.n_q; g.n_k = p.n_k; g.static_mask = p.static_mask; g.static_ld = p.static_ld;
+  g.gather = p.gather != 0; g.col = 0; g.n_alloc = p.n_k; g.n_stat = p.n_q; g.t_pad = 0;
+  if (g.gather) {
+    g.col = p.pattern == DB200_ATTN_AXIAL_COL;
+    g.pattern = DB200_ATTN_AXIAL_ROW;           // column attention IS row attention in the column-major virtual order
+    g.n_alloc = gather_n_alloc(p.text_len, g.fmap);
+    g.n_stat = gather_n_stat(p.text_len, g.fmap);
+    g.t_pad = gather_t_pad(p.text_len);
+  }
   return g;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Gathered axial tiling (reference attention.py:287-323 reshapes the image keys by rows / columns and attends text + own axis).
+// Virtual sequence: u in [0,T) = text position u; u = T + v = image token number v in AXIS-MAJOR order (row-major for
+// axis 0 = the natural order, column-major for axis 1).  In this order both axial patterns are "same line of fm tokens, up to
+// itself", i.e. the AXIAL_ROW predicate, and the token that does not exist in training (the last image token) is the last
+// in either order.  Tiles are cut per SEGMENT: text tiles start at multiples of W from 0, image tiles at T + multiples of W, so
+// an image tile is a whole number of lines and one TMA box: a contiguous run of rows for axis 0, a strided 4-D box
+// {dh, fm rows of the grid, W/fm columns, 1} (row pitch fm tokens) for axis 1.
+// ---------------------------------------------------------------------------------------------------------------------
+struct SegTiles {
+  int gather, T, n, W, nt_text, nt;
+  __device__ SegTiles(const AttnGeom& g, int W_, int n_) : gather(g.gather), T(g.text_len), n(n_), W(W_) {
+    if (gather) { nt_text = (T + W - 1) / W; nt = nt_text + g.fmap * g.fmap / W; }
+    else { nt_text = 0; nt = (n + W - 1) / W; }
+  }
+  __device__ int count() const { return nt; }
+  __device__ bool is_img(int t) const { return gather && t >= nt_text; }
+  __device__ int origin(int t) const { return (gather && t >= nt_text) ? T + (t - nt_text) * W : t * W; }
+  __device__ int limit(int t) const {           // exclusive end of the valid positions of tile t
+    const int e = origin(t) + W;
+    const int cap = (gather && t < nt_text) ? T : n;
+    return e < cap ? e : cap;
+  }
+};
+__host__ inline int seg_tile_count(const AttnGeom& g, int W, int n) {
+  return g.gather ? (g.text_len + W - 1) / W + g.fmap * g.fmap / W : (n + W - 1) / W;
+}
+
+// virtual position -> position in the token sequence (identity unless column-major)
+__device__ __forceinline__ int attn_nat(const AttnGeom& g, int u) {
+  if (!g.col || u < g.text_len) return u;
+  const int v = u - g.text_len, c = v / g.fmap, r = v - c * g.fmap;
+  return g.text_len + r * g.fmap + c;
+}
+// token position -> virtual position
+__device__ __forceinline__ int attn_virt(const AttnGeom& g, int p) {
+  if (!g.col || p < g.text_len) return p;
+  const int i = p - g.text_len, r = i / g.fmap, c = i - r * g.fmap;
+  return g.text_len + c * g.fmap + r;
+}
+// virtual position -> index into the per-(b,h) lse / delta arrays (image entries start at t_pad so that every tile's
+// statistics are one 16-byte aligned run)
+__device__ __forceinline__ int attn_sidx(const AttnGeom& g, int u) {
+  return (g.gather && u >= g.text_len) ? g.t_pad + (u - g.text_len) : u;
 }
 
 // i = absolute position of the query, j = key position.

@@ -365,10 +365,10 @@ int attn_fwd_simt_t(const db200_attn_fwd_params& p, cudaStream_t st) {
   AttnPtrs P{p.q, p.k, p.v, p.out, p.lse, p.key_mask, p.batch, p.heads};
   const AttnGeom g = make_geom(p);
   const size_t smem = (size_t)4 * 64 * LD * sizeof(float);
-  static bool attr_done = false;   // benign race: idempotent
-  if (!attr_done) {
+  static std::atomic<bool> attr_done{false};   // idempotent set-up; atomic because forward and autograd threads both launch
+  if (!attr_done.load(std::memory_order_acquire)) {
     DB200_CUDA_OK(cudaFuncSetAttribute(attn_fwd_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done.store(true, std::memory_order_release);
   }
   dim3 grid(ceil_div(p.n_q, TQ), p.batch * p.heads);
   attn_fwd_simt_kernel<T><<<grid, 256, smem, st>>>(P, g);
@@ -383,11 +383,11 @@ int attn_bwd_simt_t(const db200_attn_bwd_params& p, cudaStream_t st) {
   AttnBwdPtrs P{f.q, f.k, f.v, p.d_out, f.lse, p.delta, f.key_mask, p.cos_t, p.sin_t, p.q_scale, p.dqkv, f.batch, f.heads};
   const AttnGeom g = make_geom(f);
   const size_t smem = ((size_t)6 * 64 * LD + 128) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<bool> attr_done{false};   // idempotent set-up; atomic because forward and autograd threads both launch
+  if (!attr_done.load(std::memory_order_acquire)) {
     DB200_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DB200_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_simt_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done.store(true, std::memory_order_release);
   }
   const int total_rows = f.batch * f.heads * n;
   attn_delta_kernel<T><<<ceil_div(total_rows * 32, 256), 256, 0, st>>>(reinterpret_cast<const T*>(f.out),

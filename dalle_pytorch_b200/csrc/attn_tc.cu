@@ -11,6 +11,11 @@
 //                             more than 2^8 (lazy rescale); final O / l and the log-sum-exp are written by the same threads.
 // Three CTAs fit per SM (48 KB smem, 128 TMEM columns each), so one CTA's softmax overlaps the others' MMAs.
 //
+// Axial row / column attention runs the same kernels in "gathered" mode (attn_common.cuh: virtual axis-major order, tiles cut per
+// segment): an image query tile is four whole lines of the 32 x 32 grid and needs the text key tiles plus its own 128 keys --
+// 7 key tiles instead of the ~12 a causal sweep over the token sequence touches for the column pattern -- and for axis 1 the Q / K /
+// V / dO tiles are fetched as strided 4-D / 5-D TMA boxes ({dh, 32 image rows at a pitch of 32 tokens, 4 columns, (b,h)}).
+//
 // Backward: delta = rowsum(dO*O), then a dK/dV kernel (CTA = 128 keys, loops over query tiles, works on the transposed
 // score tile so that thread = key row) and a dQ kernel (CTA = 128 queries, loops over key tiles); both recompute P from
 // the saved log-sum-exp, keep P / dS in TMEM as the A operand of the second-stage MMAs, and fold the rotary adjoint and
@@ -116,7 +121,9 @@ struct FwdSmem {
 
 template <bool P_TMEM>
 __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                                                          const __grid_constant__ CUtensorMap tmV, FwdArgs P, AttnGeom g) {
+                                                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQg,
+                                                          const __grid_constant__ CUtensorMap tmKg, const __grid_constant__ CUtensorMap tmVg,
+                                                          FwdArgs P, AttnGeom g) {
   using L = FwdSmem<P_TMEM>;
   extern __shared__ uint8_t smem_raw[];
   pdl_launch();
@@ -133,14 +140,18 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
   const int bh = blockIdx.y, b = bh / P.heads, h = bh - b * P.heads;
   // heaviest query tiles first: with a causal pattern the last tile of a head does the most key tiles; scheduling it first
   // keeps the final partial wave short
-  const int q0 = (gridDim.x - 1 - blockIdx.x) * TQ;
+  const SegTiles SQ(g, TQ, g.n_q), SK(g, FK, g.n_k);
+  const int qt = gridDim.x - 1 - blockIdx.x;
+  const int q0 = SQ.origin(qt), q_lim = SQ.limit(qt);       // valid queries of this tile: [q0, q_lim)
   const int off = g.n_k - g.n_q;
-  const int q_last = min(q0 + TQ, g.n_q) - 1;
-  const int nkt = (g.n_k + FK - 1) / FK;
-  auto needed = [&](int kt) { return attn_tile_needed(g, q0 + off, q_last + off, kt * FK, min(kt * FK + FK, g.n_k) - 1); };
+  const int q_last = q_lim - 1;
+  const int nkt = SK.count();
+  const int rows_q = g.gather ? g.n_alloc : g.n_q, rows_k = g.gather ? g.n_alloc : g.n_k;   // rows per (b,h) of q / k,v
+  auto needed = [&](int kt) { return attn_tile_needed(g, q0 + off, q_last + off, SK.origin(kt), SK.limit(kt) - 1); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    if (g.col) { tma_prefetch_desc(&tmQg); tma_prefetch_desc(&tmKg); tma_prefetch_desc(&tmVg); }
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
     mbar_init(s_full, 1); mbar_init(p_ready, 128); mbar_init(o_done, 1);
@@ -158,15 +169,23 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       mbar_expect_tx(q_full, TILE_BYTES);
-      tma_load_2d(sQ, &tmQ, q_full, 0, bh * g.n_q + q0);
+      if (g.col && SQ.is_img(qt)) tma_load_4d(sQ, &tmQg, q_full, 0, 0, (q0 - g.text_len) / g.fmap, bh);   // 4 image columns, all rows
+      else tma_load_2d(sQ, &tmQ, q_full, 0, bh * rows_q + q0);
       int it = 0;
       for (int kt = 0; kt < nkt; ++kt) {
         if (!needed(kt)) continue;
         const int s = it & 1;
+        const int k0 = SK.origin(kt);
         mbar_wait(kv_empty + 8 * s, ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(kv_full + 8 * s, 2 * FK_BYTES);
-        tma_load_2d(sK + s * FK_BYTES, &tmK, kv_full + 8 * s, 0, bh * g.n_k + kt * FK);
-        tma_load_2d(sV + s * FK_BYTES, &tmV, kv_full + 8 * s, 0, bh * g.n_k + kt * FK);
+        if (g.col && SK.is_img(kt)) {
+          const int c0 = (k0 - g.text_len) / g.fmap;
+          tma_load_4d(sK + s * FK_BYTES, &tmKg, kv_full + 8 * s, 0, 0, c0, bh);
+          tma_load_4d(sV + s * FK_BYTES, &tmVg, kv_full + 8 * s, 0, 0, c0, bh);
+        } else {
+          tma_load_2d(sK + s * FK_BYTES, &tmK, kv_full + 8 * s, 0, bh * rows_k + k0);
+          tma_load_2d(sV + s * FK_BYTES, &tmV, kv_full + 8 * s, 0, bh * rows_k + k0);
+        }
         ++it;
       }
     }
@@ -237,11 +256,11 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
     int it = 0;
     for (int kt = 0; kt < nkt; ++kt) {
       if (!needed(kt)) continue;
-      const int k0 = kt * FK, k1 = min(k0 + FK, g.n_k) - 1;
+      const int k0 = SK.origin(kt), k1 = SK.limit(kt) - 1;
       const bool full = (k1 - k0 == FK - 1) && km == nullptr && attn_tile_full(g, q0 + off, q_last + off, k0, k1);
       Mask128 mk = {{0xffffffffu, 0xffffffffu, 0u, 0u}};
       if (!full) {
-        if (qi < g.n_q) mk = attn_row_bits(g, qi + off, k0, km, FK);
+        if (qi < q_lim) mk = attn_row_bits(g, qi + off, k0, km, k1 - k0 + 1);
         else mk.w[0] = mk.w[1] = 0u;
       }
       mbar_wait(s_full, it & 1);                   // also implies the previous tile's O += P V has completed (in-order pipe)
@@ -312,8 +331,8 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
 #pragma unroll
         for (int i = 0; i < 32; ++i) r[i] = 0u;
       }
-      if (qi < g.n_q) {
-        bf16* orow = P.out + ((long long)b * g.n_q + qi) * inner + h * DH + c * 32;
+      if (qi < q_lim) {
+        bf16* orow = P.out + ((long long)b * g.n_q + attn_nat(g, qi)) * inner + h * DH + c * 32;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 u;
@@ -325,7 +344,13 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
         }
       }
     }
-    if (qi < g.n_q) P.lse[(long long)bh * g.n_q + qi] = l_run > 0.f ? m_run + logf(l_run) : 0.f;
+    if (qi < q_lim) P.lse[(long long)bh * g.n_stat + attn_sidx(g, qi)] = l_run > 0.f ? m_run + logf(l_run) : 0.f;
+    else if (g.gather) {
+      // padding entries of the statistics array (text tail up to t_pad, the image token that does not exist in training) are
+      // bulk-copied by the backward kernels together with real ones: keep them finite
+      if (SQ.is_img(qt)) P.lse[(long long)bh * g.n_stat + g.t_pad + (qi - g.text_len)] = 0.f;
+      else if (qi < g.t_pad) P.lse[(long long)bh * g.n_stat + qi] = 0.f;
+    }
   }
 
   tc_fence_before();
@@ -339,10 +364,15 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
 // =============================================== backward ====================================================
 // delta[b,h,i] = sum_d O[b,i,h,d] * dO[b,i,h,d].  Rows of 64 bf16 (128 B) are contiguous in (b,i,h) order: 8 lanes per row,
 // one 16-byte load of O and dO per lane, 4 rows per warp per step, 4 steps in flight.
+// Gathered mode: delta is stored like lse ([b*h, n_stat], virtual order); the thread of token 0 of every (b,h) also zeroes the
+// padding entries, and block 0 zeroes the row after the last token of dO that the strided 5-D box of the last batch reaches.
 __global__ void __launch_bounds__(256) attn_delta_tc_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ delta,
-                                                            int batch, int heads, int n) {
+                                                            int batch, int heads, int n, AttnGeom g, bf16* dO_pad_row) {
   pdl_launch();
   pdl_wait();
+  if (dO_pad_row != nullptr && blockIdx.x == 0) {
+    for (int j = threadIdx.x * 8; j < heads * DH; j += 256 * 8) *reinterpret_cast<uint4*>(dO_pad_row + j) = make_uint4(0, 0, 0, 0);
+  }
   const long long total = (long long)batch * heads * n;
   const int part = threadIdx.x & 7;
   const long long stride = (long long)gridDim.x * 32 * 4;            // rows per grid step (32 rows per 256-thread block, x4 unroll)
@@ -378,7 +408,12 @@ __global__ void __launch_bounds__(256) attn_delta_tc_kernel(const bf16* __restri
         const int h = static_cast<int>(r - bi * heads);
         const long long b = bi / n;
         const int i = static_cast<int>(bi - b * n);
-        delta[(b * heads + h) * n + i] = acc;
+        float* drow = delta + (b * heads + h) * (long long)g.n_stat;
+        drow[attn_sidx(g, attn_virt(g, i))] = acc;
+        if (g.gather && i == 0) {
+          for (int s = g.text_len; s < g.t_pad; ++s) drow[s] = 0.f;
+          if (n < g.text_len + g.fmap * g.fmap) drow[g.n_stat - 1] = 0.f;
+        }
       }
     }
   }
@@ -484,6 +519,8 @@ struct DkvSmem {
 
 __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                                                               const __grid_constant__ CUtensorMap tmQg, const __grid_constant__ CUtensorMap tmKg,
+                                                               const __grid_constant__ CUtensorMap tmVg, const __grid_constant__ CUtensorMap tmdOg,
                                                                BwdArgs P, AttnGeom g) {
   using L = DkvSmem;
   extern __shared__ uint8_t smem_raw[];
@@ -501,14 +538,18 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / P.heads, h = bh - b * P.heads;
   const int n = g.n_k, inner = P.heads * DH;
-  const int k0 = blockIdx.x * TK, k1 = min(k0 + TK, n) - 1;
-  const int nqt = (n + BW - 1) / BW;
-  auto needed = [&](int qt) { return attn_tile_needed(g, qt * BW, min(qt * BW + BW, n) - 1, k0, k1); };
+  const SegTiles SK(g, TK, n), SQ(g, BW, n);
+  const int ktile = blockIdx.x;
+  const int k0 = SK.origin(ktile), k_lim = SK.limit(ktile), k1 = k_lim - 1;     // valid keys of this CTA: [k0, k_lim)
+  const int nqt = SQ.count();
+  const int rows = g.gather ? g.n_alloc : n;                                   // rows per (b,h) of q / k / v
+  auto needed = [&](int qt) { return attn_tile_needed(g, SQ.origin(qt), SQ.limit(qt) - 1, k0, k1); };
   // per-query statistics ride along with the Q / dO tiles as two 1-D bulk copies when the rows are 16-byte aligned
-  const bool stats_tma = (n & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.lse) | reinterpret_cast<uintptr_t>(P.delta)) & 15) == 0;
+  const bool stats_tma = (g.n_stat & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.lse) | reinterpret_cast<uintptr_t>(P.delta)) & 15) == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    if (g.col) { tma_prefetch_desc(&tmQg); tma_prefetch_desc(&tmKg); tma_prefetch_desc(&tmVg); tma_prefetch_desc(&tmdOg); }
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(q_full + 8 * s, 1); mbar_init(q_empty + 8 * s, 1); }
     mbar_init(st_full, 1); mbar_init(ps_ready, BWD_THREADS - 64); mbar_init(acc_done, 1);
@@ -527,20 +568,35 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(kv_full, 2 * TILE_BYTES);
-      tma_load_2d(sK, &tmK, kv_full, 0, bh * n + k0);
-      tma_load_2d(sV, &tmV, kv_full, 0, bh * n + k0);
+      if (g.col && SK.is_img(ktile)) {
+        const int c0 = (k0 - g.text_len) / g.fmap;
+        tma_load_4d(sK, &tmKg, kv_full, 0, 0, c0, bh);
+        tma_load_4d(sV, &tmVg, kv_full, 0, 0, c0, bh);
+      } else {
+        tma_load_2d(sK, &tmK, kv_full, 0, bh * rows + k0);
+        tma_load_2d(sV, &tmV, kv_full, 0, bh * rows + k0);
+      }
       int it = 0;
       for (int qt = 0; qt < nqt; ++qt) {
         if (!needed(qt)) continue;
         const int s = it & 1;
+        const int qq0 = SQ.origin(qt);
         mbar_wait(q_empty + 8 * s, ((it >> 1) & 1) ^ 1);
-        const uint32_t stat_bytes = stats_tma ? static_cast<uint32_t>(min(BW, n - qt * BW)) * 4u : 0u;
+        // (gathered mode: the statistics arrays are padded so that a full 64-entry run exists behind every tile origin)
+        const uint32_t stat_bytes = stats_tma ? static_cast<uint32_t>(g.gather ? BW : min(BW, n - qq0)) * 4u : 0u;
         mbar_expect_tx(q_full + 8 * s, 2 * HALF_TILE + 2 * stat_bytes);
-        tma_load_2d(sQ + s * HALF_TILE, &tmQ, q_full + 8 * s, 0, bh * n + qt * BW);
-        tma_load_2d(sdO + s * HALF_TILE, &tmdO, q_full + 8 * s, h * DH, b * n + qt * BW);
+        if (g.col && SQ.is_img(qt)) {
+          const int c0 = (qq0 - g.text_len) / g.fmap;
+          tma_load_4d(sQ + s * HALF_TILE, &tmQg, q_full + 8 * s, 0, 0, c0, bh);
+          tma_load_5d(sdO + s * HALF_TILE, &tmdOg, q_full + 8 * s, 0, 0, c0, h, b);
+        } else {
+          tma_load_2d(sQ + s * HALF_TILE, &tmQ, q_full + 8 * s, 0, bh * rows + qq0);
+          tma_load_2d(sdO + s * HALF_TILE, &tmdO, q_full + 8 * s, h * DH, b * n + qq0);
+        }
         if (stats_tma) {
-          bulk_load_1d(smem_u32(s_lse + s * BW), P.lse + (long long)bh * n + qt * BW, stat_bytes, q_full + 8 * s);
-          bulk_load_1d(smem_u32(s_delta + s * BW), P.delta + (long long)bh * n + qt * BW, stat_bytes, q_full + 8 * s);
+          const long long so = (long long)bh * g.n_stat + attn_sidx(g, qq0);
+          bulk_load_1d(smem_u32(s_lse + s * BW), P.lse + so, stat_bytes, q_full + 8 * s);
+          bulk_load_1d(smem_u32(s_delta + s * BW), P.delta + so, stat_bytes, q_full + 8 * s);
         }
         ++it;
       }
@@ -608,26 +664,27 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
     const int kj = k0 + row;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const uint8_t* km = P.key_mask ? P.key_mask + (long long)b * n : nullptr;
-    const bool key_ok = kj < n && (km == nullptr || km[kj] != 0);
+    const bool key_ok = kj < k_lim && (km == nullptr || km[kj] != 0);
     int it = 0;
     for (int qt = 0; qt < nqt; ++qt) {
       if (!needed(qt)) continue;
       const int s = it & 1;
-      const int qq0 = qt * BW, qq1 = min(qq0 + BW, n) - 1;
+      const int qq0 = SQ.origin(qt), qq1 = SQ.limit(qt) - 1;
       if (stats_tma) {
         mbar_wait(q_full + 8 * s, (it >> 1) & 1);
       } else {
         if (chunk == 0 && row < BW) {   // per-query statistics of this tile -> smem
           const int qi = qq0 + row;
-          s_lse[s * BW + row] = qi < n ? P.lse[(long long)bh * n + qi] : 0.f;
-          s_delta[s * BW + row] = qi < n ? P.delta[(long long)bh * n + qi] : 0.f;
+          const long long so = (long long)bh * g.n_stat + attn_sidx(g, qi);
+          s_lse[s * BW + row] = qi <= qq1 ? P.lse[so] : 0.f;
+          s_delta[s * BW + row] = qi <= qq1 ? P.delta[so] : 0.f;
         }
         named_bar_sync(1, BWD_THREADS - 64);
       }
       const bool full = (k1 - k0 == TK - 1) && (qq1 - qq0 == BW - 1) && km == nullptr && attn_tile_full(g, qq0, qq1, k0, k1);
       uint32_t mb = 0xffffffffu;
       if (!full) {
-        if (key_ok) { const Mask128 mk = attn_col_bits(g, kj, qq0, n, BW); mb = chunk == 0 ? mk.w[0] : mk.w[1]; }
+        if (key_ok) { const Mask128 mk = attn_col_bits(g, kj, qq0, n, qq1 - qq0 + 1); mb = chunk == 0 ? mk.w[0] : mk.w[1]; }
         else mb = 0u;
       }
       ATTN_DBG(threadIdx.x == 64 ? 4 : 8);                   // softmax: masks ready, waiting for S^T / dP^T
@@ -667,12 +724,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
     if (it > 0) {
       mbar_wait(acc_done, (it - 1) & 1);
       tc_fence_after();
-      bf16* rowp = P.dqkv + ((long long)b * n + (kj < n ? kj : 0)) * (3 * inner) + h * DH;
-      const float* cr = P.cos_t ? P.cos_t + (long long)(kj < n ? kj : 0) * (DH / 2) : nullptr;
-      const float* sr = P.sin_t ? P.sin_t + (long long)(kj < n ? kj : 0) * (DH / 2) : nullptr;
-      store_grad_row(tacc + lane_off, rowp + sel * inner, cr, sr, 1.0f, kj < n);
-    } else if (kj < n) {
-      bf16* rowp = P.dqkv + ((long long)b * n + kj) * (3 * inner) + h * DH;
+      const int pk = kj < k_lim ? attn_nat(g, kj) : 0;                 // token position of this key row
+      bf16* rowp = P.dqkv + ((long long)b * n + pk) * (3 * inner) + h * DH;
+      const float* cr = P.cos_t ? P.cos_t + (long long)pk * (DH / 2) : nullptr;
+      const float* sr = P.sin_t ? P.sin_t + (long long)pk * (DH / 2) : nullptr;
+      store_grad_row(tacc + lane_off, rowp + sel * inner, cr, sr, 1.0f, kj < k_lim);
+    } else if (kj < k_lim) {
+      bf16* rowp = P.dqkv + ((long long)b * n + attn_nat(g, kj)) * (3 * inner) + h * DH;
       for (int d = 0; d < DH; d += 8) *reinterpret_cast<uint4*>(rowp + sel * inner + d) = make_uint4(0, 0, 0, 0);
     }
   }
@@ -696,6 +754,8 @@ struct DqSmem {
 
 __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                                                              const __grid_constant__ CUtensorMap tmQg, const __grid_constant__ CUtensorMap tmKg,
+                                                              const __grid_constant__ CUtensorMap tmVg, const __grid_constant__ CUtensorMap tmdOg,
                                                               BwdArgs P, AttnGeom g) {
   using L = DqSmem;
   extern __shared__ uint8_t smem_raw[];
@@ -711,12 +771,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / P.heads, h = bh - b * P.heads;
   const int n = g.n_k, inner = P.heads * DH;
-  const int q0 = (gridDim.x - 1 - blockIdx.x) * TQ, q1 = min(q0 + TQ, n) - 1;   // heaviest (causal) tiles first
-  const int nkt = (n + BW - 1) / BW;
-  auto needed = [&](int kt) { return attn_tile_needed(g, q0, q1, kt * BW, min(kt * BW + BW, n) - 1); };
+  const SegTiles SQ(g, TQ, n), SK(g, BW, n);
+  const int qtile = gridDim.x - 1 - blockIdx.x;                                // heaviest (causal) tiles first
+  const int q0 = SQ.origin(qtile), q_lim = SQ.limit(qtile), q1 = q_lim - 1;     // valid queries of this CTA: [q0, q_lim)
+  const int nkt = SK.count();
+  const int rows = g.gather ? g.n_alloc : n;
+  auto needed = [&](int kt) { return attn_tile_needed(g, q0, q1, SK.origin(kt), SK.limit(kt) - 1); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    if (g.col) { tma_prefetch_desc(&tmQg); tma_prefetch_desc(&tmKg); tma_prefetch_desc(&tmVg); tma_prefetch_desc(&tmdOg); }
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
     mbar_init(s_full, 1); mbar_init(ds_ready, BWD_THREADS - 64); mbar_init(acc_done, 1);
@@ -733,16 +797,29 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(q_full, 2 * TILE_BYTES);
-      tma_load_2d(sQ, &tmQ, q_full, 0, bh * n + q0);
-      tma_load_2d(sdO, &tmdO, q_full, h * DH, b * n + q0);
+      if (g.col && SQ.is_img(qtile)) {
+        const int c0 = (q0 - g.text_len) / g.fmap;
+        tma_load_4d(sQ, &tmQg, q_full, 0, 0, c0, bh);
+        tma_load_5d(sdO, &tmdOg, q_full, 0, 0, c0, h, b);
+      } else {
+        tma_load_2d(sQ, &tmQ, q_full, 0, bh * rows + q0);
+        tma_load_2d(sdO, &tmdO, q_full, h * DH, b * n + q0);
+      }
       int it = 0;
       for (int kt = 0; kt < nkt; ++kt) {
         if (!needed(kt)) continue;
         const int s = it & 1;
+        const int k0 = SK.origin(kt);
         mbar_wait(kv_empty + 8 * s, ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(kv_full + 8 * s, 2 * HALF_TILE);
-        tma_load_2d(sK + s * HALF_TILE, &tmK, kv_full + 8 * s, 0, bh * n + kt * BW);
-        tma_load_2d(sV + s * HALF_TILE, &tmV, kv_full + 8 * s, 0, bh * n + kt * BW);
+        if (g.col && SK.is_img(kt)) {
+          const int c0 = (k0 - g.text_len) / g.fmap;
+          tma_load_4d(sK + s * HALF_TILE, &tmKg, kv_full + 8 * s, 0, 0, c0, bh);
+          tma_load_4d(sV + s * HALF_TILE, &tmVg, kv_full + 8 * s, 0, 0, c0, bh);
+        } else {
+          tma_load_2d(sK + s * HALF_TILE, &tmK, kv_full + 8 * s, 0, bh * rows + k0);
+          tma_load_2d(sV + s * HALF_TILE, &tmV, kv_full + 8 * s, 0, bh * rows + k0);
+        }
         ++it;
       }
     }
@@ -802,16 +879,17 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
     const int qi = q0 + row;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const uint8_t* km = P.key_mask ? P.key_mask + (long long)b * n : nullptr;
-    const float lse_r = qi < n ? P.lse[(long long)bh * n + qi] * LOG2E : 0.f;
-    const float delta_r = qi < n ? P.delta[(long long)bh * n + qi] : 0.f;
+    const long long so = (long long)bh * g.n_stat + attn_sidx(g, qi);
+    const float lse_r = qi < q_lim ? P.lse[so] * LOG2E : 0.f;
+    const float delta_r = qi < q_lim ? P.delta[so] : 0.f;
     int it = 0;
     for (int kt = 0; kt < nkt; ++kt) {
       if (!needed(kt)) continue;
-      const int k0 = kt * BW, k1 = min(k0 + BW, n) - 1;
+      const int k0 = SK.origin(kt), k1 = SK.limit(kt) - 1;
       const bool full = (k1 - k0 == BW - 1) && km == nullptr && attn_tile_full(g, q0, q1, k0, k1);
       uint32_t mb = 0xffffffffu;
       if (!full) {
-        if (qi < n) { const Mask128 mk = attn_row_bits(g, qi, k0, km, BW); mb = chunk == 0 ? mk.w[0] : mk.w[1]; }
+        if (qi < q_lim) { const Mask128 mk = attn_row_bits(g, qi, k0, km, k1 - k0 + 1); mb = chunk == 0 ? mk.w[0] : mk.w[1]; }
         else mb = 0u;
       }
       mbar_wait_mode(s_full, it & 1, P.wait_mode & 1);
@@ -841,13 +919,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
     if (it > 0) {
       mbar_wait(acc_done, (it - 1) & 1);
       tc_fence_after();
-      const int qs = qi < n ? qi : 0;
+      const int qs = qi < q_lim ? attn_nat(g, qi) : 0;                     // token position of this query row
       bf16* rowp = P.dqkv + ((long long)b * n + qs) * (3 * inner) + h * DH;
       const float* cr = P.cos_t ? P.cos_t + (long long)qs * (DH / 2) : nullptr;
       const float* sr = P.sin_t ? P.sin_t + (long long)qs * (DH / 2) : nullptr;
-      store_grad_cols(tdQ + lane_off, rowp, cr, sr, P.q_scale, qi < n, chunk);    // q = rot(x) * scale (attention.py:69)
-    } else if (qi < n) {
-      bf16* rowp = P.dqkv + ((long long)b * n + qi) * (3 * inner) + h * DH + chunk * 32;
+      store_grad_cols(tdQ + lane_off, rowp, cr, sr, P.q_scale, qi < q_lim, chunk);    // q = rot(x) * scale (attention.py:69)
+    } else if (qi < q_lim) {
+      bf16* rowp = P.dqkv + ((long long)b * n + attn_nat(g, qi)) * (3 * inner) + h * DH + chunk * 32;
       for (int d = 0; d < 32; d += 8) *reinterpret_cast<uint4*>(rowp + d) = make_uint4(0, 0, 0, 0);
     }
   }
@@ -866,24 +944,51 @@ int tc_mode_env() {   // DALLE_B200_ATTN_P=smem forces the SS variant (P staged 
   return (v && !strcmp(v, "smem")) ? 1 : 0;
 }
 
+// Strided box over the image tokens of a [b*h, n_alloc, 64] tensor for axis 1: dims {dh, image row r, image column c, (b,h)},
+// pitches {1, fm, 1, n_alloc} tokens -- the box {64, fm, W/fm, 1} lands in shared memory with the image ROW as the faster index,
+// i.e. as W consecutive tokens of the column-major virtual order (attn_common.cuh).
+int make_gather_map_qkv(CUtensorMap* map, const void* base, const AttnGeom& g, uint64_t bh, int W) {
+  const uint64_t fm = g.fmap;
+  const uint64_t dims[4] = {DH, fm, fm, bh};
+  const uint64_t strides[4] = {1, fm * DH, DH, (uint64_t)g.n_alloc * DH};
+  const uint32_t box[4] = {DH, (uint32_t)fm, (uint32_t)(W / fm), 1};
+  return make_tensor_map_bf16_nd(map, reinterpret_cast<const bf16*>(base) + (size_t)g.text_len * DH, 4, dims, strides, box);
+}
+// the same box over the [b, n, heads*64] gradient of the attention output: dims {dh, r, c, head, batch}
+int make_gather_map_do(CUtensorMap* map, const void* base, const AttnGeom& g, int batch, int heads, int n, int W) {
+  const uint64_t fm = g.fmap, inner = (uint64_t)heads * DH;
+  const uint64_t dims[5] = {DH, fm, fm, (uint64_t)heads, (uint64_t)batch};
+  const uint64_t strides[5] = {1, fm * inner, inner, DH, (uint64_t)n * inner};
+  const uint32_t box[5] = {DH, (uint32_t)fm, (uint32_t)(W / fm), 1, 1};
+  return make_tensor_map_bf16_nd(map, reinterpret_cast<const bf16*>(base) + (size_t)g.text_len * inner, 5, dims, strides, box);
+}
+
 template <bool P_TMEM>
 int launch_fwd(const db200_attn_fwd_params& p, cudaStream_t st) {
   using L = FwdSmem<P_TMEM>;
   CUtensorMap tmQ, tmK, tmV;
+  const AttnGeom g = make_geom(p);
   const uint64_t bh = (uint64_t)p.batch * p.heads;
-  int rc = make_tensor_map_bf16(&tmQ, p.q, DH, bh * p.n_q, DH, DH, TQ);
+  const uint64_t rows_q = g.gather ? g.n_alloc : p.n_q, rows_k = g.gather ? g.n_alloc : p.n_k;
+  int rc = make_tensor_map_bf16(&tmQ, p.q, DH, bh * rows_q, DH, DH, TQ);
   if (rc) return rc;
-  if ((rc = make_tensor_map_bf16(&tmK, p.k, DH, bh * p.n_k, DH, DH, FK))) return rc;
-  if ((rc = make_tensor_map_bf16(&tmV, p.v, DH, bh * p.n_k, DH, DH, FK))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmK, p.k, DH, bh * rows_k, DH, DH, FK))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmV, p.v, DH, bh * rows_k, DH, DH, FK))) return rc;
+  CUtensorMap tmQg = tmQ, tmKg = tmK, tmVg = tmV;          // placeholders unless the column gather is on
+  if (g.col) {
+    if ((rc = make_gather_map_qkv(&tmQg, p.q, g, bh, TQ))) return rc;
+    if ((rc = make_gather_map_qkv(&tmKg, p.k, g, bh, FK))) return rc;
+    if ((rc = make_gather_map_qkv(&tmVg, p.v, g, bh, FK))) return rc;
+  }
   auto kern = attn_fwd_tc_kernel<P_TMEM>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<bool> attr_done{false};   // idempotent set-up; atomic because forward and autograd threads both launch
+  if (!attr_done.load(std::memory_order_acquire)) {
     DB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_done = true;
+    attr_done.store(true, std::memory_order_release);
   }
   FwdArgs A{reinterpret_cast<bf16*>(p.out), p.lse, p.key_mask, p.heads, p.batch};
-  dim3 grid(ceil_div(p.n_q, TQ), p.batch * p.heads);
-  DB200_CUDA_OK(launch_pdl(kern, grid, dim3(192), L::TOTAL, st, tmQ, tmK, tmV, A, make_geom(p)));
+  dim3 grid(seg_tile_count(g, TQ, p.n_q), p.batch * p.heads);
+  DB200_CUDA_OK(launch_pdl(kern, grid, dim3(192), L::TOTAL, st, tmQ, tmK, tmV, tmQg, tmKg, tmVg, A, g));
   DB200_LAUNCH_OK("attn_fwd_tc_kernel");
   return DB200_OK;
 }
@@ -893,6 +998,20 @@ int launch_fwd(const db200_attn_fwd_params& p, cudaStream_t st) {
 int attn_debug_timeline(long long* out, int count) {
   if (count > 256) count = 256;
   return cudaMemcpyFromSymbol(out, g_attn_dbg, sizeof(long long) * count) == cudaSuccess ? 0 : -1;
+}
+
+// Gathered axial mode (db200_attn_fwd_params::gather): what the caller must have laid out, see include/dalle_b200.h
+bool attn_gather_ok(const db200_attn_fwd_params& p, const char** why) {
+  const int fm = p.fmap, T = p.text_len;
+  const char* w = nullptr;
+  if (p.pattern != DB200_ATTN_AXIAL_ROW && p.pattern != DB200_ATTN_AXIAL_COL) w = "gather needs an axial pattern";
+  else if (p.dtype != DB200_BF16 || p.dim_head != 64) w = "gather needs bf16, dim_head 64";
+  else if (fm != 16 && fm != 32 && fm != 64) w = "gather needs fmap in {16, 32, 64}";
+  else if (p.n_q != p.n_k) w = "gather needs n_q == n_k";
+  else if (p.n_k != T + fm * fm - 1 && p.n_k != T + fm * fm) w = "gather needs the full image (n = text_len + fmap^2 [- 1])";
+  else if (p.key_mask != nullptr) w = "gather does not take a key mask";
+  if (why) *why = w;
+  return w == nullptr;
 }
 
 bool attn_tc_supported(const db200_attn_fwd_params& p) {
@@ -910,24 +1029,42 @@ int attn_bwd_tc_launch(const db200_attn_bwd_params& p, cudaStream_t st) {
   const db200_attn_fwd_params& f = p.f;
   const int n = f.n_k;
   if (!al16(p.d_out) || !al16(p.dqkv)) return set_error(DB200_ERR_BAD_ARG, "attn_bwd: d_out / dqkv must be 16-byte aligned");
+  const AttnGeom g = make_geom(f);
   // 128-row boxes for the CTA's own rows, 64-row boxes for the streamed column tiles
   CUtensorMap tmQ128, tmK128, tmV128, tmdO128, tmQ64, tmK64, tmV64, tmdO64;
   const uint64_t bh = (uint64_t)f.batch * f.heads;
   const uint64_t inner = (uint64_t)f.heads * DH;
+  const uint64_t rows = g.gather ? g.n_alloc : n;
   int rc;
-  if ((rc = make_tensor_map_bf16(&tmQ128, f.q, DH, bh * n, DH, DH, 128))) return rc;
-  if ((rc = make_tensor_map_bf16(&tmK128, f.k, DH, bh * n, DH, DH, 128))) return rc;
-  if ((rc = make_tensor_map_bf16(&tmV128, f.v, DH, bh * n, DH, DH, 128))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmQ128, f.q, DH, bh * rows, DH, DH, 128))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmK128, f.k, DH, bh * rows, DH, DH, 128))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmV128, f.v, DH, bh * rows, DH, DH, 128))) return rc;
   if ((rc = make_tensor_map_bf16(&tmdO128, p.d_out, inner, (uint64_t)f.batch * n, inner, DH, 128))) return rc;
-  if ((rc = make_tensor_map_bf16(&tmQ64, f.q, DH, bh * n, DH, DH, BW))) return rc;
-  if ((rc = make_tensor_map_bf16(&tmK64, f.k, DH, bh * n, DH, DH, BW))) return rc;
-  if ((rc = make_tensor_map_bf16(&tmV64, f.v, DH, bh * n, DH, DH, BW))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmQ64, f.q, DH, bh * rows, DH, DH, BW))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmK64, f.k, DH, bh * rows, DH, DH, BW))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmV64, f.v, DH, bh * rows, DH, DH, BW))) return rc;
   if ((rc = make_tensor_map_bf16(&tmdO64, p.d_out, inner, (uint64_t)f.batch * n, inner, DH, BW))) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
+  CUtensorMap gQ128 = tmQ128, gK128 = tmK128, gV128 = tmV128, gdO128 = tmdO128, gQ64 = tmQ64, gK64 = tmK64, gV64 = tmV64, gdO64 = tmdO64;
+  bf16* dO_pad_row = nullptr;
+  if (g.col) {
+    if ((rc = make_gather_map_qkv(&gQ128, f.q, g, bh, 128))) return rc;
+    if ((rc = make_gather_map_qkv(&gK128, f.k, g, bh, 128))) return rc;
+    if ((rc = make_gather_map_qkv(&gV128, f.v, g, bh, 128))) return rc;
+    if ((rc = make_gather_map_do(&gdO128, p.d_out, g, f.batch, f.heads, n, 128))) return rc;
+    if ((rc = make_gather_map_qkv(&gQ64, f.q, g, bh, BW))) return rc;
+    if ((rc = make_gather_map_qkv(&gK64, f.k, g, bh, BW))) return rc;
+    if ((rc = make_gather_map_qkv(&gV64, f.v, g, bh, BW))) return rc;
+    if ((rc = make_gather_map_do(&gdO64, p.d_out, g, f.batch, f.heads, n, BW))) return rc;
+    // the box of the last image column of the last batch reaches one token past the end of d_out: the caller allocates that
+    // row (include/dalle_b200.h), the delta kernel zeroes it
+    if (n < g.text_len + g.fmap * g.fmap)
+      dO_pad_row = reinterpret_cast<bf16*>(const_cast<void*>(p.d_out)) + (size_t)f.batch * n * inner;
+  }
+  static std::atomic<bool> attr_done{false};   // idempotent set-up; atomic because forward and autograd threads both launch
+  if (!attr_done.load(std::memory_order_acquire)) {
     DB200_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::TOTAL));
     DB200_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL));
-    attr_done = true;
+    attr_done.store(true, std::memory_order_release);
   }
   const int total_rows = f.batch * f.heads * n;
   {
@@ -935,16 +1072,17 @@ int attn_bwd_tc_launch(const db200_attn_bwd_params& p, cudaStream_t st) {
     const int cap = sm_count() * 8;
     if (blocks > cap) blocks = cap;
     DB200_CUDA_OK(launch_pdl(attn_delta_tc_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<const bf16*>(f.out),
-                             reinterpret_cast<const bf16*>(p.d_out), p.delta, f.batch, f.heads, n));
+                             reinterpret_cast<const bf16*>(p.d_out), p.delta, f.batch, f.heads, n, g, dO_pad_row));
   }
   DB200_LAUNCH_OK("attn_delta_tc_kernel");
   static const int wait_mode = [] { const char* v = getenv("DALLE_B200_ATTN_WAIT"); return v ? atoi(v) : 0; }();
   BwdArgs A{f.lse, p.delta, f.key_mask, p.cos_t, p.sin_t, p.q_scale, reinterpret_cast<bf16*>(p.dqkv), f.heads, f.batch, wait_mode};
-  const AttnGeom g = make_geom(f);
-  dim3 grid(ceil_div(n, TQ), f.batch * f.heads);
-  DB200_CUDA_OK(launch_pdl(attn_bwd_dkv_tc_kernel, grid, dim3(BWD_THREADS), DkvSmem::TOTAL, st, tmQ64, tmK128, tmV128, tmdO64, A, g));
+  dim3 grid(seg_tile_count(g, TQ, n), f.batch * f.heads);
+  DB200_CUDA_OK(launch_pdl(attn_bwd_dkv_tc_kernel, grid, dim3(BWD_THREADS), DkvSmem::TOTAL, st, tmQ64, tmK128, tmV128, tmdO64, gQ64, gK128, gV128,
+                           gdO64, A, g));
   DB200_LAUNCH_OK("attn_bwd_dkv_tc_kernel");
-  DB200_CUDA_OK(launch_pdl(attn_bwd_dq_tc_kernel, grid, dim3(BWD_THREADS), DqSmem::TOTAL, st, tmQ128, tmK64, tmV64, tmdO128, A, g));
+  DB200_CUDA_OK(launch_pdl(attn_bwd_dq_tc_kernel, grid, dim3(BWD_THREADS), DqSmem::TOTAL, st, tmQ128, tmK64, tmV64, tmdO128, gQ128, gK64, gV64,
+                           gdO128, A, g));
   DB200_LAUNCH_OK("attn_bwd_dq_tc_kernel");
   return DB200_OK;
 }

@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(T* __restrict__ logits, con
 template <typename T>
 __global__ void __launch_bounds__(256) qkv_rotary_kernel(const T* __restrict__ qkv, T* __restrict__ q, T* __restrict__ k, T* __restrict__ v,
                                                          const float* __restrict__ cos_t, const float* __restrict__ sin_t, int rows, int seq_n,
-                                                         int heads, int dh, int pos_offset, float q_scale) {
+                                                         int heads, int dh, int pos_offset, float q_scale, int n_alloc) {
   pdl_launch();
   pdl_wait();
   const int inner = heads * dh;
@@ -838,7 +838,13 @@ __global__ void __launch_bounds__(256) qkv_rotary_kernel(const T* __restrict__ q
     for (int i = 0; i < 8; ++i) x[i] *= q_scale;
   }
   T* base = which == 0 ? q : (which == 1 ? k : v);
-  Vec8<T>::store(base + (((long long)b * heads + head) * seq_n + p) * dh + d, x);
+  T* dst = base + (((long long)b * heads + head) * n_alloc + p) * dh + d;
+  Vec8<T>::store(dst, x);
+  if (p == seq_n - 1 && n_alloc > seq_n) {      // zero token(s) behind the sequence (gathered axial layout)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = 0.f;
+    for (int r = 1; r <= n_alloc - seq_n; ++r) Vec8<T>::store(dst + (long long)r * dh, x);
+  }
 }
 
 constexpr int CS_ROWS = 512;
@@ -1138,16 +1144,16 @@ int ce_bwd_launch(void* logits, int dtype, int rows, int vocab, const long long*
 }
 
 int qkv_rotary_launch(const void* qkv, void* q, void* k, void* v, const float* cos_t, const float* sin_t, int dtype, int rows, int seq_n, int heads,
-                      int dh, int pos_offset, float q_scale, cudaStream_t st) {
+                      int dh, int pos_offset, float q_scale, int n_alloc, cudaStream_t st) {
   if (rows == 0) return DB200_OK;
   const dim3 grid(rows, ceil_div(3 * heads * dh / 8, 256));
   if (dtype == DB200_F32)
     DB200_CUDA_OK(launch_pdl(qkv_rotary_kernel<float>, grid, dim3(256), 0, st, reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(q),
-                             reinterpret_cast<float*>(k), reinterpret_cast<float*>(v), cos_t, sin_t, rows, seq_n, heads, dh, pos_offset, q_scale));
+                             reinterpret_cast<float*>(k), reinterpret_cast<float*>(v), cos_t, sin_t, rows, seq_n, heads, dh, pos_offset, q_scale, n_alloc));
   else
     DB200_CUDA_OK(launch_pdl(qkv_rotary_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
                              reinterpret_cast<__nv_bfloat16*>(q), reinterpret_cast<__nv_bfloat16*>(k), reinterpret_cast<__nv_bfloat16*>(v), cos_t, sin_t,
-                             rows, seq_n, heads, dh, pos_offset, q_scale));
+                             rows, seq_n, heads, dh, pos_offset, q_scale, n_alloc));
   DB200_LAUNCH_OK("qkv_rotary_kernel");
   return DB200_OK;
 }

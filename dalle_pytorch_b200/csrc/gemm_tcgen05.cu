@@ -380,10 +380,10 @@ int launch_cfg_mode(const db200_gemm_params& p, cudaStream_t st) {
   else rc = make_tensor_map_bf16(&tmB, p.B, p.N, p.K, p.ldb, 64, BLOCK_K);
   if (rc) return rc;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI, A_MN, B_MN, EPI_COLS>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<bool> attr_done{false};   // idempotent set-up; atomic because forward and autograd threads both launch
+  if (!attr_done.load(std::memory_order_acquire)) {
     DB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_done = true;
+    attr_done.store(true, std::memory_order_release);
   }
   const int num_mn = ceil_div(p.M, BLOCK_M) * ceil_div(p.N, BLOCK_N);
   // split-K only where the reduction is free to express: fp32 STORE without bias into a buffer the caller has zeroed
@@ -440,7 +440,7 @@ int launch_bn(const db200_gemm_params& p, cudaStream_t st) {
 }
 
 bool device_is_sm100() {
-  static int cached[64];
+  static std::atomic<int> cached[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
   if (cached[dev] == 0) {
@@ -489,12 +489,34 @@ int make_tensor_map_bf16_impl(CUtensorMap* map, const void* base, uint64_t inner
   return DB200_OK;
 }
 
+// rank-N (2..5) bf16 tensor map: dims[0] is the contiguous dimension; strides_elems[i] (i >= 1) is the pitch of dimension i in
+// elements (need not be monotonic: the axial-column gather walks the token grid with the ROW of the image as the faster dim)
+int make_tensor_map_bf16_nd_impl(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                                 const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(DB200_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point not available");
+  if (rank < 2 || rank > 5) return set_error(DB200_ERR_BAD_ARG, "tensor map rank %d", rank);
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+  for (int i = 1; i < rank; ++i) gstride[i - 1] = strides_elems[i] * 2;
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstride, bx, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(DB200_ERR_CUDA, "cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, (int)r);
+  return DB200_OK;
+}
+
 }  // namespace
 
 namespace tc {
 int make_tensor_map_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
                          uint32_t box_outer) {
   return make_tensor_map_bf16_impl(map, base, inner, outer, ld, box_inner, box_outer);
+}
+int make_tensor_map_bf16_nd(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                            const uint32_t* box) {
+  return make_tensor_map_bf16_nd_impl(map, base, rank, dims, strides_elems, box);
 }
 }  // namespace tc
 

@@ -143,15 +143,16 @@ def attn_sublayer_forward(g: SublayerGeom, x_in, resid, ln_w, ln_b, w_qkv, w_out
     shift = g.shift_active(n)
     a1, mean, rstd = ops.ln_shift_fwd(x_in, ln_w, ln_b, g.dtype, g.text_len, g.fmap, do_ln=g.do_ln, do_shift=shift, eps=g.eps)
     wq, wo = _w(w_qkv, g.dtype), _w(w_out, g.dtype)
-    q, k, v = ops.gemm_qkv_auto(a1, wq, b, n, g.heads, g.dim_head, cos_t, sin_t, g.q_scale)
-    o, lse = ops.attn_fwd(g.attn_spec, q, k, v, key_mask)
+    lay = ops.gather_layout(g.attn_spec, g.dtype, n, g.dim_head, key_mask)      # axial row / column on the gathered kernels
+    q, k, v = ops.gemm_qkv_auto(a1, wq, b, n, g.heads, g.dim_head, cos_t, sin_t, g.q_scale, n_alloc=None if lay is None else lay.n_alloc)
+    o, lse = ops.attn_fwd(g.attn_spec, q, k, v, key_mask, lay=lay)
     keep_y = save and scale is not None
     out, y = ops.gemm_resid(o.view(b * n, -1), wo, b_out, None if resid is None else resid.contiguous().view(b * n, d),
                             None if scale is None else scale.detach().reshape(-1).contiguous(), sign, keep_y=keep_y)
     out = out.view(b, n, d)
     ctx = None
     if save:
-        ctx = (x_in, mean, rstd, a1, wq, wo, q, k, v, o, lse, y, shift)
+        ctx = (x_in, mean, rstd, a1, wq, wo, q, k, v, o, lse, y, shift, lay)
     return out, ctx
 
 
@@ -161,7 +162,7 @@ def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t
     `dres` (optional, fp32) is added to dx_in inside the LayerNorm-backward kernel (sequential executor: the residual
     branch gradient, which equals d_out).  `wslots` (optional) = (dw_qkv_out, dw_out_out): preallocated fp32 destinations
     (views into the data-parallel flat gradient buffer) the weight-gradient GEMMs write straight into."""
-    x_in, mean, rstd, a1, wq, wo, q, k, v, o, lse, y, shift = ctx
+    x_in, mean, rstd, a1, wq, wo, q, k, v, o, lse, y, shift, lay = ctx
     s_qkv, s_out = wslots if wslots is not None else (None, None)
     b, n, d = x_in.shape
     M = b * n
@@ -172,9 +173,9 @@ def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t
         dy, dscale, db_out = pre
     else:
         dy, dscale, db_out = ops.scale_bwd(d_out, y, sc, sign, g.dtype, zeroed=(pool[0], pool[1]))
-    d_o = ops.gemm_store(dy, wo, a_mn=False, b_mn=True)                                   # [M, inner]
+    d_o = ops.gemm_store(dy, wo, a_mn=False, b_mn=True, out=ops.attn_dout_buffer(lay, M, wo.shape[1], dy.device, dy.dtype))   # [M, inner]
     dw_out = ops.gemm_store(dy, o.view(M, -1), a_mn=True, b_mn=True, out_dtype=torch.float32, out=s_out)   # [d, inner]
-    dqkv = ops.attn_bwd(g.attn_spec, q, k, v, o, lse, d_o.view(b, n, -1), cos_t, sin_t, g.q_scale, key_mask)
+    dqkv = ops.attn_bwd(g.attn_spec, q, k, v, o, lse, d_o.view(b, n, -1), cos_t, sin_t, g.q_scale, key_mask, lay=lay)
     da1 = ops.gemm_store(dqkv, wq, a_mn=False, b_mn=True)                                 # [M, d]
     dw_qkv = ops.gemm_store(dqkv, a1, a_mn=True, b_mn=True, out_dtype=torch.float32, out=s_qkv)      # [3*inner, d]
     dln_w = dln_b = None

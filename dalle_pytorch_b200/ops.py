@@ -2,6 +2,7 @@
 each function fills a POD struct with device pointers and enqueues the kernel on the current CUDA stream.
 Tensors are allocated by torch (the library never owns memory)."""
 import ctypes
+import os
 
 import torch
 
@@ -191,14 +192,16 @@ FUSE_QKV_EPILOGUE = False   # True: rotary + head split inside the GEMM epilogue
 #                             B200): plain GEMM + dalle_b200_qkv_rotary streaming pass
 
 
-def gemm_qkv_auto(A, W, batch, seq_n, heads, dim_head, cos_t, sin_t, q_scale, pos_offset=0):
-    if FUSE_QKV_EPILOGUE or A.dtype != torch.bfloat16 or dim_head % 8:
+def gemm_qkv_auto(A, W, batch, seq_n, heads, dim_head, cos_t, sin_t, q_scale, pos_offset=0, n_alloc=None):
+    """n_alloc (gathered axial layout, see GatherLayout): rows per (batch, head) of the returned q/k/v, rows >= seq_n zero."""
+    if n_alloc is None and (FUSE_QKV_EPILOGUE or A.dtype != torch.bfloat16 or dim_head % 8):
         return gemm_qkv(A, W, batch, seq_n, heads, dim_head, cos_t, sin_t, q_scale, pos_offset)
     raw = gemm_store(A, W)                                      # [M, 3*h*dh]
     M = raw.shape[0]
-    qkv = torch.empty(3, batch, heads, seq_n, dim_head, device=A.device, dtype=A.dtype)
+    rows = n_alloc or seq_n
+    qkv = torch.empty(3, batch, heads, rows, dim_head, device=A.device, dtype=A.dtype)
     _lib.check(_lib.lib().dalle_b200_qkv_rotary(_p(raw), _p(qkv[0]), _p(qkv[1]), _p(qkv[2]), _p(cos_t), _p(sin_t), dt_code(A.dtype), M, seq_n,
-                                                heads, dim_head, pos_offset, q_scale, _stream()), 'qkv_rotary')
+                                                heads, dim_head, pos_offset, q_scale, rows, _stream()), 'qkv_rotary')
     _count()
     return qkv[0], qkv[1], qkv[2]
 
@@ -253,34 +256,84 @@ class AttnSpec:
         self.static_mask = static_mask      # uint8 [n, n] on device or None
 
 
-def _attn_params(spec, q, k, v, out, lse, key_mask):
+class GatherLayout:
+    """Tensor layout of the gathered axial attention kernels (include/dalle_b200.h, db200_attn_fwd_params::gather):
+    q/k/v carry n_alloc = text_len + fmap^2 rows per (batch, head) (the reference's zero pad token, attention.py:255-258, is
+    materialised as a zero row), lse/delta n_stat entries; for axis 1 the gradient of the attention output needs one spare row."""
+    __slots__ = ('n', 'n_alloc', 'n_stat', 'col', 'pad_dout')
+
+    def __init__(self, spec, n):
+        T, fm = spec.text_len, spec.fmap
+        self.n, self.n_alloc, self.n_stat = n, T + fm * fm, (T + 63) // 64 * 64 + fm * fm
+        self.col = spec.pattern == ATTN_AXIAL_COL
+        self.pad_dout = self.col and n < T + fm * fm
+
+
+GATHER_AXIAL = os.environ.get('DALLE_B200_AXIAL_GATHER', '1') != '0'    # 0: axial patterns run the dense-tile predicate kernels
+
+
+def gather_layout(spec, dtype, n, dim_head=64, key_mask=None):
+    """The gathered layout if axial attention of this shape can use it (bf16 tensor-core path, whole image), else None."""
+    if not GATHER_AXIAL or spec is None or spec.pattern not in (ATTN_AXIAL_ROW, ATTN_AXIAL_COL):
+        return None
+    if dtype != torch.bfloat16 or dim_head != 64 or key_mask is not None:
+        return None
+    if os.environ.get('DALLE_B200_ATTN', 'tc') != 'tc' or spec.fmap not in (16, 32, 64):
+        return None
+    full = spec.text_len + spec.fmap * spec.fmap
+    if n not in (full - 1, full):
+        return None
+    return GatherLayout(spec, n)
+
+
+def _attn_params(spec, q, k, v, out, lse, key_mask, lay=None):
     b, h, n_q, dh = q.shape
     n_k = k.shape[2]
+    if lay is not None:
+        assert n_q == n_k == lay.n_alloc, 'gathered layout: q/k/v must carry n_alloc rows per head'
+        n_q = n_k = lay.n
     sm = spec.static_mask
     return _lib.AttnFwdParams(batch=b, heads=h, n_q=n_q, n_k=n_k, dim_head=dh, dtype=dt_code(q.dtype), pattern=spec.pattern,
                               causal=int(spec.causal), stable=int(spec.stable), text_len=spec.text_len, fmap=spec.fmap,
-                              kernel_size=spec.kernel_size, dilation=spec.dilation, key_mask=_p(key_mask),
+                              kernel_size=spec.kernel_size, dilation=spec.dilation, gather=int(lay is not None), key_mask=_p(key_mask),
                               static_mask=_p(sm), static_ld=(sm.shape[1] if sm is not None else 0),
                               q=_p(_c(q)), k=_p(_c(k)), v=_p(_c(v)), out=_p(out), lse=_p(lse))
 
 
-def attn_fwd(spec, q, k, v, key_mask=None):
-    """q [b,h,n_q,64], k,v [b,h,n_k,64] -> out [b,n_q,h*64], lse [b,h,n_q]"""
+def attn_fwd(spec, q, k, v, key_mask=None, lay=None):
+    """q [b,h,n_q,64], k,v [b,h,n_k,64] -> out [b,n_q,h*64], lse [b,h,n_q]
+    (lay = GatherLayout: q,k,v [b,h,n_alloc,64] -> out [b,n,h*64], lse [b,h,n_stat])"""
     b, h, n_q, dh = q.shape
+    if lay is not None:
+        n_q = lay.n
     out = torch.empty(b, n_q, h * dh, device=q.device, dtype=q.dtype)
-    lse = torch.empty(b, h, n_q, device=q.device, dtype=torch.float32)
-    P = _attn_params(spec, q, k, v, out, lse, key_mask)
+    lse = torch.empty(b, h, lay.n_stat if lay is not None else n_q, device=q.device, dtype=torch.float32)
+    P = _attn_params(spec, q, k, v, out, lse, key_mask, lay)
     _lib.check(_lib.lib().dalle_b200_attn_fwd(ctypes.byref(P), _stream()), 'attn_fwd')
     _count()
     return out, lse
 
 
-def attn_bwd(spec, q, k, v, out, lse, d_out, cos_t, sin_t, q_scale, key_mask=None):
-    """-> dqkv [b*n, 3*h*64] : gradient w.r.t. the to_qkv output (rotary adjoint and q scale folded in)"""
+def attn_dout_buffer(lay, rows, inner, device, dtype):
+    """[rows, inner] destination for the gradient of the attention output; with the column gather the buffer carries the spare
+    row the strided box of the last batch reaches (the library zeroes it)."""
+    if lay is not None and lay.pad_dout:
+        return torch.empty(rows + 1, inner, device=device, dtype=dtype)[:rows]
+    return torch.empty(rows, inner, device=device, dtype=dtype)
+
+
+def attn_bwd(spec, q, k, v, out, lse, d_out, cos_t, sin_t, q_scale, key_mask=None, lay=None):
+    """-> dqkv [b*n, 3*h*64] : gradient w.r.t. the to_qkv output (rotary adjoint and q scale folded in).
+    With a GatherLayout whose pad_dout is set, d_out must come from attn_dout_buffer()."""
     b, h, n, dh = q.shape
+    if lay is not None:
+        n = lay.n
+        if lay.pad_dout:
+            assert d_out.untyped_storage().nbytes() - d_out.storage_offset() * d_out.element_size() >= (b * n + 1) * h * dh * d_out.element_size(), \
+                'column gather: d_out needs one spare row (ops.attn_dout_buffer)'
     dqkv = torch.empty(b * n, 3 * h * dh, device=q.device, dtype=q.dtype)
-    delta = torch.empty(b, h, n, device=q.device, dtype=torch.float32)
-    P = _lib.AttnBwdParams(f=_attn_params(spec, q, k, v, out, lse, key_mask), d_out=_p(_c(d_out)), cos_t=_p(cos_t), sin_t=_p(sin_t),
+    delta = torch.empty(b, h, lay.n_stat if lay is not None else n, device=q.device, dtype=torch.float32)
+    P = _lib.AttnBwdParams(f=_attn_params(spec, q, k, v, out, lse, key_mask, lay), d_out=_p(_c(d_out)), cos_t=_p(cos_t), sin_t=_p(sin_t),
                            q_scale=q_scale, delta=_p(delta), dqkv=_p(dqkv))
     _lib.check(_lib.lib().dalle_b200_attn_bwd(ctypes.byref(P), _stream()), 'attn_bwd')
     _count(3)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DALLE_B200_VERSION 100
+#define DALLE_B200_VERSION 110
 
 typedef enum {
   DB200_OK = 0,
@@ -157,6 +157,16 @@ int dalle_b200_gemm_select(const db200_gemm_params* p);
  * attention.py:71-76).
  * out [batch, n_q, heads*64] (merged heads, A operand of to_out), lse [batch, heads, n_q] fp32.
  * Replaces attention.py:78-96 and :271-331 (+ :147-207 for conv_like).
+ *
+ * gather != 0 (axial patterns, bf16, dim_head 64, fmap in {16,32,64}, n_q == n_k == n with n = text_len + fmap^2 [- 1], no
+ * key mask): the kernels tile the TEXT keys and each group of 128 / fmap image lines separately and, for AXIAL_COL, fetch
+ * the lines with strided TMA boxes (what attention.py:287-292 does with rearrange(..., axis = 1)).  Layout contract:
+ *   q, k, v : [batch, heads, n_alloc, 64] with n_alloc = text_len + fmap^2, rows >= n ZERO (the reference pads the
+ *             sequence with a zero token, attention.py:255-258; dalle_b200_qkv_rotary writes this layout);
+ *   lse, delta : [batch, heads, n_stat] with n_stat = roundup(text_len, 64) + fmap^2 (library-internal ordering);
+ *   d_out (backward, AXIAL_COL, n = text_len + fmap^2 - 1): one extra row of heads*64 elements must exist after the last
+ *             token row; the library zeroes it.
+ * Everything else (out, dqkv, the rotary tables) keeps the layouts documented here.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   int batch, heads, n_q, n_k, dim_head;
@@ -166,6 +176,7 @@ typedef struct {
   int stable;               /* stable_softmax (attention.py:27-30); alpha = 2^10 is an exact rescale, see DESIGN.md */
   int text_len, fmap;
   int kernel_size, dilation;            /* CONV_LIKE */
+  int gather;               /* AXIAL_ROW / AXIAL_COL, bf16, training shapes only: gathered axial tiling, see below */
   const uint8_t* key_mask;  /* optional [batch, n_k] 1 = keep (attention.py:80-83) */
   const uint8_t* static_mask; int64_t static_ld;   /* STATIC: [n, static_ld] 1 = allowed */
   const void* q; const void* k; const void* v;
@@ -209,9 +220,11 @@ int dalle_b200_scale_bwd(const db200_scale_bwd_params* p, void* stream);
 int dalle_b200_colsum(const void* x, int dtype, int rows, int cols, float* out, void* stream);
 
 /* Head split + rotary(q,k,v) + q scale as a streaming pass over the plain to_qkv output (the same math as EPI_QKV,
- * attention.py:63-69): qkv [rows, 3*heads*dim_head] -> q,k,v [rows/seq_n, heads, seq_n, dim_head] (dtype) */
+ * attention.py:63-69): qkv [rows, 3*heads*dim_head] -> q,k,v [rows/seq_n, heads, n_alloc, dim_head] (dtype).
+ * n_alloc >= seq_n rows are laid out per (batch, head) (0 = seq_n); rows seq_n .. n_alloc-1 are written as zeros (the zero
+ * token the reference's axial attention pads with, attention.py:255-258). */
 int dalle_b200_qkv_rotary(const void* qkv, void* q, void* k, void* v, const float* cos_t, const float* sin_t, int dtype, int rows, int seq_n,
-                          int heads, int dim_head, int pos_offset, float q_scale, void* stream);
+                          int heads, int dim_head, int pos_offset, float q_scale, int n_alloc, void* stream);
 
 /* GEGLU adjoint as a streaming pass: dh [rows, hidden], u = [a|g] [rows, 2*hidden] -> du [rows, 2*hidden] (dtype);
  * dbias [2*hidden] fp32 (optional, +=) receives the column sums of du = gradient of net.0.bias (transformer.py:106-115) */

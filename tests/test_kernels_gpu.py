@@ -402,3 +402,73 @@ def test_ln_shift_bwd_fused_upstream_scale_adjoint(dtype):
     report('fused dscale', dsc1, dsc0, tol, tol * float(dsc0.abs().max()))
     report('fused dbias', dbi1, dbi0, tol, tol * float(dbi0.abs().max()))
     report('dgamma', dg1, dg0, 1e-4, 1e-4 * float(dg0.abs().max()))
+
+
+# ---- gathered axial attention (segment tiling + strided TMA boxes) ------------------------------------------------
+def _gather_stat_index(T, fm, n, col):
+    """token position -> index into the [b, h, n_stat] statistics arrays of the gathered kernels (attn_common.cuh)."""
+    t_pad = (T + 63) // 64 * 64
+    idx = torch.arange(n)
+    img = idx - T
+    r, c = img // fm, img % fm
+    virt = torch.where(idx < T, idx, t_pad + (c * fm + r if col else img))
+    return virt
+
+
+@pytest.mark.parametrize('kind,code', [('axial_row', 1), ('axial_col', 2)])
+@pytest.mark.parametrize('T,fm,missing', [(21, 16, 1), (64, 16, 1), (65, 16, 0), (257, 32, 1), (130, 64, 1)])
+def test_axial_gather_kernels(kind, code, T, fm, missing):
+    """Gathered axial kernels (db200_attn_fwd_params::gather) against a torch fp32 evaluation, rotary adjoint and q scale
+    included, and bit-for-bit layout checks of what the library promises about padding rows."""
+    o = ops()
+    torch.manual_seed(21)
+    b, h, dh = 2, 3, 64
+    n = T + fm * fm - missing
+    spec = o.AttnSpec(code, causal=True, text_len=T, fmap=fm)
+    lay = o.gather_layout(spec, torch.bfloat16, n)
+    assert lay is not None and lay.n_alloc == T + fm * fm and lay.col == (code == 2)
+    inner = h * dh
+    ang = torch.randn(n, 60) * 2.0
+    ang[:, 1::2] = ang[:, 0::2]                                  # pair-repeated angles (transformer.py:304-328)
+    from dalle_pytorch_b200.attention import rotary_tables
+    cos_t, sin_t = rotary_tables(ang.to(dev()), dh)
+    scale = dh ** -0.5
+    raw = _mk((b * n, 3 * inner), torch.bfloat16, 1.0)           # the to_qkv output
+    qkv = torch.full((3, b, h, lay.n_alloc, dh), float('nan'), device=dev(), dtype=torch.bfloat16)
+    from dalle_pytorch_b200 import _lib
+    import ctypes
+    _lib.check(_lib.lib().dalle_b200_qkv_rotary(o._p(raw), o._p(qkv[0]), o._p(qkv[1]), o._p(qkv[2]), o._p(cos_t), o._p(sin_t), 1, b * n, n, h, dh, 0,
+                                                scale, lay.n_alloc, o._stream()), 'qkv_rotary')
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    assert torch.isfinite(qkv.float()).all() and (qkv[:, :, :, n:] == 0).all(), 'rows behind the sequence must be written as zeros'
+    # reference: fp32 evaluation from the same bf16 operands
+    x = raw.float().view(b, n, 3, h, dh).permute(2, 0, 3, 1, 4).detach().requires_grad_()     # [3, b, h, n, dh]
+    rot = apply_rotary(ang.to(dev()), x)
+    qr, kr, vr = rot[0] * scale, rot[1], rot[2]
+    report('q layout', q[:, :, :n], qr, 2e-2, 2e-2)
+    allow = allowed_mask(kind, n, n, T, fm).to(dev())
+    want = _attn_ref(q[:, :, :n].float(), k[:, :, :n].float(), v[:, :, :n].float(), allow)
+    out, lse = o.attn_fwd(spec, q, k, v, lay=lay)
+    assert out.shape == (b, n, inner) and lse.shape == (b, h, lay.n_stat)
+    report(f'gather fwd {kind}', out.view(b, n, h, dh).permute(0, 2, 1, 3), want, 2e-2, 2e-2)
+    s = (q[:, :, :n].float() @ k[:, :, :n].float().transpose(-1, -2)).masked_fill(~allow, float('-inf'))
+    sidx = _gather_stat_index(T, fm, n, lay.col).to(dev())
+    report(f'gather lse {kind}', lse[:, :, sidx], torch.logsumexp(s, -1), 1e-2, 1e-2)
+    assert torch.isfinite(lse).all(), 'padding entries of lse must be finite (they are bulk-copied by the backward kernels)'
+    # the dense-tile predicate kernels on the same operands must agree
+    o2, lse2 = o.attn_fwd(spec, q[:, :, :n].contiguous(), k[:, :, :n].contiguous(), v[:, :, :n].contiguous())
+    report(f'gather == predicate fwd {kind}', out, o2, 1e-2, 1e-2)
+    # backward
+    g = _mk((b, n, inner), torch.bfloat16)
+    gbuf = o.attn_dout_buffer(lay, b * n, inner, dev(), torch.bfloat16)
+    gbuf.copy_(g.view(b * n, inner))
+    dqkv = o.attn_bwd(spec, q, k, v, out, lse, gbuf.view(b, n, inner), cos_t, sin_t, scale, lay=lay)
+    # reference gradient w.r.t. the to_qkv output through rotary, scale and attention
+    qa, ka, va = rot[0] * scale, rot[1], rot[2]
+    wa = _attn_ref(qa, ka, va, allow)
+    wa.backward(g.float().view(b, n, h, dh).permute(0, 2, 1, 3))
+    ref = x.grad.permute(1, 3, 0, 2, 4).reshape(b * n, 3 * inner)                     # [b*n, 3*inner]
+    scale_ref = float(ref.abs().max())
+    report(f'gather bwd {kind}', dqkv, ref, 3e-2, 3e-2 * scale_ref)
+    d2 = o.attn_bwd(spec, q[:, :, :n].contiguous(), k[:, :, :n].contiguous(), v[:, :, :n].contiguous(), o2, lse2, g, cos_t, sin_t, scale)
+    report(f'gather == predicate bwd {kind}', dqkv, d2, 1e-2, 1e-2 * scale_ref)

@@ -14,6 +14,7 @@ ap.add_argument('--backend', default='tc')
 ap.add_argument('--pattern', default='full')
 ap.add_argument('--iters', type=int, default=10)
 ap.add_argument('--batch', type=int, default=16)
+ap.add_argument('--gather', type=int, default=1, help='axial patterns: 1 = gathered kernels (default), 0 = dense-tile predicate kernels')
 args = ap.parse_args()
 os.environ['DALLE_B200_ATTN'] = args.backend
 code = {'full': 0, 'axial_row': 1, 'axial_col': 2, 'conv_like': 3}[args.pattern]
@@ -39,8 +40,15 @@ def timeit(fn):
     return s.elapsed_time(e) / args.iters
 
 
-out, lse = ops.attn_fwd(spec, q, k, v)
-t_f = timeit(lambda: ops.attn_fwd(spec, q, k, v))
-t_b = timeit(lambda: ops.attn_bwd(spec, q, k, v, out, lse, g, None, None, 1.0))
+lay = ops.gather_layout(spec, torch.bfloat16, n) if args.gather else None
+if lay is not None:
+    pad = lambda t: torch.cat([t, torch.zeros(b, h, lay.n_alloc - n, dh, device='cuda', dtype=t.dtype)], 2).contiguous()
+    q, k, v = pad(q), pad(k), pad(v)
+    gb = ops.attn_dout_buffer(lay, b * n, h * dh, q.device, q.dtype)
+    gb.copy_(g.view(b * n, h * dh))
+    g = gb.view(b, n, h * dh)
+out, lse = ops.attn_fwd(spec, q, k, v, lay=lay)
+t_f = timeit(lambda: ops.attn_fwd(spec, q, k, v, lay=lay))
+t_b = timeit(lambda: ops.attn_bwd(spec, q, k, v, out, lse, g, None, None, 1.0, lay=lay))
 fl = 4.0 * dh * pairs * b * h
-print(f'[{args.backend} {args.pattern}] fwd {t_f:.3f} ms ({fl / t_f / 1e9:.0f} TFLOP/s algorithmic)  bwd {t_b:.3f} ms ({2.5 * fl / t_b / 1e9:.0f} TFLOP/s)')
+print(f'[{args.backend} {args.pattern}{" gather" if lay is not None else ""}] fwd {t_f:.3f} ms ({fl / t_f / 1e9:.0f} TFLOP/s algorithmic)  bwd {t_b:.3f} ms ({2.5 * fl / t_b / 1e9:.0f} TFLOP/s)')
