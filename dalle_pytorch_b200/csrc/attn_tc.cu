@@ -58,6 +58,40 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 
 
+// The list of tiles a CTA streams (those the pattern needs), built ONCE by one warp into shared memory before the role split:
+// every role then walks the same compact list instead of re-evaluating the pattern predicates (integer divisions, segment
+// arithmetic) in every thread for every tile -- ncu counted ~400 of the ~600 warp-instructions per tile iteration as such
+// bookkeeping.  Entry: bits [0,16) first position of the tile, [16,24) number of valid positions - 1, bit 30 = image tile of the
+// column gather (strided TMA box), bit 31 = every (query, key) pair of the tile is allowed (no mask needed).
+constexpr int TL_CAP = 256;                   // entries (n <= 8192 with 32-wide tiles)
+__device__ __forceinline__ int tl_pos(uint32_t e) { return static_cast<int>(e & 0xffffu); }
+__device__ __forceinline__ int tl_width(uint32_t e) { return static_cast<int>((e >> 16) & 0xffu) + 1; }
+__device__ __forceinline__ bool tl_img(uint32_t e) { return (e >> 30) & 1u; }
+__device__ __forceinline__ bool tl_full(uint32_t e) { return (e >> 31) != 0u; }
+// all 32 lanes of one warp; returns the number of entries (also stored in list[TL_CAP])
+template <class Needed, class Full>
+__device__ __forceinline__ int build_tile_list(uint32_t* list, int lane, const SegTiles& S, bool col, Needed needed, Full full) {
+  int cnt = 0;
+  const int nt = S.count();
+  for (int base = 0; base < nt; base += 32) {
+    const int t = base + lane;
+    const bool ok = t < nt && needed(t);
+    const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+      if (pos < TL_CAP) {
+        const int o = S.origin(t), w = S.limit(t) - o;
+        list[pos] = static_cast<uint32_t>(o) | (static_cast<uint32_t>(w - 1) << 16) | ((col && S.is_img(t)) ? (1u << 30) : 0u) |
+                    (full(t) ? (1u << 31) : 0u);
+      }
+    }
+    cnt += __popc(bal);
+  }
+  if (cnt > TL_CAP) cnt = TL_CAP;             // (launchers refuse shapes that could exceed the capacity)
+  if (lane == 0) list[TL_CAP] = static_cast<uint32_t>(cnt);
+  return cnt;
+}
+
 struct FwdArgs {
   bf16* out; float* lse; const uint8_t* key_mask; int heads, batch;
 };
@@ -70,7 +104,7 @@ constexpr int FK_BYTES = FK * DH * 2;          // one [64 x 64] bf16 tile = 8 KB
 
 // P = exp2(S*log2e - m*log2e) for one 32-column chunk held in registers, packed to bf16x2; returns the chunk's row sum
 __device__ __forceinline__ float fwd_exp_pack(const uint32_t (&r)[32], uint32_t mb, bool skip, float mb2, uint32_t (&pk)[16]) {
-  float2 rs2 = make_float2(0.f, 0.f);
+  float2 rs2 = make_float2(0.f, 0.f), rs3 = make_float2(0.f, 0.f);     // two independent chains (a packed add has 4 cycles of latency)
   const float2 kLog2e = make_float2(LOG2E, LOG2E), nm = make_float2(-mb2, -mb2);
   if (skip) {
 #pragma unroll
@@ -80,7 +114,7 @@ __device__ __forceinline__ float fwd_exp_pack(const uint32_t (&r)[32], uint32_t 
     for (int i = 0; i < 16; ++i) {
       const float2 t = fma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), kLog2e, nm);
       const float2 p = make_float2(ex2(t.x), ex2(t.y));
-      rs2 = add2(rs2, p);
+      if (i & 1) rs3 = add2(rs3, p); else rs2 = add2(rs2, p);
       pk[i] = pack2(p.x, p.y);
     }
   } else {
@@ -88,10 +122,11 @@ __device__ __forceinline__ float fwd_exp_pack(const uint32_t (&r)[32], uint32_t 
     for (int i = 0; i < 16; ++i) {
       const float2 t = fma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), kLog2e, nm);
       const float2 p = make_float2(sel_bit(mb, 2 * i, ex2(t.x), 0.f), sel_bit(mb, 2 * i + 1, ex2(t.y), 0.f));
-      rs2 = add2(rs2, p);
+      if (i & 1) rs3 = add2(rs3, p); else rs2 = add2(rs2, p);
       pk[i] = pack2(p.x, p.y);
     }
   }
+  rs2 = add2(rs2, rs3);
   return rs2.x + rs2.y;
 }
 template <bool P_TMEM>
@@ -116,7 +151,8 @@ struct FwdSmem {
   static constexpr int V_OFF = TILE_BYTES + 2 * FK_BYTES;
   static constexpr int P_OFF = TILE_BYTES + 4 * FK_BYTES;
   static constexpr int BAR_OFF = P_OFF + (P_TMEM ? 0 : TILE_BYTES);
-  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+  static constexpr int LIST_OFF = BAR_OFF + 128;
+  static constexpr int TOTAL = LIST_OFF + (TL_CAP + 4) * 4 + 1024;
 };
 
 template <bool P_TMEM>
@@ -145,9 +181,15 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
   const int q0 = SQ.origin(qt), q_lim = SQ.limit(qt);       // valid queries of this tile: [q0, q_lim)
   const int off = g.n_k - g.n_q;
   const int q_last = q_lim - 1;
-  const int nkt = SK.count();
   const int rows_q = g.gather ? g.n_alloc : g.n_q, rows_k = g.gather ? g.n_alloc : g.n_k;   // rows per (b,h) of q / k,v
-  auto needed = [&](int kt) { return attn_tile_needed(g, q0 + off, q_last + off, SK.origin(kt), SK.limit(kt) - 1); };
+  uint32_t* tlist = reinterpret_cast<uint32_t*>(smem + L::LIST_OFF);
+  if (warp == 2) {                              // key tiles of this query tile, once per CTA (geometry only: before pdl_wait)
+    const bool no_km = P.key_mask == nullptr;
+    build_tile_list(tlist, lane, SK, g.col != 0,
+                    [&](int kt) { return attn_tile_needed(g, q0 + off, q_last + off, SK.origin(kt), SK.limit(kt) - 1); },
+                    [&](int kt) { return no_km && SK.limit(kt) - SK.origin(kt) == FK &&
+                                         attn_tile_full(g, q0 + off, q_last + off, SK.origin(kt), SK.limit(kt) - 1); });
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -162,6 +204,7 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const int n_its = static_cast<int>(tlist[TL_CAP]);
   pdl_wait();                                   // set-up above overlapped the previous kernel's tail
   const uint32_t tS = tmem, tO = tmem + 64, tP = tmem;
 
@@ -171,14 +214,13 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
       mbar_expect_tx(q_full, TILE_BYTES);
       if (g.col && SQ.is_img(qt)) tma_load_4d(sQ, &tmQg, q_full, 0, 0, (q0 - g.text_len) / g.fmap, bh);   // 4 image columns, all rows
       else tma_load_2d(sQ, &tmQ, q_full, 0, bh * rows_q + q0);
-      int it = 0;
-      for (int kt = 0; kt < nkt; ++kt) {
-        if (!needed(kt)) continue;
+      for (int it = 0; it < n_its; ++it) {
         const int s = it & 1;
-        const int k0 = SK.origin(kt);
+        const uint32_t te = tlist[it];
+        const int k0 = tl_pos(te);
         mbar_wait(kv_empty + 8 * s, ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(kv_full + 8 * s, 2 * FK_BYTES);
-        if (g.col && SK.is_img(kt)) {
+        if (tl_img(te)) {
           const int c0 = (k0 - g.text_len) / g.fmap;
           tma_load_4d(sK + s * FK_BYTES, &tmKg, kv_full + 8 * s, 0, 0, c0, bh);
           tma_load_4d(sV + s * FK_BYTES, &tmVg, kv_full + 8 * s, 0, 0, c0, bh);
@@ -186,7 +228,6 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
           tma_load_2d(sK + s * FK_BYTES, &tmK, kv_full + 8 * s, 0, bh * rows_k + k0);
           tma_load_2d(sV + s * FK_BYTES, &tmV, kv_full + 8 * s, 0, bh * rows_k + k0);
         }
-        ++it;
       }
     }
     __syncwarp();
@@ -197,12 +238,10 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
     {
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, FK, false, false);    // S = Q K^T : both K-major
       constexpr uint32_t IDESC_O = make_idesc_bf16(128, 64, false, true);     // O = P V   : A K-major (TMEM / smem), B N-major
-      auto next_needed = [&](int kt) { while (kt < nkt && !needed(kt)) ++kt; return kt; };
       mbar_wait(q_full, 0);
       const uint64_t dq = make_smem_desc(sQ, 16, 1024);
       const uint64_t dp = make_smem_desc(sP, 16, 1024);
-      int kt = next_needed(0);
-      if (kt < nkt) {
+      if (n_its > 0) {
         mbar_wait(kv_full, 0);
         tc_fence_after();
         const uint64_t dk = make_smem_desc(sK, 16, 1024);
@@ -213,11 +252,9 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
         }
         __syncwarp();
       }
-      int it = 0;
-      while (kt < nkt) {
+      for (int it = 0; it < n_its; ++it) {
         const int s = it & 1, sn = s ^ 1;
-        const int kn = next_needed(kt + 1);
-        const bool more = kn < nkt;
+        const bool more = it + 1 < n_its;
         if (more) { mbar_wait(kv_full + 8 * sn, ((it + 1) >> 1) & 1); }
         mbar_wait(p_ready, it & 1);
         tc_fence_after();
@@ -241,8 +278,6 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
           }
         }
         __syncwarp();
-        kt = kn;
-        ++it;
       }
     }
   } else {
@@ -253,11 +288,10 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const uint8_t* km = P.key_mask ? P.key_mask + (long long)b * g.n_k : nullptr;
     float m_run = -1.0e30f, l_run = 0.f;
-    int it = 0;
-    for (int kt = 0; kt < nkt; ++kt) {
-      if (!needed(kt)) continue;
-      const int k0 = SK.origin(kt), k1 = SK.limit(kt) - 1;
-      const bool full = (k1 - k0 == FK - 1) && km == nullptr && attn_tile_full(g, q0 + off, q_last + off, k0, k1);
+    for (int it = 0; it < n_its; ++it) {
+      const uint32_t te = tlist[it];
+      const int k0 = tl_pos(te), k1 = k0 + tl_width(te) - 1;
+      const bool full = tl_full(te);
       Mask128 mk = {{0xffffffffu, 0xffffffffu, 0u, 0u}};
       if (!full) {
         if (qi < q_lim) mk = attn_row_bits(g, qi + off, k0, km, k1 - k0 + 1);
@@ -275,13 +309,15 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
         uint32_t r[32];
         tmem_ld32(tS + lane_off + c * 32, r);
         tmem_ld_wait();
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // four independent chains instead of one of 32
         if (mb == 0xffffffffu) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r[i]));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, sel_bit(mb, i, __uint_as_float(r[i]), -INFINITY));
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], sel_bit(mb, i, __uint_as_float(r[i]), -INFINITY));
         }
+        mx = fmaxf(fmaxf(mx, m4[0]), fmaxf(fmaxf(m4[1], m4[2]), m4[3]));
       }
       const float m_new = (mx > m_run + RESCALE_TAU) ? mx : m_run;
       const float corr = ex2((m_run - m_new) * LOG2E);
@@ -314,10 +350,10 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
       if constexpr (P_TMEM) tmem_st_wait(); else { tmem_st_wait(); fence_proxy_async(); }
       tc_fence_before();
       mbar_arrive(p_ready);
-      ++it;
     }
     // ---- epilogue: O / l -> out[b, qi, h*64 ..] (bf16), lse ----
     const int inner = P.heads * DH;
+    const int it = n_its;
     if (it > 0) {
       mbar_wait(o_done, (it - 1) & 1);
       tc_fence_after();
@@ -348,6 +384,270 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
     else if (g.gather) {
       // padding entries of the statistics array (text tail up to t_pad, the image token that does not exist in training) are
       // bulk-copied by the backward kernels together with real ones: keep them finite
+      if (SQ.is_img(qt)) P.lse[(long long)bh * g.n_stat + g.t_pad + (qi - g.text_len)] = 0.f;
+      else if (qi < g.t_pad) P.lse[(long long)bh * g.n_stat + qi] = 0.f;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Forward, version 2: S double-buffered in tensor memory.
+//
+// In the kernel above S(i+1) = Q K(i+1)^T can only be issued after softmax(i) has written P(i) (it shares the burst with
+// O += P(i) V(i)), so every iteration of a CTA is the serial chain  S-MMA -> commit -> softmax -> arrive -> PV-MMA: ncu's
+// warp-state sampling shows the softmax warps asleep on s_full for most of their life (profiles/r02_attn_*).  Here two S
+// buffers let the MMA warp run one tile AHEAD: S(i+2) is issued together with O += P(i) V(i), S(i+1) has long completed when
+// softmax(i) ends, and the softmax warps go from tile to tile without waiting; the PV MMAs run in the shadow of the next
+// softmax.  P(i) is still written over the first half of the S buffer it was computed from (the in-order tensor pipe executes
+// O += P(i) V(i) before S(i+2) overwrites those columns).  K and V have separate 3-stage rings: a K stage is free as soon as
+// its S MMA has executed, a V stage only after its PV MMA.  One tmem read per score (the row's 64 scores stay in registers
+// between the max and the exponentials).  192 TMEM columns (256 allocated) and 64 KB of smem -> two CTAs per SM.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int F2_STAGES = 3;
+template <int FKT>
+struct Fwd2Smem {
+  static constexpr int KV_BYTES = FKT * DH * 2;
+  static constexpr int Q_OFF = 0;
+  static constexpr int K_OFF = TILE_BYTES;
+  static constexpr int V_OFF = K_OFF + F2_STAGES * KV_BYTES;
+  static constexpr int BAR_OFF = V_OFF + F2_STAGES * KV_BYTES;
+  static constexpr int LIST_OFF = BAR_OFF + 256;
+  static constexpr int TOTAL = LIST_OFF + (TL_CAP + 4) * 4 + 1024;
+};
+
+// FKT = keys per tile: 64 (192 TMEM columns, two CTAs per SM) or 32 (128 columns, four CTAs per SM = 16 softmax warps that
+// never wait for an MMA; the per-tile hand-offs double but they are off the critical path)
+template <int FKT>
+__global__ void __launch_bounds__(192, FKT == 32 ? 4 : 2) attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQg,
+                                                           const __grid_constant__ CUtensorMap tmKg, const __grid_constant__ CUtensorMap tmVg,
+                                                           FwdArgs P, AttnGeom g) {
+  using L = Fwd2Smem<FKT>;
+  constexpr int FK_BYTES = L::KV_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  pdl_launch();
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const uint32_t sQ = smem_u32(smem + L::Q_OFF), sK = smem_u32(smem + L::K_OFF), sV = smem_u32(smem + L::V_OFF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  // barriers: q_full | k_full[3] | k_empty[3] | v_full[3] | v_empty[3] | s_full[2] | p_ready[2] | o_done[2]
+  // (o_done alternates between two barriers: the softmax warps run up to two tiles ahead of the O += P V MMAs, and a parity
+  //  wait can only tell adjacent phases apart -- with one barrier per tile parity the waiter is never more than one phase off)
+  const uint32_t q_full = smem_u32(bars), k_full = smem_u32(bars + 1), k_empty = smem_u32(bars + 4), v_full = smem_u32(bars + 7);
+  const uint32_t v_empty = smem_u32(bars + 10), s_full = smem_u32(bars + 13), p_ready = smem_u32(bars + 15), o_done = smem_u32(bars + 17);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  constexpr uint32_t TMEM_COLS = FKT == 32 ? 128 : 256;   // S0 [0,FKT) | S1 [FKT,2 FKT) (P bf16 aliased on the first half of each) | O [2 FKT, 2 FKT + 64)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, b = bh / P.heads, h = bh - b * P.heads;
+  const SegTiles SQ(g, TQ, g.n_q), SK(g, FKT, g.n_k);
+  const int qt = gridDim.x - 1 - blockIdx.x;               // heaviest (causal) query tiles first
+  const int q0 = SQ.origin(qt), q_lim = SQ.limit(qt);
+  const int off = g.n_k - g.n_q;
+  const int q_last = q_lim - 1;
+  const int rows_q = g.gather ? g.n_alloc : g.n_q, rows_k = g.gather ? g.n_alloc : g.n_k;
+  uint32_t* tlist = reinterpret_cast<uint32_t*>(smem + L::LIST_OFF);
+  if (warp == 2) {                              // key tiles of this query tile, once per CTA (geometry only: before pdl_wait)
+    const bool no_km = P.key_mask == nullptr;
+    build_tile_list(tlist, lane, SK, g.col != 0,
+                    [&](int kt) { return attn_tile_needed(g, q0 + off, q_last + off, SK.origin(kt), SK.limit(kt) - 1); },
+                    [&](int kt) { return no_km && SK.limit(kt) - SK.origin(kt) == FKT &&
+                                         attn_tile_full(g, q0 + off, q_last + off, SK.origin(kt), SK.limit(kt) - 1); });
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    if (g.col) { tma_prefetch_desc(&tmQg); tma_prefetch_desc(&tmKg); tma_prefetch_desc(&tmVg); }
+    mbar_init(q_full, 1);
+    for (int s = 0; s < F2_STAGES; ++s) {
+      mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1); mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) { mbar_init(s_full + 8 * s, 1); mbar_init(p_ready + 8 * s, 128); }
+    mbar_init(o_done, 1); mbar_init(o_done + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_its = static_cast<int>(tlist[TL_CAP]);
+  pdl_wait();
+  const uint32_t tO = tmem + 2 * FKT;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      if (g.col && SQ.is_img(qt)) tma_load_4d(sQ, &tmQg, q_full, 0, 0, (q0 - g.text_len) / g.fmap, bh);
+      else tma_load_2d(sQ, &tmQ, q_full, 0, bh * rows_q + q0);
+      for (int it = 0; it < n_its; ++it) {
+        const int s = it % F2_STAGES;
+        const uint32_t ph = ((it / F2_STAGES) & 1) ^ 1;
+        const uint32_t te = tlist[it];
+        const int k0 = tl_pos(te);
+        const bool gat = tl_img(te);
+        const int c0 = gat ? (k0 - g.text_len) / g.fmap : 0, r0 = gat ? (k0 - g.text_len) - c0 * g.fmap : 0;   // (r0 != 0 only if FKT < fmap)
+        mbar_wait(k_empty + 8 * s, ph);
+        mbar_expect_tx(k_full + 8 * s, FK_BYTES);
+        if (gat) tma_load_4d(sK + s * FK_BYTES, &tmKg, k_full + 8 * s, 0, r0, c0, bh);
+        else tma_load_2d(sK + s * FK_BYTES, &tmK, k_full + 8 * s, 0, bh * rows_k + k0);
+        mbar_wait(v_empty + 8 * s, ph);
+        mbar_expect_tx(v_full + 8 * s, FK_BYTES);
+        if (gat) tma_load_4d(sV + s * FK_BYTES, &tmVg, v_full + 8 * s, 0, r0, c0, bh);
+        else tma_load_2d(sV + s * FK_BYTES, &tmV, v_full + 8 * s, 0, bh * rows_k + k0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (converged warp, elected lane) =====================================
+    constexpr uint32_t IDESC_S = make_idesc_bf16(128, FKT, false, false);
+    constexpr uint32_t IDESC_O = make_idesc_bf16(128, 64, false, true);
+    mbar_wait(q_full, 0);
+    const uint64_t dq = make_smem_desc(sQ, 16, 1024);
+    auto issue_s = [&](int j) {           // S(j) = Q K(j)^T into buffer j & 1; frees the K stage when it has executed
+      const int s = j % F2_STAGES;
+      mbar_wait(k_full + 8 * s, (j / F2_STAGES) & 1);
+      tc_fence_after();
+      const uint64_t dk = make_smem_desc(sK + s * FK_BYTES, 16, 1024);
+      const uint32_t tS = tmem + FKT * (j & 1);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) umma_bf16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
+        umma_commit(s_full + 8 * (j & 1));
+        umma_commit(k_empty + 8 * s);
+      }
+      __syncwarp();
+    };
+    if (n_its > 0) issue_s(0);
+    if (n_its > 1) issue_s(1);
+    for (int i = 0; i < n_its; ++i) {
+      const int s = i % F2_STAGES;
+      mbar_wait(v_full + 8 * s, (i / F2_STAGES) & 1);
+      mbar_wait(p_ready + 8 * (i & 1), (i >> 1) & 1);
+      tc_fence_after();
+      const uint64_t dv = make_smem_desc(sV + s * FK_BYTES, FK_BYTES, 1024);     // V tile read N-major: K = keys, N = dh
+      const uint32_t tP = tmem + FKT * (i & 1);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < FKT / 16; ++k) umma_bf16_ts(tO, tP + 8 * k, dv + 128 * k, IDESC_O, (i | k) != 0);
+        umma_commit(v_empty + 8 * s);
+        umma_commit(o_done + 8 * (i & 1));
+      }
+      __syncwarp();
+      if (i + 2 < n_its) issue_s(i + 2);
+    }
+  } else {
+    // ===================================== softmax / epilogue =====================================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int qi = q0 + row;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint8_t* km = P.key_mask ? P.key_mask + (long long)b * g.n_k : nullptr;
+    float m_run = -1.0e30f, l_run = 0.f;
+    for (int it = 0; it < n_its; ++it) {
+      const uint32_t te = tlist[it];
+      const int k0 = tl_pos(te), k1 = k0 + tl_width(te) - 1;
+      const bool full = tl_full(te);
+      Mask128 mk = {{0xffffffffu, FKT == 64 ? 0xffffffffu : 0u, 0u, 0u}};
+      if (!full) {
+        if (qi < q_lim) mk = attn_row_bits(g, qi + off, k0, km, k1 - k0 + 1);
+        else mk.w[0] = mk.w[1] = 0u;
+      }
+      const uint32_t tS = tmem + FKT * (it & 1) + lane_off;
+      mbar_wait(s_full + 8 * (it & 1), (it >> 1) & 1);
+      tc_fence_after();
+      const bool skip0 = __all_sync(0xffffffffu, mk.w[0] == 0u), skip1 = FKT == 32 || __all_sync(0xffffffffu, mk.w[1] == 0u);
+      uint32_t r0[32], r1[FKT == 64 ? 32 : 1];
+      if (!skip0) tmem_ld32(tS, r0);
+      if constexpr (FKT == 64) { if (!skip1) tmem_ld32(tS + 32, r1); }
+      tmem_ld_wait();
+      float mx = -INFINITY;
+      if (!skip0) {
+        if (mk.w[0] == 0xffffffffu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r0[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, sel_bit(mk.w[0], i, __uint_as_float(r0[i]), -INFINITY));
+        }
+      }
+      if constexpr (FKT == 64) if (!skip1) {
+        if (mk.w[1] == 0xffffffffu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r1[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, sel_bit(mk.w[1], i, __uint_as_float(r1[i]), -INFINITY));
+        }
+      }
+      const float m_new = (mx > m_run + RESCALE_TAU) ? mx : m_run;
+      const float corr = ex2((m_run - m_new) * LOG2E);
+      const float mb2 = m_new * LOG2E;
+      uint32_t pk[16];
+      float rs = fwd_exp_pack(r0, mk.w[0], skip0, mb2, pk);
+      tmem_st16(tS, pk);
+      if constexpr (FKT == 64) {
+        rs += fwd_exp_pack(r1, mk.w[1], skip1, mb2, pk);
+        tmem_st16(tS + 16, pk);
+      }
+      l_run = l_run * corr + rs;
+      m_run = m_new;
+      // ---- lazy rescale of O: needs every earlier O += P V to have executed (they run in the shadow of this softmax) ----
+      if (it > 0 && __any_sync(0xffffffffu, corr != 1.0f)) {
+        mbar_wait(o_done + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tO + lane_off + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+          tmem_st32(tO + lane_off + c * 32, r);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_ready + 8 * (it & 1));
+    }
+    // ---- epilogue: O / l -> out[b, token, h*64 ..] (bf16), lse ----
+    const int inner = P.heads * DH;
+    const int it = n_its;
+    if (it > 0) {
+      mbar_wait(o_done + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);
+      tc_fence_after();
+    }
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      if (it > 0) { tmem_ld32(tO + lane_off + c * 32, r); tmem_ld_wait(); }
+      else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      if (qi < q_lim) {
+        bf16* orow = P.out + ((long long)b * g.n_q + attn_nat(g, qi)) * inner + h * DH + c * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          u.x = pack2(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+          u.y = pack2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+          u.z = pack2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+          u.w = pack2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + 8 * j) = u;
+        }
+      }
+    }
+    if (qi < q_lim) P.lse[(long long)bh * g.n_stat + attn_sidx(g, qi)] = l_run > 0.f ? m_run + logf(l_run) : 0.f;
+    else if (g.gather) {
       if (SQ.is_img(qt)) P.lse[(long long)bh * g.n_stat + g.t_pad + (qi - g.text_len)] = 0.f;
       else if (qi < g.t_pad) P.lse[(long long)bh * g.n_stat + qi] = 0.f;
     }
@@ -514,7 +814,8 @@ struct DkvSmem {
   static constexpr int K_OFF = 0, V_OFF = TILE_BYTES, Q_OFF = 2 * TILE_BYTES, DO_OFF = 2 * TILE_BYTES + 2 * HALF_TILE;
   static constexpr int STAT_OFF = 2 * TILE_BYTES + 4 * HALF_TILE;   // lse [2][64], delta [2][64] (bulk-copied with the Q / dO tiles)
   static constexpr int BAR_OFF = STAT_OFF + 4 * BW * 4;
-  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+  static constexpr int LIST_OFF = BAR_OFF + 128;
+  static constexpr int TOTAL = LIST_OFF + (TL_CAP + 4) * 4 + 1024;
 };
 
 __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -541,9 +842,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
   const SegTiles SK(g, TK, n), SQ(g, BW, n);
   const int ktile = blockIdx.x;
   const int k0 = SK.origin(ktile), k_lim = SK.limit(ktile), k1 = k_lim - 1;     // valid keys of this CTA: [k0, k_lim)
-  const int nqt = SQ.count();
   const int rows = g.gather ? g.n_alloc : n;                                   // rows per (b,h) of q / k / v
-  auto needed = [&](int qt) { return attn_tile_needed(g, SQ.origin(qt), SQ.limit(qt) - 1, k0, k1); };
+  uint32_t* tlist = reinterpret_cast<uint32_t*>(smem + L::LIST_OFF);
+  if (warp == 2) {                              // query tiles this key tile is visible to, once per CTA (before pdl_wait)
+    const bool plain = P.key_mask == nullptr && k1 - k0 == TK - 1;
+    build_tile_list(tlist, lane, SQ, g.col != 0,
+                    [&](int qt) { return attn_tile_needed(g, SQ.origin(qt), SQ.limit(qt) - 1, k0, k1); },
+                    [&](int qt) { return plain && SQ.limit(qt) - SQ.origin(qt) == BW &&
+                                         attn_tile_full(g, SQ.origin(qt), SQ.limit(qt) - 1, k0, k1); });
+  }
   // per-query statistics ride along with the Q / dO tiles as two 1-D bulk copies when the rows are 16-byte aligned
   const bool stats_tma = (g.n_stat & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.lse) | reinterpret_cast<uintptr_t>(P.delta)) & 15) == 0;
 
@@ -561,6 +868,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const int n_its = static_cast<int>(tlist[TL_CAP]);
   pdl_wait();                                   // set-up above overlapped the previous kernel's tail
   const uint32_t tSt = tmem, tdPt = tmem + 64, tdV = tmem + 128, tdK = tmem + 192, tPt = tmem, tdSt = tmem + 64;
   const bool dbg = (P.wait_mode & 4) && blockIdx.x == 1 && blockIdx.y == 0 && (threadIdx.x == 32 || threadIdx.x == 64 || threadIdx.x == 192);
@@ -576,16 +884,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
         tma_load_2d(sK, &tmK, kv_full, 0, bh * rows + k0);
         tma_load_2d(sV, &tmV, kv_full, 0, bh * rows + k0);
       }
-      int it = 0;
-      for (int qt = 0; qt < nqt; ++qt) {
-        if (!needed(qt)) continue;
+      for (int it = 0; it < n_its; ++it) {
         const int s = it & 1;
-        const int qq0 = SQ.origin(qt);
+        const uint32_t te = tlist[it];
+        const int qq0 = tl_pos(te);
         mbar_wait(q_empty + 8 * s, ((it >> 1) & 1) ^ 1);
         // (gathered mode: the statistics arrays are padded so that a full 64-entry run exists behind every tile origin)
         const uint32_t stat_bytes = stats_tma ? static_cast<uint32_t>(g.gather ? BW : min(BW, n - qq0)) * 4u : 0u;
         mbar_expect_tx(q_full + 8 * s, 2 * HALF_TILE + 2 * stat_bytes);
-        if (g.col && SQ.is_img(qt)) {
+        if (tl_img(te)) {
           const int c0 = (qq0 - g.text_len) / g.fmap;
           tma_load_4d(sQ + s * HALF_TILE, &tmQg, q_full + 8 * s, 0, 0, c0, bh);
           tma_load_5d(sdO + s * HALF_TILE, &tmdOg, q_full + 8 * s, 0, 0, c0, h, b);
@@ -598,7 +905,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
           bulk_load_1d(smem_u32(s_lse + s * BW), P.lse + so, stat_bytes, q_full + 8 * s);
           bulk_load_1d(smem_u32(s_delta + s * BW), P.delta + so, stat_bytes, q_full + 8 * s);
         }
-        ++it;
       }
     }
     __syncwarp();
@@ -608,11 +914,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
       // in-order tensor pipe keeps the aliasing safe), so nothing but the softmax separates consecutive bursts.
       constexpr uint32_t IDESC_T = make_idesc_bf16(128, BW, false, false);    // S^T = K Q^T, dP^T = V dO^T
       constexpr uint32_t IDESC_G = make_idesc_bf16(128, 64, false, true);     // dV = P^T dO, dK = dS^T Q   (B N-major)
-      auto next_needed = [&](int qt) { while (qt < nqt && !needed(qt)) ++qt; return qt; };
       mbar_wait(kv_full, 0);
       const uint64_t dk = make_smem_desc(sK, 16, 1024), dv = make_smem_desc(sV, 16, 1024);
-      int qt = next_needed(0);
-      if (qt < nqt) {
+      if (n_its > 0) {
         mbar_wait(q_full, 0);
         tc_fence_after();
         const uint64_t dq = make_smem_desc(sQ, 16, 1024), ddo = make_smem_desc(sdO, 16, 1024);
@@ -625,11 +929,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
         }
         __syncwarp();
       }
-      int it = 0;
-      while (qt < nqt) {
+      for (int it = 0; it < n_its; ++it) {
         const int s = it & 1, sn = s ^ 1;
-        const int qn = next_needed(qt + 1);
-        const bool more = qn < nqt;
+        const bool more = it + 1 < n_its;
         if (more) { mbar_wait(q_full + 8 * sn, ((it + 1) >> 1) & 1); }        // next Q / dO tile (prefetched long ago)
         ATTN_DBG(1);
         mbar_wait_mode(ps_ready, it & 1, (P.wait_mode >> 1) & 1);
@@ -654,8 +956,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
         }
         __syncwarp();
         ATTN_DBG(3);                                         // MMA: burst issued
-        qt = qn;
-        ++it;
       }
     }
   } else {
@@ -665,11 +965,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const uint8_t* km = P.key_mask ? P.key_mask + (long long)b * n : nullptr;
     const bool key_ok = kj < k_lim && (km == nullptr || km[kj] != 0);
-    int it = 0;
-    for (int qt = 0; qt < nqt; ++qt) {
-      if (!needed(qt)) continue;
+    for (int it = 0; it < n_its; ++it) {
       const int s = it & 1;
-      const int qq0 = SQ.origin(qt), qq1 = SQ.limit(qt) - 1;
+      const uint32_t te = tlist[it];
+      const int qq0 = tl_pos(te), qq1 = qq0 + tl_width(te) - 1;
       if (stats_tma) {
         mbar_wait(q_full + 8 * s, (it >> 1) & 1);
       } else {
@@ -681,7 +980,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
         }
         named_bar_sync(1, BWD_THREADS - 64);
       }
-      const bool full = (k1 - k0 == TK - 1) && (qq1 - qq0 == BW - 1) && km == nullptr && attn_tile_full(g, qq0, qq1, k0, k1);
+      const bool full = tl_full(te);
       uint32_t mb = 0xffffffffu;
       if (!full) {
         if (key_ok) { const Mask128 mk = attn_col_bits(g, kj, qq0, n, qq1 - qq0 + 1); mb = chunk == 0 ? mk.w[0] : mk.w[1]; }
@@ -716,11 +1015,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
       tc_fence_before();
       mbar_arrive(ps_ready);
       ATTN_DBG(threadIdx.x == 64 ? 7 : 11);                  // softmax: arrived
-      ++it;
     }
     // warps 2-5 write dK, warps 6-9 write dV
     const uint32_t tacc = chunk == 0 ? tdK : tdV;
     const int sel = chunk == 0 ? 1 : 2;
+    const int it = n_its;
     if (it > 0) {
       mbar_wait(acc_done, (it - 1) & 1);
       tc_fence_after();
@@ -749,7 +1048,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
 struct DqSmem {
   static constexpr int Q_OFF = 0, DO_OFF = TILE_BYTES, K_OFF = 2 * TILE_BYTES, V_OFF = 2 * TILE_BYTES + 2 * HALF_TILE;
   static constexpr int BAR_OFF = 2 * TILE_BYTES + 4 * HALF_TILE;
-  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+  static constexpr int LIST_OFF = BAR_OFF + 128;
+  static constexpr int TOTAL = LIST_OFF + (TL_CAP + 4) * 4 + 1024;
 };
 
 __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -774,9 +1074,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
   const SegTiles SQ(g, TQ, n), SK(g, BW, n);
   const int qtile = gridDim.x - 1 - blockIdx.x;                                // heaviest (causal) tiles first
   const int q0 = SQ.origin(qtile), q_lim = SQ.limit(qtile), q1 = q_lim - 1;     // valid queries of this CTA: [q0, q_lim)
-  const int nkt = SK.count();
   const int rows = g.gather ? g.n_alloc : n;
-  auto needed = [&](int kt) { return attn_tile_needed(g, q0, q1, SK.origin(kt), SK.limit(kt) - 1); };
+  uint32_t* tlist = reinterpret_cast<uint32_t*>(smem + L::LIST_OFF);
+  if (warp == 2) {                              // key tiles of this query tile, once per CTA (before pdl_wait)
+    const bool no_km = P.key_mask == nullptr;
+    build_tile_list(tlist, lane, SK, g.col != 0,
+                    [&](int kt) { return attn_tile_needed(g, q0, q1, SK.origin(kt), SK.limit(kt) - 1); },
+                    [&](int kt) { return no_km && SK.limit(kt) - SK.origin(kt) == BW &&
+                                         attn_tile_full(g, q0, q1, SK.origin(kt), SK.limit(kt) - 1); });
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
@@ -791,6 +1097,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const int n_its = static_cast<int>(tlist[TL_CAP]);
   pdl_wait();                                   // set-up above overlapped the previous kernel's tail
   const uint32_t tS = tmem, tdP = tmem + 64, tdS = tmem + 64, tdQ = tmem + 128;
 
@@ -805,14 +1112,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
         tma_load_2d(sQ, &tmQ, q_full, 0, bh * rows + q0);
         tma_load_2d(sdO, &tmdO, q_full, h * DH, b * n + q0);
       }
-      int it = 0;
-      for (int kt = 0; kt < nkt; ++kt) {
-        if (!needed(kt)) continue;
+      for (int it = 0; it < n_its; ++it) {
         const int s = it & 1;
-        const int k0 = SK.origin(kt);
+        const uint32_t te = tlist[it];
+        const int k0 = tl_pos(te);
         mbar_wait(kv_empty + 8 * s, ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(kv_full + 8 * s, 2 * HALF_TILE);
-        if (g.col && SK.is_img(kt)) {
+        if (tl_img(te)) {
           const int c0 = (k0 - g.text_len) / g.fmap;
           tma_load_4d(sK + s * HALF_TILE, &tmKg, kv_full + 8 * s, 0, 0, c0, bh);
           tma_load_4d(sV + s * HALF_TILE, &tmVg, kv_full + 8 * s, 0, 0, c0, bh);
@@ -820,7 +1126,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
           tma_load_2d(sK + s * HALF_TILE, &tmK, kv_full + 8 * s, 0, bh * rows + k0);
           tma_load_2d(sV + s * HALF_TILE, &tmV, kv_full + 8 * s, 0, bh * rows + k0);
         }
-        ++it;
       }
     }
     __syncwarp();
@@ -828,11 +1133,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
     {   // whole warp converged; an elected lane issues (see elect_one()); software-pipelined like the dK/dV kernel
       constexpr uint32_t IDESC_S = make_idesc_bf16(128, BW, false, false);
       constexpr uint32_t IDESC_G = make_idesc_bf16(128, 64, false, true);
-      auto next_needed = [&](int kt) { while (kt < nkt && !needed(kt)) ++kt; return kt; };
       mbar_wait(q_full, 0);
       const uint64_t dq = make_smem_desc(sQ, 16, 1024), ddo = make_smem_desc(sdO, 16, 1024);
-      int kt = next_needed(0);
-      if (kt < nkt) {
+      if (n_its > 0) {
         mbar_wait(kv_full, 0);
         tc_fence_after();
         const uint64_t dk = make_smem_desc(sK, 16, 1024), dv = make_smem_desc(sV, 16, 1024);
@@ -845,11 +1148,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
         }
         __syncwarp();
       }
-      int it = 0;
-      while (kt < nkt) {
+      for (int it = 0; it < n_its; ++it) {
         const int s = it & 1, sn = s ^ 1;
-        const int kn = next_needed(kt + 1);
-        const bool more = kn < nkt;
+        const bool more = it + 1 < n_its;
         if (more) { mbar_wait(kv_full + 8 * sn, ((it + 1) >> 1) & 1); }
         mbar_wait_mode(ds_ready, it & 1, (P.wait_mode >> 1) & 1);
         tc_fence_after();
@@ -869,8 +1170,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
           }
         }
         __syncwarp();
-        kt = kn;
-        ++it;
       }
     }
   } else {
@@ -882,11 +1181,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
     const long long so = (long long)bh * g.n_stat + attn_sidx(g, qi);
     const float lse_r = qi < q_lim ? P.lse[so] * LOG2E : 0.f;
     const float delta_r = qi < q_lim ? P.delta[so] : 0.f;
-    int it = 0;
-    for (int kt = 0; kt < nkt; ++kt) {
-      if (!needed(kt)) continue;
-      const int k0 = SK.origin(kt), k1 = SK.limit(kt) - 1;
-      const bool full = (k1 - k0 == BW - 1) && km == nullptr && attn_tile_full(g, q0, q1, k0, k1);
+    for (int it = 0; it < n_its; ++it) {
+      const uint32_t te = tlist[it];
+      const int k0 = tl_pos(te), k1 = k0 + tl_width(te) - 1;
+      const bool full = tl_full(te);
       uint32_t mb = 0xffffffffu;
       if (!full) {
         if (qi < q_lim) { const Mask128 mk = attn_row_bits(g, qi, k0, km, k1 - k0 + 1); mb = chunk == 0 ? mk.w[0] : mk.w[1]; }
@@ -914,8 +1212,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dq_tc_kernel(const __
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(ds_ready);
-      ++it;
     }
+    const int it = n_its;
     if (it > 0) {
       mbar_wait(acc_done, (it - 1) & 1);
       tc_fence_after();
@@ -951,7 +1249,7 @@ int make_gather_map_qkv(CUtensorMap* map, const void* base, const AttnGeom& g, u
   const uint64_t fm = g.fmap;
   const uint64_t dims[4] = {DH, fm, fm, bh};
   const uint64_t strides[4] = {1, fm * DH, DH, (uint64_t)g.n_alloc * DH};
-  const uint32_t box[4] = {DH, (uint32_t)fm, (uint32_t)(W / fm), 1};
+  const uint32_t box[4] = {DH, (uint32_t)(W < (int)fm ? W : fm), (uint32_t)(W < (int)fm ? 1 : W / fm), 1};   // (part of) whole columns
   return make_tensor_map_bf16_nd(map, reinterpret_cast<const bf16*>(base) + (size_t)g.text_len * DH, 4, dims, strides, box);
 }
 // the same box over the [b, n, heads*64] gradient of the attention output: dims {dh, r, c, head, batch}
@@ -980,14 +1278,42 @@ int launch_fwd(const db200_attn_fwd_params& p, cudaStream_t st) {
     if ((rc = make_gather_map_qkv(&tmKg, p.k, g, bh, FK))) return rc;
     if ((rc = make_gather_map_qkv(&tmVg, p.v, g, bh, FK))) return rc;
   }
+  FwdArgs A{reinterpret_cast<bf16*>(p.out), p.lse, p.key_mask, p.heads, p.batch};
+  dim3 grid(seg_tile_count(g, TQ, p.n_q), p.batch * p.heads);
+  // DALLE_B200_ATTN_FWD = v1 (single S buffer, 64-key tiles, three CTAs per SM; default: measured fastest) | v2_64 | v2_32
+  // (double-buffered S, profiles/r02_summary.md): A/B timing
+  static const int variant = [] {
+    const char* v = getenv("DALLE_B200_ATTN_FWD");
+    return !v ? 0 : !strcmp(v, "v2_32") ? 32 : !strcmp(v, "v2_64") ? 64 : 0;
+  }();
+  if (P_TMEM && variant != 0) {
+    static std::atomic<bool> attr2_done{false};
+    if (!attr2_done.load(std::memory_order_acquire)) {
+      DB200_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem<32>::TOTAL));
+      DB200_CUDA_OK(cudaFuncSetAttribute(attn_fwd_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Smem<64>::TOTAL));
+      attr2_done.store(true, std::memory_order_release);
+    }
+    if (variant == 32) {
+      CUtensorMap k32, v32, kg32 = tmKg, vg32 = tmVg;
+      if ((rc = make_tensor_map_bf16(&k32, p.k, DH, bh * rows_k, DH, DH, 32))) return rc;
+      if ((rc = make_tensor_map_bf16(&v32, p.v, DH, bh * rows_k, DH, DH, 32))) return rc;
+      if (g.col) {
+        if ((rc = make_gather_map_qkv(&kg32, p.k, g, bh, 32))) return rc;
+        if ((rc = make_gather_map_qkv(&vg32, p.v, g, bh, 32))) return rc;
+      }
+      DB200_CUDA_OK(launch_pdl(attn_fwd_tc2_kernel<32>, grid, dim3(192), Fwd2Smem<32>::TOTAL, st, tmQ, k32, v32, tmQg, kg32, vg32, A, g));
+    } else {
+      DB200_CUDA_OK(launch_pdl(attn_fwd_tc2_kernel<64>, grid, dim3(192), Fwd2Smem<64>::TOTAL, st, tmQ, tmK, tmV, tmQg, tmKg, tmVg, A, g));
+    }
+    DB200_LAUNCH_OK("attn_fwd_tc2_kernel");
+    return DB200_OK;
+  }
   auto kern = attn_fwd_tc_kernel<P_TMEM>;
   static std::atomic<bool> attr_done{false};   // idempotent set-up; atomic because forward and autograd threads both launch
   if (!attr_done.load(std::memory_order_acquire)) {
     DB200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_done.store(true, std::memory_order_release);
   }
-  FwdArgs A{reinterpret_cast<bf16*>(p.out), p.lse, p.key_mask, p.heads, p.batch};
-  dim3 grid(seg_tile_count(g, TQ, p.n_q), p.batch * p.heads);
   DB200_CUDA_OK(launch_pdl(kern, grid, dim3(192), L::TOTAL, st, tmQ, tmK, tmV, tmQg, tmKg, tmVg, A, g));
   DB200_LAUNCH_OK("attn_fwd_tc_kernel");
   return DB200_OK;
@@ -1018,7 +1344,8 @@ bool attn_tc_supported(const db200_attn_fwd_params& p) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return false;
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-  return major == 10 && p.dtype == DB200_BF16 && p.dim_head == 64 && al16(p.q) && al16(p.k) && al16(p.v) && al16(p.out);
+  return major == 10 && p.dtype == DB200_BF16 && p.dim_head == 64 && al16(p.q) && al16(p.k) && al16(p.v) && al16(p.out) &&
+         p.n_k <= 32 * (TL_CAP - 8);      // capacity of the per-CTA tile list (32-wide key tiles)
 }
 
 int attn_fwd_tc_launch(const db200_attn_fwd_params& p, cudaStream_t st) {
