@@ -4,7 +4,7 @@ Same module API as lucidrains/DALLE-pytorch for the path (DALLE, Transformer, At
 SparseAxialCausalAttention, SparseConvCausalAttention, SparseAttention, FeedForward, ...), executed by the
 hand-written CUDA kernels of libdalle_b200.so through a C ABI (include/dalle_b200.h).
 """
-from .config import set_compute_dtype, compute_dtype, compute_dtype_ctx
+from .config import set_compute_dtype, compute_dtype, compute_dtype_ctx, set_fp32_gemm, fp32_gemm, fp32_gemm_ctx
 from .attention import Attention, SparseAxialCausalAttention, SparseConvCausalAttention, SparseAttention
 from .transformer import (Transformer, FeedForward, GEGLU, LayerScale, PreNorm, PreShiftToken, CachedAs, NonCached, DivideMax)
 from .reversible import SequentialSequence, ReversibleSequence

@@ -50,6 +50,9 @@ int qkv_rotary_launch(const void* qkv, void* q, void* k, void* v, const float* c
                       int dh, int pos_offset, float q_scale, int n_alloc, cudaStream_t st);
 int geglu_bwd_launch(const void* dh, const void* u, void* du, float* dbias, int dtype, int rows, int hidden, cudaStream_t st);
 int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st);
+int split_bf16x3_launch(const float* src, void* dst, int64_t rows, int cols, int concat_rows, int pat, cudaStream_t st);
+int resid_scale_launch(const float* y, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, cudaStream_t st);
+int geglu_fwd_launch(const float* u, float* h, int64_t rows, int hidden, cudaStream_t st);
 int axpby_launch(const float* a, const float* b, float alpha, float* y, int64_t count, cudaStream_t st);
 int sumsq_launch(const float* x, int64_t count, float* out, cudaStream_t st);
 int adam_launch(const db200_adam_params& P, cudaStream_t st);
@@ -278,6 +281,25 @@ int dalle_b200_qkv_rotary(const void* qkv, void* q, void* k, void* v, const floa
   DB200_CHECK_ARG(aligned16(qkv) && aligned16(q) && aligned16(k) && aligned16(v) && (!cos_t || (aligned16(cos_t) && aligned16(sin_t))),
                   "qkv_rotary: tensors must be 16-byte aligned");
   return qkv_rotary_launch(qkv, q, k, v, cos_t, sin_t, dtype, rows, seq_n, heads, dim_head, pos_offset, q_scale, n_alloc, (cudaStream_t)stream);
+}
+
+int dalle_b200_split_bf16x3(const float* src, void* dst, int64_t rows, int cols, int concat_rows, int operand, void* stream) {
+  DB200_CHECK_ARG(src && dst && rows >= 0 && cols > 0 && (cols & 1) == 0 && (operand == 0 || operand == 1), "split_bf16x3: bad args (cols must be even)");
+  DB200_CHECK_ARG(aligned16(src) && aligned16(dst), "split_bf16x3: tensors must be 16-byte aligned");
+  // K-block -> piece: products (a0 b0) (a0 b1) (a1 b0) (a1 b1) (a0 b2) (a2 b0)
+  // (nibble blk = piece held by K block blk)   A: a0 a0 a1 a1 a0 a2      B: b0 b1 b0 b1 b2 b0
+  const int pat = operand == 0 ? 0x201100 : 0x021010;
+  return split_bf16x3_launch(src, dst, rows, cols, concat_rows != 0, pat, (cudaStream_t)stream);
+}
+
+int dalle_b200_resid_scale(const float* y, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, void* stream) {
+  DB200_CHECK_ARG(y && out && rows >= 0 && d > 0 && (d & 1) == 0, "resid_scale: bad args (d must be even)");
+  return resid_scale_launch(y, resid, scale, sign, out, rows, d, (cudaStream_t)stream);
+}
+
+int dalle_b200_geglu_fwd(const float* u, float* h, int64_t rows, int hidden, void* stream) {
+  DB200_CHECK_ARG(u && h && rows >= 0 && hidden > 0, "geglu_fwd: bad args");
+  return geglu_fwd_launch(u, h, rows, hidden, (cudaStream_t)stream);
 }
 
 int dalle_b200_ce_fwd(const void* logits, int dtype, int rows, int vocab, const int64_t* labels, float coef, float* row_lse, float* loss_acc,

@@ -1167,6 +1167,100 @@ int colsum_launch(const void* x, int dtype, int rows, int cols, float* out, cuda
   return DB200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// fp32 GEMMs on the bf16 tensor cores (parity mode "bf16x6"): x = x0 + x1 + x2 with x0 = bf16(x), x1 = bf16(x - x0),
+// x2 = bf16(x - x0 - x1) carries 24 mantissa bits; A B^T = sum over (i,j) in {(0,0),(0,1),(1,0),(1,1),(0,2),(2,0)} of Ai Bj^T up to
+// terms of relative size 2^-24.  The six products are ONE tcgen05 GEMM over a K axis six times as long: this kernel writes the
+// pieces side by side along K in the order the operand needs (`pat` = piece index of each of the six K blocks), so
+// gemm_tcgen05_kernel, its operand-major modes and its fp32 accumulator in tensor memory are used unchanged.
+//   concat_rows == 0: src [rows, cols] -> dst [rows, 6*cols]  (K contiguous: K-major operand)
+//   concat_rows == 1: src [rows, cols] -> dst [6*rows, cols]  (K = the row index: MN-major operand)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows, int cols,
+                                                           int concat_rows, int pat) {
+  pdl_launch();
+  pdl_wait();
+  const long long total = rows * (long long)(cols >> 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (cols >> 1);
+    const int c = static_cast<int>(i - r * (cols >> 1)) * 2;
+    const float2 x = *reinterpret_cast<const float2*>(src + r * cols + c);
+    __nv_bfloat162 pc[3];
+    float2 rem = x;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      pc[k] = __floats2bfloat162_rn(rem.x, rem.y);
+      const float2 back = __bfloat1622float2(pc[k]);
+      rem.x -= back.x; rem.y -= back.y;                     // exact: the difference of x and its bf16 rounding is representable
+    }
+#pragma unroll
+    for (int blk = 0; blk < 6; ++blk) {
+      const int which = (pat >> (4 * blk)) & 0xf;
+      const long long off = concat_rows ? ((long long)blk * rows + r) * cols + c : r * (6LL * cols) + (long long)blk * cols + c;
+      *reinterpret_cast<__nv_bfloat162*>(dst + off) = pc[which];
+    }
+  }
+}
+
+// out = resid + sign * scale (.) y      (fp32; the LayerScale + residual step of EPI_RESID as a streaming pass, parity mode)
+__global__ void __launch_bounds__(256) resid_scale_kernel(const float* __restrict__ y, const float* __restrict__ resid, const float* __restrict__ scale,
+                                                          float sign, float* __restrict__ out, long long rows, int d) {
+  pdl_launch();
+  pdl_wait();
+  const long long total = rows * (long long)(d >> 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (d >> 1);
+    const int c = static_cast<int>(i - r * (d >> 1)) * 2;
+    const float2 v = *reinterpret_cast<const float2*>(y + r * d + c);
+    float s0 = sign, s1 = sign;
+    if (scale) { s0 *= scale[c]; s1 *= scale[c + 1]; }
+    float2 o = make_float2(s0 * v.x, s1 * v.y);
+    if (resid) { const float2 rr = *reinterpret_cast<const float2*>(resid + r * d + c); o.x += rr.x; o.y += rr.y; }
+    *reinterpret_cast<float2*>(out + r * d + c) = o;
+  }
+}
+
+// h = a * gelu_erf(g) with u = [a | g] [rows, 2*hidden]   (fp32; transformer.py:106-109, parity mode)
+__global__ void __launch_bounds__(256) geglu_fwd_kernel(const float* __restrict__ u, float* __restrict__ hout, long long rows, int hidden) {
+  pdl_launch();
+  pdl_wait();
+  const long long total = rows * (long long)hidden;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / hidden;
+    const int j = static_cast<int>(i - r * hidden);
+    const float a = u[r * (2LL * hidden) + j], g = u[r * (2LL * hidden) + hidden + j];
+    hout[i] = a * gelu_erf(g);
+  }
+}
+
+static int grid_for(long long work) {
+  long long blocks = (work + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  return static_cast<int>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+int split_bf16x3_launch(const float* src, void* dst, int64_t rows, int cols, int concat_rows, int pat, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return DB200_OK;
+  DB200_CUDA_OK(launch_pdl(split_bf16x3_kernel, dim3(grid_for(rows * (cols / 2))), dim3(256), 0, st, src, reinterpret_cast<__nv_bfloat16*>(dst),
+                           (long long)rows, cols, concat_rows, pat));
+  DB200_LAUNCH_OK("split_bf16x3_kernel");
+  return DB200_OK;
+}
+
+int resid_scale_launch(const float* y, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, cudaStream_t st) {
+  if (rows == 0) return DB200_OK;
+  DB200_CUDA_OK(launch_pdl(resid_scale_kernel, dim3(grid_for(rows * (d / 2))), dim3(256), 0, st, y, resid, scale, sign, out, (long long)rows, d));
+  DB200_LAUNCH_OK("resid_scale_kernel");
+  return DB200_OK;
+}
+
+int geglu_fwd_launch(const float* u, float* h, int64_t rows, int hidden, cudaStream_t st) {
+  if (rows == 0) return DB200_OK;
+  DB200_CUDA_OK(launch_pdl(geglu_fwd_kernel, dim3(grid_for(rows * hidden)), dim3(256), 0, st, u, h, (long long)rows, hidden));
+  DB200_LAUNCH_OK("geglu_fwd_kernel");
+  return DB200_OK;
+}
+
 int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st) {
   if (count == 0) return DB200_OK;
   int64_t blocks = ceil_div64(count, 256 * 4);

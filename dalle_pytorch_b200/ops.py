@@ -6,7 +6,7 @@ import os
 
 import torch
 
-from . import _lib
+from . import _lib, config
 from ._lib import (F32, BF16, EPI_STORE, EPI_QKV, EPI_RESID, EPI_GEGLU, EPI_GEGLU_BWD, GEMM_AUTO,
                    ATTN_FULL, ATTN_AXIAL_ROW, ATTN_AXIAL_COL, ATTN_CONV_LIKE, ATTN_STATIC)
 
@@ -143,10 +143,70 @@ def _base(M, N, K, A, lda, a_mn, B, ldb, b_mn, epilogue, backend=GEMM_AUTO):
                            B=_p(B), ldb=ldb, b_mn_major=int(b_mn), epilogue=epilogue)
 
 
+# ------------------------------------------------------------------------------------------------
+# fp32 parity mode on the tensor cores: "bf16x6"
+# ------------------------------------------------------------------------------------------------
+def split_bf16x3(x, operand, concat_rows):
+    """fp32 [rows, cols] -> the six-fold K-concatenated bf16 operand of dalle_b200_split_bf16x3 (operand 0 = A, 1 = B)."""
+    rows, cols = x.shape
+    dst = torch.empty((6 * rows, cols) if concat_rows else (rows, 6 * cols), device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().dalle_b200_split_bf16x3(_p(_c(x)), _p(dst), rows, cols, int(concat_rows), operand, _stream()), 'split_bf16x3')
+    _count()
+    return dst
+
+
+def _gemm_x6(A, B, a_mn, b_mn, bias, out):
+    """fp32 acc[M,N] = sum_k A(m,k) B(n,k) on gemm_tcgen05_kernel: both operands split into three bf16 pieces laid side by side
+    along K (six partial products = one GEMM with K' = 6K, fp32 accumulation in tensor memory, fp32 STORE epilogue).
+    Returns None if the shape does not qualify for the tcgen05 kernel (the caller then uses the CUDA-core kernel)."""
+    if a_mn:
+        K, M = A.shape
+    else:
+        M, K = A.shape
+    N = B.shape[1] if b_mn else B.shape[0]
+    if K % 8 or N % 8 or (a_mn and M % 8) or not (A.is_cuda and torch.cuda.get_device_capability(A.device)[0] == 10):
+        return None
+    A6 = split_bf16x3(A, 0, concat_rows=a_mn)
+    B6 = split_bf16x3(B, 1, concat_rows=b_mn)
+    P = _base(M, N, 6 * K, A6, A6.shape[1], a_mn, B6, B6.shape[1], b_mn, EPI_STORE, GEMM_AUTO)
+    C = out if out is not None else torch.empty(M, N, device=A.device, dtype=torch.float32)
+    P.C, P.ldc, P.c_dtype, P.bias, P.split_k_ok = _p(C), N, F32, _p(bias), 0
+    if _lib.lib().dalle_b200_gemm_select(ctypes.byref(P)) != _lib.GEMM_TCGEN05:
+        return None
+    _gemm(P)
+    return C
+
+
+def _use_x6(A):
+    return A.dtype == torch.float32 and config.fp32_gemm() == 'bf16x6'
+
+
+def resid_scale(y, resid, scale, sign):
+    """fp32: resid + sign * scale (.) y"""
+    M, d = y.shape
+    out = torch.empty_like(y)
+    _lib.check(_lib.lib().dalle_b200_resid_scale(_p(_c(y)), _p(resid), _p(scale), sign, _p(out), M, d, _stream()), 'resid_scale')
+    _count()
+    return out
+
+
+def geglu_fwd(u):
+    """fp32 u = [a | g] [M, 2H] -> a * gelu_erf(g) [M, H]"""
+    M, H2 = u.shape
+    h = torch.empty(M, H2 // 2, device=u.device, dtype=torch.float32)
+    _lib.check(_lib.lib().dalle_b200_geglu_fwd(_p(_c(u)), _p(h), M, H2 // 2, _stream()), 'geglu_fwd')
+    _count()
+    return h
+
+
 def gemm_store(A, B, a_mn=False, b_mn=False, out_dtype=None, bias=None, backend=GEMM_AUTO, out=None):
     """acc[M,N] = sum_k A(m,k) B(n,k).  A: [M,K] (a_mn=False) or [K,M] (a_mn=True); B: [N,K] or [K,N].
     `out` (optional, contiguous [M,N]) receives the result instead of a fresh tensor."""
     _c(A), _c(B)
+    if backend == GEMM_AUTO and _use_x6(A) and (out is None or out.dtype == torch.float32) and out_dtype in (None, torch.float32):
+        C6 = _gemm_x6(A, B, a_mn, b_mn, bias, out)
+        if C6 is not None:
+            return C6
     if a_mn:
         K, M = A.shape
     else:
@@ -179,6 +239,14 @@ def gemm_qkv(A, W, batch, seq_n, heads, dim_head, cos_t, sin_t, q_scale, pos_off
     _c(A), _c(W)
     M, K = A.shape
     N = W.shape[0]
+    if backend == GEMM_AUTO and _use_x6(A) and dim_head % 8 == 0:
+        raw = _gemm_x6(A, W, False, False, None, None)           # plain product on the tensor cores, then the streaming head split
+        if raw is not None:
+            qkv = torch.empty(3, batch, heads, seq_n, dim_head, device=A.device, dtype=A.dtype)
+            _lib.check(_lib.lib().dalle_b200_qkv_rotary(_p(raw), _p(qkv[0]), _p(qkv[1]), _p(qkv[2]), _p(cos_t), _p(sin_t), F32, M, seq_n, heads,
+                                                        dim_head, pos_offset, q_scale, seq_n, _stream()), 'qkv_rotary')
+            _count()
+            return qkv[0], qkv[1], qkv[2]
     qkv = torch.empty(3, batch, heads, seq_n, dim_head, device=A.device, dtype=A.dtype)
     P = _base(M, N, K, A, K, False, W, K, False, EPI_QKV, backend)
     P.q, P.k, P.v = _p(qkv[0]), _p(qkv[1]), _p(qkv[2])
@@ -211,6 +279,10 @@ def gemm_resid(A, W, bias, resid, scale, sign=1.0, keep_y=False, backend=GEMM_AU
     _c(A), _c(W)
     M, K = A.shape
     N = W.shape[0]
+    if backend == GEMM_AUTO and _use_x6(A):
+        y6 = _gemm_x6(A, W, False, False, bias, None)            # y = A W^T + bias
+        if y6 is not None:
+            return resid_scale(y6, resid, scale, sign), (y6 if keep_y else None)
     out = torch.empty(M, N, device=A.device, dtype=torch.float32)
     y = torch.empty(M, N, device=A.device, dtype=A.dtype) if keep_y else None
     P = _base(M, N, K, A, K, False, W, K, False, EPI_RESID, backend)
@@ -225,6 +297,10 @@ def gemm_geglu(A, W1, b1, keep_u=True, backend=GEMM_AUTO):
     M, K = A.shape
     N = W1.shape[0]
     H = N // 2
+    if backend == GEMM_AUTO and _use_x6(A):
+        u6 = _gemm_x6(A, W1, False, False, b1, None)             # u = A W1^T + b1
+        if u6 is not None:
+            return geglu_fwd(u6), (u6 if keep_u else None)
     h = torch.empty(M, H, device=A.device, dtype=A.dtype)
     u = torch.empty(M, N, device=A.device, dtype=A.dtype) if keep_u else None
     P = _base(M, N, K, A, K, False, W1, K, False, EPI_GEGLU, backend)

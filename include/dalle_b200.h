@@ -238,6 +238,19 @@ int dalle_b200_ce_fwd(const void* logits, int dtype, int rows, int vocab, const 
 int dalle_b200_ce_bwd(void* logits, int dtype, int rows, int vocab, const int64_t* labels, float coef, const float* row_lse, const float* upstream,
                       void* stream);
 
+/* fp32 GEMMs on the bf16 tensor cores ("bf16x6" parity mode): split an fp32 matrix into three bf16 pieces x0 + x1 + x2 (24
+ * mantissa bits) and lay the pieces out six times along the GEMM's K axis in the order operand A (operand = 0:
+ * a0 a0 a1 a1 a0 a2) or operand B (operand = 1: b0 b1 b0 b1 b2 b0) needs, so that ONE dalle_b200_gemm call over K' = 6K with bf16
+ * operands and an fp32 STORE result equals the fp32 product up to relative terms of 2^-24.
+ *   concat_rows = 0: src [rows, cols] fp32 -> dst [rows, 6*cols] bf16  (K-major operand: K is the contiguous axis)
+ *   concat_rows = 1: src [rows, cols] fp32 -> dst [6*rows, cols] bf16  (MN-major operand: K is the row index) */
+int dalle_b200_split_bf16x3(const float* src, void* dst, int64_t rows, int cols, int concat_rows, int operand, void* stream);
+/* out[r,c] = resid[r,c] + sign * scale[c] * y[r,c]   (fp32; resid / scale optional) -- the LayerScale + residual step of
+ * EPI_RESID as a streaming pass (transformer.py:88, reversible.py:139-140), used by the bf16x6 parity mode */
+int dalle_b200_resid_scale(const float* y, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, void* stream);
+/* h[r,j] = u[r,j] * gelu_erf(u[r,hidden+j])   (fp32; transformer.py:106-109) -- the GEGLU step of EPI_GEGLU as a streaming pass */
+int dalle_b200_geglu_fwd(const float* u, float* h, int64_t rows, int hidden, void* stream);
+
 /* fp32 -> bf16 cast of `count` elements (weights are kept in fp32 and cast once per step) */
 int dalle_b200_cast_bf16(const float* src, void* dst, int64_t count, void* stream);
 

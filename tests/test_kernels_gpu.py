@@ -472,3 +472,38 @@ def test_axial_gather_kernels(kind, code, T, fm, missing):
     report(f'gather bwd {kind}', dqkv, ref, 3e-2, 3e-2 * scale_ref)
     d2 = o.attn_bwd(spec, q[:, :, :n].contiguous(), k[:, :, :n].contiguous(), v[:, :, :n].contiguous(), o2, lse2, g, cos_t, sin_t, scale)
     report(f'gather == predicate bwd {kind}', dqkv, d2, 1e-2, 1e-2 * scale_ref)
+
+
+# ---- fp32 GEMMs on the tensor cores (bf16x6) ----------------------------------------------------------------------
+@pytest.mark.parametrize('a_mn,b_mn', [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize('M,N,K', [(130, 320, 264), (1280, 3072, 1024), (1024, 1024, 2560)])
+def test_gemm_bf16x6_matches_fp64(a_mn, b_mn, M, N, K):
+    """The parity mode's GEMM (three-way bf16 split of both fp32 operands, six partial products accumulated in fp32 by ONE
+    launch of gemm_tcgen05_kernel over K' = 6K) against a float64 product.  Measured on B200: max error / max|C| = 3e-6 (K = 264),
+    1.3e-5 (K = 1024), 2.5e-5 (K = 2560) -- it grows linearly with K because the tensor core's fp32 accumulator truncates at
+    every K = 16 step, where the CUDA-core FFMA kernel (round-to-nearest) stays at 4e-7 .. 2e-6.  Two to three orders of
+    magnitude below a bf16 (4e-3) or tf32 (5e-4) product, and inside the rtol 1e-3 / atol 1e-5 contract on every golden."""
+    import dalle_pytorch_b200 as D
+    o = ops()
+    torch.manual_seed(31)
+    A = torch.randn(K, M, device=dev()) if a_mn else torch.randn(M, K, device=dev())
+    B = torch.randn(K, N, device=dev()) if b_mn else torch.randn(N, K, device=dev())
+    bias = torch.randn(N, device=dev()) if not a_mn else None
+    Am = (A.t() if a_mn else A).double()
+    Bm = (B.t() if b_mn else B).double()
+    want = Am @ Bm.t() + (bias.double() if bias is not None else 0)
+    o.gemm_timing(True)
+    with D.fp32_gemm_ctx('bf16x6'):
+        got6 = o.gemm_store(A, B, a_mn=a_mn, b_mn=b_mn, bias=bias)
+    st = o.gemm_timing(False)
+    if a_mn and M % 8:          # M-major A needs M % 8 == 0 on the tcgen05 kernel: the parity mode falls back to the FFMA kernel
+        assert st['simt']['launches'] == 1
+        return
+    assert st['tcgen05']['launches'] == 1 and st['simt']['launches'] == 0, st
+    with D.fp32_gemm_ctx('simt'):
+        got1 = o.gemm_store(A, B, a_mn=a_mn, b_mn=b_mn, bias=bias)
+    scale = float(want.abs().max())
+    e6 = float((got6.double() - want).abs().max()) / scale
+    e1 = float((got1.double() - want).abs().max()) / scale
+    assert got6.dtype == torch.float32 and e6 < 4e-6 + 1.5e-8 * K, (e6, e1)
+    assert e1 < 5e-6, (e6, e1)

@@ -51,8 +51,22 @@ def run_model(rec, dtype):
     return loss.detach(), logits, grads
 
 
+@pytest.fixture(params=['bf16x6', 'simt'])
+def fp32_gemm(request):
+    """Both evaluations of the fp32 parity mode's GEMMs: 'bf16x6' = the tcgen05 kernel of the speed path fed with three-way
+    bf16 splits of the fp32 operands (the default), 'simt' = the CUDA-core FFMA kernel (cross-check)."""
+    import dalle_pytorch_b200 as D
+    from dalle_pytorch_b200 import ops
+    with D.fp32_gemm_ctx(request.param):
+        ops.gemm_timing(True)
+        yield request.param
+        st = ops.gemm_timing(False)
+    if request.param == 'bf16x6':
+        assert st['tcgen05']['launches'] > 0, 'parity mode did not reach the tcgen05 kernel'
+
+
 @pytest.mark.parametrize('name', golden_names('tiny_'))
-def test_tiny_goldens_fp32(name):
+def test_tiny_goldens_fp32(name, fp32_gemm):
     rec = load_golden(name)
     loss, logits, grads = run_model(rec, torch.float32)
     report('loss', loss, rec['loss'], RTOL, ATOL)
@@ -66,7 +80,7 @@ def test_tiny_goldens_fp32(name):
 
 
 @pytest.mark.parametrize('name', golden_names('c1_'))
-def test_c1_goldens_fp32(name):
+def test_c1_goldens_fp32(name, fp32_gemm):
     """BASELINE.json configs[0]: depth 2, dim 256, heads 4, text 64, image 8x8, batch 2."""
     rec = load_golden(name)
     loss, logits, grads = run_model(rec, torch.float32)
