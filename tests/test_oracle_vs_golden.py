@@ -32,7 +32,12 @@ def _oracle_run(rec):
     return loss.detach(), logits, grads
 
 
-@pytest.mark.parametrize('name', golden_names('tiny_'))
+# fixtures whose weights are tied (stored with the fixture): the oracle restates the un-tied block stack; these goldens pin
+# the product directly (tests/test_parity_gpu.py::test_tied_weight_goldens_fp32)
+TIED = {'tiny_shared', 'tiny_tied_emb'}
+
+
+@pytest.mark.parametrize('name', [n for n in golden_names('tiny_') if n not in TIED])
 def test_oracle_matches_reference_tiny(name):
     rec = load_golden(name)
     loss, logits, grads = _oracle_run(rec)
@@ -46,7 +51,7 @@ def test_oracle_matches_reference_tiny(name):
         torch.testing.assert_close(grads[k], g, rtol=RTOL, atol=ATOL, msg=lambda m: f'{k}: {m}')
 
 
-@pytest.mark.parametrize('name', golden_names('c1_'))
+@pytest.mark.parametrize('name', golden_names('c1_') + ['c3_geom'])
 def test_oracle_matches_reference_c1(name):
     rec = load_golden(name)
     loss, logits, grads = _oracle_run(rec)

@@ -35,11 +35,23 @@ def build(cfg, sd, device='cuda:0'):
     return m.to(device)
 
 
+TIED = {'tiny_shared', 'tiny_tied_emb'}      # fixtures that carry the reference's own (tied) state dict
+
+
 def run_model(rec, dtype):
     import dalle_pytorch_b200 as D
     cfg = _cfg(rec)
-    sd = make_state_dict(cfg, seed=rec['seed'])
-    m = build(cfg, sd)
+    if 'state' in rec:
+        vae = D.TokenVAE(image_size=8 * cfg.fmap, num_layers=3, num_tokens=cfg.num_image_tokens)
+        m = D.DALLE(dim=cfg.dim, vae=vae, num_text_tokens=cfg.num_text_tokens, text_seq_len=cfg.text_seq_len, depth=cfg.depth,
+                    heads=cfg.heads, dim_head=cfg.dim_head, reversible=cfg.reversible, attn_types=cfg.attn_types, stable=cfg.stable,
+                    sandwich_norm=cfg.sandwich_norm, shift_tokens=cfg.shift_tokens, loss_img_weight=cfg.loss_img_weight,
+                    shared_attn_ids=cfg.shared_attn_ids, shared_ff_ids=cfg.shared_ff_ids, **rec.get('extra', {}))
+        m.load_state_dict(rec['state'])            # strict: the tied reference state dict must fit key for key
+        m = m.cuda()
+    else:
+        sd = make_state_dict(cfg, seed=rec['seed'])
+        m = build(cfg, sd)
     m.train()
     text, image = rec['text'].cuda(), rec['image'].cuda()
     with D.compute_dtype_ctx(dtype):
@@ -67,6 +79,8 @@ def fp32_gemm(request):
 
 @pytest.mark.parametrize('name', golden_names('tiny_'))
 def test_tiny_goldens_fp32(name, fp32_gemm):
+    """Includes `tiny_shared` (shared_attn_ids / shared_ff_ids, transformer.py:261-292), `tiny_tied_emb`
+    (share_input_output_emb, dalle_pytorch.py:432-443) and `tiny_axial_stable` (stable softmax on the axial classes)."""
     rec = load_golden(name)
     loss, logits, grads = run_model(rec, torch.float32)
     report('loss', loss, rec['loss'], RTOL, ATOL)
@@ -79,9 +93,12 @@ def test_tiny_goldens_fp32(name, fp32_gemm):
         report(f'grad {k}', grads[k], g, RTOL, ATOL)
 
 
-@pytest.mark.parametrize('name', golden_names('c1_'))
+@pytest.mark.parametrize('name', golden_names('c1_') + ['c3_geom', 'c4_geom_rev'])
 def test_c1_goldens_fp32(name, fp32_gemm):
-    """BASELINE.json configs[0]: depth 2, dim 256, heads 4, text 64, image 8x8, batch 2."""
+    """c1_*: BASELINE.json configs[0] (depth 2, dim 256, heads 4, text 64, image 8x8, batch 2).  c3_geom / c4_geom_rev: the
+    geometry of configs[2..4] (dim 1024, heads 16, text 256, image 32x32, full vocabulary; axial row+column, sequential and
+    reversible executors) at depth 2, batch 1 -- sampled logits, log-sum-exp of every row, sampled gradients and gradient norms
+    of every parameter from the unmodified reference."""
     rec = load_golden(name)
     loss, logits, grads = run_model(rec, torch.float32)
     report('loss', loss, rec['loss'], RTOL, ATOL)
@@ -98,7 +115,8 @@ def test_c1_goldens_fp32(name, fp32_gemm):
         assert abs(gn - rec['grad_norms'][k]) <= 1e-3 * rec['grad_norms'][k] + 1e-7, (k, gn, rec['grad_norms'][k])
 
 
-@pytest.mark.parametrize('name', ['tiny_full', 'tiny_axial', 'tiny_axial_rev', 'tiny_cycle4', 'c1_full', 'c1_axial_rev'])
+@pytest.mark.parametrize('name', ['tiny_full', 'tiny_axial', 'tiny_axial_rev', 'tiny_cycle4', 'tiny_shared', 'c1_full', 'c1_axial_rev',
+                                  'c3_geom', 'c4_geom_rev'])
 def test_goldens_bf16_mode(name):
     """Speed mode (bf16 storage, tensor-core GEMMs) computes the same function: loss within 2e-2, logits within
     6e-2 absolute (bf16 has 8 mantissa bits; SURVEY.md App. C measured 1.5e-2 for a bf16 evaluation of the reference)."""
