@@ -441,6 +441,28 @@ def measure_config(cfg_name, args, ctx, steps, want_e2e=True, want_clocks=True, 
         e2e_step()
         res['ms_e2e'] = timed(e2e_step, steps)
         log(f"{cfg_name}: e2e {res['ms_e2e'] / steps:.2f} ms/step")
+    # ---- the same step captured into ONE CUDA graph and replayed (single process): no Python / ctypes between the kernels ----
+    if world == 1 and not args.no_graph:
+        try:
+            step = D.GraphedStep(model, text_d, image_d, autocast_bf16=head_autocast)
+            for _ in range(2):
+                step()
+            ms_g = timed(lambda: step(), steps)
+            g = {'ms_dev': ms_g, 'kernels_per_step': step.kernels_per_step}
+            if want_e2e:
+                def e2e_graph():
+                    return step(text_h, image_h).item()          # H2D copies of the ids into the static buffers, replay, D2H of the loss
+
+                e2e_graph()
+                g['ms_e2e'] = timed(e2e_graph, steps)
+            res['graph'] = g
+            log(f"{cfg_name}: CUDA-graph replay {ms_g / steps:.2f} ms/step ({step.kernels_per_step} library kernels per step)"
+                + (f", e2e {g['ms_e2e'] / steps:.2f}" if 'ms_e2e' in g else ''))
+            del step
+        except Exception as ex:
+            log(f'{cfg_name}: CUDA-graph capture failed ({type(ex).__name__}: {str(ex)[:200]}); eager numbers stand')
+            res['graph'] = {'error': f'{type(ex).__name__}: {str(ex)[:200]}'}
+            torch.cuda.synchronize()
     if args.with_optimizer and cfg_name == args.config:
         # full training step of the reference trainer (train_dalle.py:609-619): fwd + bwd + clip_grad_norm_(0.5) + Adam
         opt = D.FusedAdam(model.parameters(), lr=3e-4, max_grad_norm=0.5, reducer=reducer)
@@ -469,10 +491,14 @@ def leg_summary(res, world, peak_tf):
     """Compact per-configuration entry for `extra_configs`."""
     c = res['c']
     tokens = res['batch'] * res['seq'] * world * res['steps']
-    value = tokens / (res['ms_dev'] / 1e3)
+    graphed = 'ms_dev' in res.get('graph', {})
+    value = tokens / ((res['graph']['ms_dev'] if graphed else res['ms_dev']) / 1e3)
     fam = res['gemm_stats']['tcgen05']
     flops_tok = model_flops_per_token(c)
-    out = {'workload': workload_name(res['cfg'], c), 'value': value, 'unit': 'tokens/s', 'ms_per_step': res['ms_dev'] / res['steps'],
+    out = {'workload': workload_name(res['cfg'], c), 'value': value, 'unit': 'tokens/s',
+           'ms_per_step': (res['graph']['ms_dev'] if graphed else res['ms_dev']) / res['steps'],
+           'execution': 'one CUDA-graph replay per step' if graphed else 'eager launches',
+           'eager_ms_per_step': res['ms_dev'] / res['steps'],
            'steps': res['steps'], 'n_gpus': world, 'gpu_launches': res['launches'], 'peak_mem_gb': res['peak_mem_gb'],
            'mfu_vs_sustained_peak': value / world * flops_tok / 1e12 / peak_tf,
            'gemm_roofline_frac': (fam['flops'] / (fam['ms'] * 1e-3) / 1e12 / peak_tf) if fam['ms'] > 0 else None,
@@ -526,7 +552,12 @@ def run_gpu_arm(args):
         return
 
     c, batch, seq, dtype = main_res['c'], main_res['batch'], main_res['seq'], main_res['dtype']
-    ms_dev, ms_e2e, gemm_stats = main_res['ms_dev'], main_res['ms_e2e'], main_res['gemm_stats']
+    ms_eager, ms_e2e_eager, gemm_stats = main_res['ms_dev'], main_res['ms_e2e'], main_res['gemm_stats']
+    gr = main_res.get('graph', {})
+    graphed = 'ms_dev' in gr
+    # headline = the product's execution path: the captured step when the capture succeeded (single process), eager otherwise
+    ms_dev = gr['ms_dev'] if graphed else ms_eager
+    ms_e2e = gr.get('ms_e2e', ms_e2e_eager) if graphed else ms_e2e_eager
     tokens_per_step = batch * seq * world
     value = tokens_per_step * args.steps / (ms_dev / 1e3)
     e2e_value = tokens_per_step * args.steps / (ms_e2e / 1e3)
@@ -538,14 +569,15 @@ def run_gpu_arm(args):
                 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': ach / peak_tf, 'traffic': GEMM_DRAM_BYTES_PER_LAUNCH if args.config == 'c2' else None,
                 'traffic_note': 'dram__bytes_read+write per launch, mean of the 20 consecutive GEMM launches (last forward layer, head, first backward layer) of the ncu --set full capture summarised in profiles/r01_gemm_ncu_summary.txt; algorithmic bytes of the same 20 launches average 226 MB',
                 'peak_source': peak_src,
-                'launches_per_step': fam['launches'] / args.steps, 'share_of_step': fam['ms'] / ms_dev,
+                'launches_per_step': fam['launches'] / args.steps, 'share_of_step': fam['ms'] / ms_eager,
+                'timing_note': 'per-GEMM CUDA events are taken in the eager pass of the same run (events cannot be read back from inside a graph replay); share_of_step is relative to the eager step',
                 'simt_gemm_launches': gemm_stats['simt']['launches'],
                 'by_shape': gemm_stats.get('by_shape', {})}
     else:
         fam = gemm_stats.get('simt', {'flops': 0.0, 'ms': 0.0, 'launches': 0})
         ach = fam['flops'] / (fam['ms'] * 1e-3) / 1e12 if fam['ms'] > 0 else 0.0
         roof = {'bound': 'tensor', 'kernel': 'gemm_simt_kernel (fp32 FFMA path)', 'achieved': ach, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': ach / peak_tf, 'traffic': None, 'peak_source': peak_src, 'share_of_step': fam['ms'] / ms_dev if ms_dev else None}
+                'frac': ach / peak_tf, 'traffic': None, 'peak_source': peak_src, 'share_of_step': fam['ms'] / ms_eager if ms_eager else None}
 
     def sub(flag, limit, extra_args=()):
         r = subprocess.run([sys.executable, os.path.abspath(__file__), flag, '--config', args.config, *extra_args], capture_output=True,
@@ -582,7 +614,12 @@ def run_gpu_arm(args):
                       'head': 'token embedding gather/scatter, block stack, logits head GEMMs and cross-entropy all run in libdalle_b200'},
            'e2e': {'value': e2e_value, 'unit': 'tokens/s', 'ms_per_step': ms_e2e / args.steps,
                    'h2d_bytes_per_step': main_res['h2d'] * world, 'd2h_bytes_per_step': 4 * world},
-           'gpu_launches': main_res['launches'], 'model_tflops_per_gpu': value / world * flops_tok / 1e12,
+           'gpu_launches': (gr['kernels_per_step'] * args.steps) if graphed else main_res['launches'],
+           'execution': ({'mode': 'cuda_graph', 'host_launches_per_step': 1, 'library_kernels_per_step': gr['kernels_per_step'],
+                          'eager_ms_per_step': ms_eager / args.steps, 'eager_e2e_ms_per_step': ms_e2e_eager / args.steps}
+                         if graphed else {'mode': 'eager', 'library_kernels_per_step': main_res['launches'] / args.steps,
+                                          **({'graph_error': gr['error']} if 'error' in gr else {})}),
+           'model_tflops_per_gpu': value / world * flops_tok / 1e12,
            'mfu_vs_sustained_peak': value / world * flops_tok / 1e12 / peak_tf,
            'clocks': main_res['clocks'], 'roofline': roof}
     if cpu is not None:
@@ -608,6 +645,7 @@ def main():
     ap.add_argument('--batch', type=int, default=None)
     ap.add_argument('--dtype', default=None, choices=['fp32', 'bf16'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='time the eager step only (no CUDA-graph capture)')
     ap.add_argument('--with-optimizer', action='store_true',
                     help='also time fwd+bwd+FusedAdam(clip 0.5) steps and report them under "train_step" (headline metric unchanged)')
     ap.add_argument('--extra', default=None,

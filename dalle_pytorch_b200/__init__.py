@@ -12,5 +12,6 @@ from .dalle import DALLE, TokenVAE
 from . import ops, functional
 from .optim import FusedAdam
 from .patch import patch_dalle_pytorch
+from .graph import GraphedStep
 
 __version__ = '0.1.0'

@@ -17,7 +17,7 @@ from torch import nn
 import torch.nn.functional as F
 
 from . import ops, config
-from .functional import SublayerGeom, AttnSublayerFn, attn_sublayer_forward
+from .functional import SublayerGeom, AttnSublayerFn, attn_sublayer_forward, _w
 from ._lib import ATTN_FULL, ATTN_AXIAL_ROW, ATTN_AXIAL_COL, ATTN_CONV_LIKE, ATTN_STATIC
 
 
@@ -139,8 +139,7 @@ class Attention(_AttentionBase):
         offset = cache.get('offset', 0)
         cos_t, sin_t = rotary_tables(rotary_pos_emb, self.dim_head)
         a, _, _ = ops.ln_shift_fwd(x.float().contiguous(), None, None, dtype, 0, 1, do_ln=False, do_shift=False)
-        wq = ops.cast_bf16(self.to_qkv.weight.detach()) if dtype == torch.bfloat16 else self.to_qkv.weight.detach()
-        wo = ops.cast_bf16(self.to_out[0].weight.detach()) if dtype == torch.bfloat16 else self.to_out[0].weight.detach()
+        wq, wo = _w(self.to_qkv.weight, dtype), _w(self.to_out[0].weight, dtype)        # cached bf16 copies in bf16 mode
         q, k, v = ops.gemm_qkv(a, wq, b, n, self.heads, self.dim_head, cos_t, sin_t, self.scale, pos_offset=offset)
         if offset > 0:
             k_top, v_top = cache[cache_key]

@@ -340,6 +340,8 @@ class NCCLBackend(DistributedBackend):
         with torch.no_grad():
             for t in list(model.parameters()) + list(model.buffers()):
                 dist.broadcast(t, src=self.ROOT_RANK)
+        from .functional import invalidate_weight_cache
+        invalidate_weight_cache()             # cached bf16 weight copies predate the broadcast
         params = list(model_parameters) if model_parameters is not None else list(model.parameters())
         self.reducer = GradAllReducer(params, bucket_bytes=self.bucket_bytes)
         model.grad_reducer = self.reducer

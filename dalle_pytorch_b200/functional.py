@@ -107,12 +107,45 @@ class SublayerGeom:
         return self.do_shift and n >= self.text_len
 
 
+# bf16 copies of the fp32 master weights, keyed by the parameter's storage and valid for one value of its version counter:
+# a weight is cast once after each in-place update (optimizer step, load_state_dict) instead of once per use -- 49 cast launches
+# and 1.4 GB of traffic per C2 step otherwise.  `weight_cache_enabled(False)` (used while a training step that UPDATES the weights
+# is captured into a CUDA graph: Python does not run at replay, so a cached copy would go stale) forces the cast at every use.
+_wcache = {}
+_wcache_on = True
+
+
+def weight_cache_enabled(flag):
+    global _wcache_on
+    old, _wcache_on = _wcache_on, bool(flag)
+    if not flag:
+        _wcache.clear()
+    return old
+
+
+def invalidate_weight_cache():
+    """For writers that update parameters through raw pointers (FusedAdam's kernel, collectives): torch's version counter does
+    not see those writes."""
+    _wcache.clear()
+
+
 def _w(weight, dtype):
-    """Weights are stored in fp32 (reference checkpoints); bf16 mode casts them once per use with the cast kernel."""
+    """Weights are stored in fp32 (reference checkpoints); bf16 mode uses a cached bf16 copy (see _wcache)."""
     weight = weight.detach()
     if dtype == torch.float32:
         return weight.contiguous()
-    return ops.cast_bf16(weight.contiguous())
+    weight = weight.contiguous()
+    if not _wcache_on:
+        return ops.cast_bf16(weight)
+    key = (weight.data_ptr(), weight.numel(), weight.device.index)
+    hit = _wcache.get(key)
+    if hit is not None and hit[0] == weight._version and hit[1].shape == weight.shape:
+        return hit[1]
+    if len(_wcache) > 4096:
+        _wcache.clear()
+    c = ops.cast_bf16(weight)
+    _wcache[key] = (weight._version, c)
+    return c
 
 
 def _up_args(up, da):

@@ -10,6 +10,7 @@ import torch
 
 from . import ops
 from .distributed import GradAllReducer
+from .functional import invalidate_weight_cache
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -79,6 +80,7 @@ class FusedAdam(torch.optim.Optimizer):
             ops.sumsq_(g, self.gnorm_sq)
         ops.adam_(self.flat_p, g, self.m, self.v, self.steps, float(hp['lr']), hp['betas'][0], hp['betas'][1], hp['eps'],
                   hp['weight_decay'], clip, self.gnorm_sq if clip > 0 else None)
+        invalidate_weight_cache()             # the kernel wrote the parameters through raw pointers: cached bf16 copies are stale
         self.reducer.zero_grad()
         return loss
 
