@@ -17,7 +17,7 @@ from torch import nn
 import torch.nn.functional as F
 
 from . import ops, config
-from .functional import SublayerGeom, AttnSublayerFn, attn_sublayer_forward, _w
+from .functional import SublayerGeom, AttnSublayerFn, attn_sublayer_forward, _w, draw_dropout
 from ._lib import ATTN_FULL, ATTN_AXIAL_ROW, ATTN_AXIAL_COL, ATTN_CONV_LIKE, ATTN_STATIC
 
 
@@ -83,7 +83,8 @@ class _AttentionBase(nn.Module):
 
     def geom(self, dtype, do_ln=False, do_shift=False, text_len=0, fmap=0, n=None):
         return SublayerGeom(dtype=dtype, text_len=text_len, fmap=fmap, do_ln=do_ln, do_shift=do_shift, heads=self.heads,
-                            dim_head=self.dim_head, attn_spec=self.attn_spec(n), q_scale=self.scale)
+                            dim_head=self.dim_head, attn_spec=self.attn_spec(n), q_scale=self.scale,
+                            p_drop=self.to_out[1].p if self.dropout_active() else 0.0)
 
     def _plain_forward(self, x, mask, rotary_pos_emb):
         """to_out(attend(to_qkv(x))) without norm / shift / LayerScale / residual."""
@@ -94,11 +95,12 @@ class _AttentionBase(nn.Module):
         g = self.geom(dtype, n=n)
         km = _key_mask_u8(mask, n)
         w_qkv, w_out, b_out = self.to_qkv.weight, self.to_out[0].weight, self.to_out[0].bias
+        # (the Dropout of to_out, attention.py:53-56, is applied inside the fused sub-layer when it is active: g.p_drop)
         if torch.is_grad_enabled() and (x.requires_grad or w_qkv.requires_grad):
-            out = AttnSublayerFn.apply(g, False, 1.0, cos_t, sin_t, km, x, None, None, None, w_qkv, w_out, b_out, None)
-        else:
-            out, _ = attn_sublayer_forward(g, x, None, None, None, w_qkv, w_out, b_out, None, 1.0, cos_t, sin_t, km, save=False)
-        return self.to_out[1](out)
+            return AttnSublayerFn.apply(g, False, 1.0, cos_t, sin_t, km, x, None, None, None, w_qkv, w_out, b_out, None)
+        out, _ = attn_sublayer_forward(g, x, None, None, None, w_qkv, w_out, b_out, None, 1.0, cos_t, sin_t, km, save=False,
+                                       drop=draw_dropout(g, 'attn', x))
+        return out
 
 
 class Attention(_AttentionBase):

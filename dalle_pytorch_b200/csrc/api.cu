@@ -51,7 +51,8 @@ int qkv_rotary_launch(const void* qkv, void* q, void* k, void* v, const float* c
 int geglu_bwd_launch(const void* dh, const void* u, void* du, float* dbias, int dtype, int rows, int hidden, cudaStream_t st);
 int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st);
 int split_bf16x3_launch(const float* src, void* dst, int64_t rows, int cols, int concat_rows, int pat, cudaStream_t st);
-int resid_scale_launch(const float* y, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, cudaStream_t st);
+int resid_scale_launch(const void* y, int dtype, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, cudaStream_t st);
+int dropout_launch(const void* x, void* y, int dtype, int64_t count, float p, unsigned long long seed, unsigned long long offset, cudaStream_t st);
 int geglu_fwd_launch(const float* u, float* h, int64_t rows, int hidden, cudaStream_t st);
 int axpby_launch(const float* a, const float* b, float alpha, float* y, int64_t count, cudaStream_t st);
 int sumsq_launch(const float* x, int64_t count, float* out, cudaStream_t st);
@@ -292,9 +293,14 @@ int dalle_b200_split_bf16x3(const float* src, void* dst, int64_t rows, int cols,
   return split_bf16x3_launch(src, dst, rows, cols, concat_rows != 0, pat, (cudaStream_t)stream);
 }
 
-int dalle_b200_resid_scale(const float* y, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, void* stream) {
-  DB200_CHECK_ARG(y && out && rows >= 0 && d > 0 && (d & 1) == 0, "resid_scale: bad args (d must be even)");
-  return resid_scale_launch(y, resid, scale, sign, out, rows, d, (cudaStream_t)stream);
+int dalle_b200_resid_scale(const void* y, int dtype, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, void* stream) {
+  DB200_CHECK_ARG(y && out && rows >= 0 && d > 0 && (d & 1) == 0 && dtype_ok(dtype), "resid_scale: bad args (d must be even)");
+  return resid_scale_launch(y, dtype, resid, scale, sign, out, rows, d, (cudaStream_t)stream);
+}
+
+int dalle_b200_dropout(const void* x, void* y, int dtype, int64_t count, float p, uint64_t seed, uint64_t offset, void* stream) {
+  DB200_CHECK_ARG(x && y && count >= 0 && dtype_ok(dtype) && p >= 0.f && p <= 1.f, "dropout: bad args (0 <= p <= 1)");
+  return dropout_launch(x, y, dtype, count, p, seed, offset, (cudaStream_t)stream);
 }
 
 int dalle_b200_geglu_fwd(const float* u, float* h, int64_t rows, int hidden, void* stream) {

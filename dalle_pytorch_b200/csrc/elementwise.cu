@@ -1203,7 +1203,8 @@ __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restri
 }
 
 // out = resid + sign * scale (.) y      (fp32; the LayerScale + residual step of EPI_RESID as a streaming pass, parity mode)
-__global__ void __launch_bounds__(256) resid_scale_kernel(const float* __restrict__ y, const float* __restrict__ resid, const float* __restrict__ scale,
+template <typename T>
+__global__ void __launch_bounds__(256) resid_scale_kernel(const T* __restrict__ y, const float* __restrict__ resid, const float* __restrict__ scale,
                                                           float sign, float* __restrict__ out, long long rows, int d) {
   pdl_launch();
   pdl_wait();
@@ -1211,7 +1212,7 @@ __global__ void __launch_bounds__(256) resid_scale_kernel(const float* __restric
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / (d >> 1);
     const int c = static_cast<int>(i - r * (d >> 1)) * 2;
-    const float2 v = *reinterpret_cast<const float2*>(y + r * d + c);
+    const float2 v = load2<T>(y + r * d + c);
     float s0 = sign, s1 = sign;
     if (scale) { s0 *= scale[c]; s1 *= scale[c + 1]; }
     float2 o = make_float2(s0 * v.x, s1 * v.y);
@@ -1233,6 +1234,47 @@ __global__ void __launch_bounds__(256) geglu_fwd_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Dropout (attention.py:53-56 after to_out, transformer.py:117 after GEGLU) with a counter-based generator: element i keeps
+// its value iff word (i & 3) of Philox4x32-10(key = seed, counter = offset + i / 4) is below the keep threshold, and is scaled
+// by 1 / (1 - p).  The mask is a pure function of (seed, offset, i): the backward pass and the reversible executor's
+// recomputation (reference Deterministic.record_rng / set_rng, reversible.py:20-50) replay it by passing the same pair.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long count, float p, float inv_keep,
+                                                      unsigned long long seed, unsigned long long offset) {
+  pdl_launch();
+  pdl_wait();
+  const uint32_t thresh = p <= 0.f ? 0xffffffffu : static_cast<uint32_t>(fminf((1.0f - p) * 4294967296.0f, 4294967295.0f));
+  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const long long groups = (count + 3) >> 2;
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long c = offset + static_cast<unsigned long long>(gidx);
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32), 0u, 0u), key);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    const long long i0 = gidx << 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j < count) {
+        const float v = to_f32(x[i0 + j]);
+        y[i0 + j] = from_f32<T>(w[j] <= thresh && p < 1.f ? v * inv_keep : 0.f);
+      }
+    }
+  }
+}
+
 static int grid_for(long long work) {
   long long blocks = (work + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
@@ -1247,9 +1289,14 @@ int split_bf16x3_launch(const float* src, void* dst, int64_t rows, int cols, int
   return DB200_OK;
 }
 
-int resid_scale_launch(const float* y, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, cudaStream_t st) {
+int resid_scale_launch(const void* y, int dtype, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, cudaStream_t st) {
   if (rows == 0) return DB200_OK;
-  DB200_CUDA_OK(launch_pdl(resid_scale_kernel, dim3(grid_for(rows * (d / 2))), dim3(256), 0, st, y, resid, scale, sign, out, (long long)rows, d));
+  if (dtype == DB200_F32)
+    DB200_CUDA_OK(launch_pdl(resid_scale_kernel<float>, dim3(grid_for(rows * (d / 2))), dim3(256), 0, st, reinterpret_cast<const float*>(y), resid, scale,
+                             sign, out, (long long)rows, d));
+  else
+    DB200_CUDA_OK(launch_pdl(resid_scale_kernel<__nv_bfloat16>, dim3(grid_for(rows * (d / 2))), dim3(256), 0, st,
+                             reinterpret_cast<const __nv_bfloat16*>(y), resid, scale, sign, out, (long long)rows, d));
   DB200_LAUNCH_OK("resid_scale_kernel");
   return DB200_OK;
 }
@@ -1258,6 +1305,20 @@ int geglu_fwd_launch(const float* u, float* h, int64_t rows, int hidden, cudaStr
   if (rows == 0) return DB200_OK;
   DB200_CUDA_OK(launch_pdl(geglu_fwd_kernel, dim3(grid_for(rows * hidden)), dim3(256), 0, st, u, h, (long long)rows, hidden));
   DB200_LAUNCH_OK("geglu_fwd_kernel");
+  return DB200_OK;
+}
+
+int dropout_launch(const void* x, void* y, int dtype, int64_t count, float p, unsigned long long seed, unsigned long long offset, cudaStream_t st) {
+  if (count == 0) return DB200_OK;
+  const float inv_keep = p < 1.f ? 1.0f / (1.0f - p) : 0.f;
+  const int grid = grid_for((count + 3) / 4);
+  if (dtype == DB200_F32)
+    DB200_CUDA_OK(launch_pdl(dropout_kernel<float>, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float*>(x), reinterpret_cast<float*>(y),
+                             (long long)count, p, inv_keep, seed, offset));
+  else
+    DB200_CUDA_OK(launch_pdl(dropout_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(x),
+                             reinterpret_cast<__nv_bfloat16*>(y), (long long)count, p, inv_keep, seed, offset));
+  DB200_LAUNCH_OK("dropout_kernel");
   return DB200_OK;
 }
 

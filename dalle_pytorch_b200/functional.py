@@ -89,11 +89,33 @@ def _chain_link(x_in, resid_is_input, rec):
     return prev if ok else None
 
 
+class DropoutRNG:
+    """(seed, offset) pairs for dalle_b200_dropout.  The seed is torch's (torch.manual_seed), the offset -- the first Philox
+    counter of the call -- is a 62-bit draw from torch's CPU generator: a run is reproducible from its seed exactly like torch's
+    own dropout, every dropout site gets its own counter range, and restoring the CPU generator state (reversible.py:20-50,
+    Deterministic.set_rng) repeats the draw.  The pair a forward pass drew is kept by its autograd node / the reversible executor and
+    passed again to the backward pass and to the recomputation."""
+
+    @staticmethod
+    def draw(numel):
+        return (torch.initial_seed(), int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item()))
+
+
+def draw_dropout(g, kind, x_in, hidden=None):
+    """The (seed, offset) pair of one sub-layer call, or None when its dropout is off."""
+    if g.p_drop <= 0:
+        return None
+    b, n, d = x_in.shape
+    return DropoutRNG.draw(b * n * (d if kind == 'attn' else hidden))
+
+
 class SublayerGeom:
-    """Static description of a sub-layer (everything that is not a tensor)."""
+    """Static description of a sub-layer (everything that is not a tensor).  p_drop > 0: dropout (training) after the output
+    projection of attention (attention.py:53-56) / after GEGLU in the feed-forward (transformer.py:117)."""
 
     def __init__(self, *, dtype, text_len=0, fmap=0, do_ln=True, do_shift=False, heads=0, dim_head=64, attn_spec=None,
-                 q_scale=None, eps=1e-5):
+                 q_scale=None, eps=1e-5, p_drop=0.0):
+        self.p_drop = float(p_drop)
         self.dtype = dtype
         self.text_len, self.fmap = text_len, fmap
         self.do_ln, self.do_shift = do_ln, do_shift
@@ -170,7 +192,8 @@ def _up_store(up, res):
 # attention sub-layer
 # =====================================================================================================
 def attn_sublayer_forward(g: SublayerGeom, x_in, resid, ln_w, ln_b, w_qkv, w_out, b_out, scale, sign, cos_t, sin_t,
-                          key_mask=None, save=True):
+                          key_mask=None, save=True, drop=None):
+    """drop = (seed, offset) from DropoutRNG.draw(b*n*d) when g.p_drop > 0 (None = no dropout in this call)."""
     b, n, d = x_in.shape
     x_in = x_in.contiguous()
     shift = g.shift_active(n)
@@ -180,8 +203,15 @@ def attn_sublayer_forward(g: SublayerGeom, x_in, resid, ln_w, ln_b, w_qkv, w_out
     q, k, v = ops.gemm_qkv_auto(a1, wq, b, n, g.heads, g.dim_head, cos_t, sin_t, g.q_scale, n_alloc=None if lay is None else lay.n_alloc)
     o, lse = ops.attn_fwd(g.attn_spec, q, k, v, key_mask, lay=lay)
     keep_y = save and scale is not None
-    out, y = ops.gemm_resid(o.view(b * n, -1), wo, b_out, None if resid is None else resid.contiguous().view(b * n, d),
-                            None if scale is None else scale.detach().reshape(-1).contiguous(), sign, keep_y=keep_y)
+    r2 = None if resid is None else resid.contiguous().view(b * n, d)
+    sc = None if scale is None else scale.detach().reshape(-1).contiguous()
+    if drop is None:
+        out, y = ops.gemm_resid(o.view(b * n, -1), wo, b_out, r2, sc, sign, keep_y=keep_y)
+    else:       # to_out -> Dropout -> LayerScale -> residual: the mask sits between the projection and the scale
+        y = ops.dropout_(ops.gemm_store(o.view(b * n, -1), wo, bias=b_out), g.p_drop, *drop)
+        out = ops.resid_scale(y, r2, sc, sign)
+        if not keep_y:
+            y = None
     out = out.view(b, n, d)
     ctx = None
     if save:
@@ -190,7 +220,7 @@ def attn_sublayer_forward(g: SublayerGeom, x_in, resid, ln_w, ln_b, w_qkv, w_out
 
 
 def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t, sin_t, key_mask=None, dres=None, wslots=None,
-                           pre=None, up=None):
+                           pre=None, up=None, drop=None):
     """d_out: gradient w.r.t. `out` [b,n,d] fp32.  Returns (dx_in, dln_w, dln_b, dw_qkv, dw_out, db_out, dscale).
     `dres` (optional, fp32) is added to dx_in inside the LayerNorm-backward kernel (sequential executor: the residual
     branch gradient, which equals d_out).  `wslots` (optional) = (dw_qkv_out, dw_out_out): preallocated fp32 destinations
@@ -202,7 +232,11 @@ def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t
     d_out = d_out.contiguous().view(M, d)
     sc = None if scale is None else scale.detach().reshape(-1).contiguous()
     pool = torch.zeros(6, d, device=x_in.device, dtype=torch.float32)     # one fill for dscale, db_out, dln_w, dln_b (+ upstream dscale, dbias)
-    if pre is not None:      # already formed by the downstream sub-layer's LayerNorm backward (FUSE_UPSTREAM_SCALE_BWD)
+    if drop is not None:     # adjoint of the dropout between to_out and the LayerScale: same mask on the gradient; the bias sits before it
+        dy, dscale, _ = ops.scale_bwd(d_out, y, sc, sign, g.dtype, want_dbias=False, zeroed=(pool[0], pool[1]))
+        ops.dropout_(dy, g.p_drop, *drop)
+        db_out = ops.colsum(dy)
+    elif pre is not None:      # already formed by the downstream sub-layer's LayerNorm backward (FUSE_UPSTREAM_SCALE_BWD)
         dy, dscale, db_out = pre
     else:
         dy, dscale, db_out = ops.scale_bwd(d_out, y, sc, sign, g.dtype, zeroed=(pool[0], pool[1]))
@@ -226,13 +260,16 @@ def attn_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, cos_t
 # =====================================================================================================
 # feed-forward sub-layer
 # =====================================================================================================
-def ff_sublayer_forward(g: SublayerGeom, x_in, resid, ln_w, ln_b, w1, b1, w2, b2, scale, sign, save=True):
+def ff_sublayer_forward(g: SublayerGeom, x_in, resid, ln_w, ln_b, w1, b1, w2, b2, scale, sign, save=True, drop=None):
+    """drop = (seed, offset) from DropoutRNG.draw(b*n*hidden) when g.p_drop > 0."""
     b, n, d = x_in.shape
     x_in = x_in.contiguous()
     shift = g.shift_active(n)
     a2, mean, rstd = ops.ln_shift_fwd(x_in, ln_w, ln_b, g.dtype, g.text_len, g.fmap, do_ln=g.do_ln, do_shift=shift, eps=g.eps)
     w1c, w2c = _w(w1, g.dtype), _w(w2, g.dtype)
     h, u = ops.gemm_geglu(a2, w1c, b1, keep_u=save)
+    if drop is not None:
+        ops.dropout_(h, g.p_drop, *drop)          # net.2 (transformer.py:117); h is only kept for the net.3 weight gradient
     keep_y = save and scale is not None
     out, y = ops.gemm_resid(h, w2c, b2, None if resid is None else resid.contiguous().view(b * n, d),
                             None if scale is None else scale.detach().reshape(-1).contiguous(), sign, keep_y=keep_y)
@@ -243,7 +280,7 @@ def ff_sublayer_forward(g: SublayerGeom, x_in, resid, ln_w, ln_b, w1, b1, w2, b2
     return out, ctx
 
 
-def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=None, wslots=None, pre=None, up=None):
+def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=None, wslots=None, pre=None, up=None, drop=None):
     """Returns (dx_in, dln_w, dln_b, dw1, db1, dw2, db2, dscale).  `wslots` = (dw1_out, dw2_out), see attn_sublayer_backward."""
     x_in, mean, rstd, a2, w1c, w2c, u, h, y, shift = ctx
     s_w1, s_w2 = wslots if wslots is not None else (None, None)
@@ -262,6 +299,8 @@ def ff_sublayer_backward(g: SublayerGeom, ctx, d_out, ln_w, scale, sign, dres=No
         db1 = ops.colsum(du)
     else:   # measured faster on B200 (profiles/): plain dgrad GEMM + one streaming pass that also forms the bias gradient
         dh = ops.gemm_store(dy, w2c, a_mn=False, b_mn=True)                               # [M, H]
+        if drop is not None:
+            ops.dropout_(dh, g.p_drop, *drop)                                             # same mask as the forward
         du, db1 = ops.geglu_bwd(dh, u, zeroed=pool[6 * d:])
     dw2 = ops.gemm_store(dy, h, a_mn=True, b_mn=True, out_dtype=torch.float32, out=s_w2)            # [d, H]
     da2 = ops.gemm_store(du, w1c, a_mn=False, b_mn=True)                                  # [M, d]
@@ -313,9 +352,9 @@ class AttnSublayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, g, resid_is_input, sign, cos_t, sin_t, key_mask, x_in, resid, ln_w, ln_b, w_qkv, w_out, b_out, scale):
         r = x_in if resid_is_input else resid
-        need = torch.is_grad_enabled()
+        ctx.drop = DropoutRNG.draw(x_in.numel()) if g.p_drop > 0 else None
         out, saved = attn_sublayer_forward(g, x_in, r, ln_w, ln_b, w_qkv, w_out, b_out, scale, sign, cos_t, sin_t, key_mask,
-                                           save=True)
+                                           save=True, drop=ctx.drop)
         ctx.g, ctx.resid_is_input, ctx.sign = g, resid_is_input, sign
         ctx.cos_t, ctx.sin_t, ctx.key_mask = cos_t, sin_t, key_mask
         ctx.saved = saved
@@ -324,7 +363,9 @@ class AttnSublayerFn(torch.autograd.Function):
         ctx.wparams = (w_qkv, w_out)
         _note_use(w_qkv, w_out)
         ctx.rec = ctx.up = None
-        if any(ctx.needs_input_grad) and saved is not None:
+        if ctx.drop is not None:
+            chain_reset()            # the LayerScale adjoint is not a plain function of dx when a dropout mask sits in between
+        elif any(ctx.needs_input_grad) and saved is not None:
             y = saved[11]
             ctx.rec = _SubRec(y, None if scale is None else scale.detach().reshape(-1).contiguous(), sign, out)
             ctx.up = _chain_link(x_in, resid_is_input, ctx.rec)
@@ -340,7 +381,7 @@ class AttnSublayerFn(torch.autograd.Function):
         pre = rec.take_pre(d_out) if rec is not None else None
         dx, dln_w, dln_b, dw_qkv, dw_out, db_out, dscale = attn_sublayer_backward(
             g, ctx.saved, d_out, ctx.ln_w, ctx.scale, ctx.sign, ctx.cos_t, ctx.sin_t, ctx.key_mask, dres=dres, wslots=slots,
-            pre=pre, up=ctx.up)
+            pre=pre, up=ctx.up, drop=ctx.drop)
         ctx.rec = ctx.up = None
         dw_qkv = _commit(ctx.wparams[0], slots[0], dw_qkv)
         dw_out = _commit(ctx.wparams[1], slots[1], dw_out)
@@ -353,7 +394,8 @@ class FFSublayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, g, resid_is_input, sign, x_in, resid, ln_w, ln_b, w1, b1, w2, b2, scale):
         r = x_in if resid_is_input else resid
-        out, saved = ff_sublayer_forward(g, x_in, r, ln_w, ln_b, w1, b1, w2, b2, scale, sign, save=True)
+        ctx.drop = DropoutRNG.draw(x_in.shape[0] * x_in.shape[1] * w2.shape[1]) if g.p_drop > 0 else None
+        out, saved = ff_sublayer_forward(g, x_in, r, ln_w, ln_b, w1, b1, w2, b2, scale, sign, save=True, drop=ctx.drop)
         ctx.g, ctx.resid_is_input, ctx.sign = g, resid_is_input, sign
         ctx.saved = saved
         ctx.ln_w, ctx.scale = ln_w, scale
@@ -375,7 +417,7 @@ class FFSublayerFn(torch.autograd.Function):
         rec = ctx.rec
         pre = rec.take_pre(d_out) if rec is not None else None
         dx, dln_w, dln_b, dw1, db1, dw2, db2, dscale = ff_sublayer_backward(ctx.g, ctx.saved, d_out, ctx.ln_w, ctx.scale, ctx.sign,
-                                                                              dres=dres, wslots=slots, pre=pre, up=ctx.up)
+                                                                              dres=dres, wslots=slots, pre=pre, up=ctx.up, drop=ctx.drop)
         ctx.rec = ctx.up = None
         dw1 = _commit(ctx.wparams[0], slots[0], dw1)
         dw2 = _commit(ctx.wparams[1], slots[1], dw2)

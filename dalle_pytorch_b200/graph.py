@@ -23,6 +23,10 @@ class GraphedStep:
         assert text.is_cuda and image.is_cuda, 'GraphedStep needs CUDA tensors'
         assert getattr(model, 'grad_reducer', None) is None or model.grad_reducer.world == 1, \
             'GraphedStep captures a single-process step (the data-parallel all-reduce is driven from Python hooks)'
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout) and mod.p > 0 and model.training:
+                raise NotImplementedError('GraphedStep: dropout > 0 draws a new mask offset per step from Python; a captured step would '
+                                          'replay one mask')
         self.model, self.optimizer = model, optimizer
         self.text, self.image = text.clone(), image.clone()            # static input buffers
         self.kw = dict(return_loss_kwargs or {})

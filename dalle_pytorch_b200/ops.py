@@ -182,12 +182,20 @@ def _use_x6(A):
 
 
 def resid_scale(y, resid, scale, sign):
-    """fp32: resid + sign * scale (.) y"""
+    """resid + sign * scale (.) y  -> fp32 [M, d]   (y fp32 or bf16)"""
     M, d = y.shape
-    out = torch.empty_like(y)
-    _lib.check(_lib.lib().dalle_b200_resid_scale(_p(_c(y)), _p(resid), _p(scale), sign, _p(out), M, d, _stream()), 'resid_scale')
+    out = torch.empty(M, d, device=y.device, dtype=torch.float32)
+    _lib.check(_lib.lib().dalle_b200_resid_scale(_p(_c(y)), dt_code(y.dtype), _p(resid), _p(scale), sign, _p(out), M, d, _stream()), 'resid_scale')
     _count()
     return out
+
+
+def dropout_(x, p, seed, offset):
+    """In place: x[i] <- keep(i) ? x[i] / (1 - p) : 0 with the Philox mask of (seed, offset) (include/dalle_b200.h)."""
+    _lib.check(_lib.lib().dalle_b200_dropout(_p(_c(x)), _p(x), dt_code(x.dtype), x.numel(), float(p), int(seed) & (2 ** 64 - 1), int(offset), _stream()),
+               'dropout')
+    _count()
+    return x
 
 
 def geglu_fwd(u):

@@ -12,7 +12,7 @@ from torch import nn
 
 from . import ops
 from .functional import (attn_sublayer_forward, attn_sublayer_backward, ff_sublayer_forward, ff_sublayer_backward, _note_use,
-                         chain_reset)
+                         chain_reset, draw_dropout)
 
 
 def route_args(router, args, depth):
@@ -51,13 +51,18 @@ class _Sub:
     __slots__ = ('kind', 'geom', 'params', 'cos_t', 'sin_t', 'key_mask')
 
 
-def _run_fwd(p, x_in, resid, sign, save):
+def _draw(p, x_in):
+    """The dropout (seed, offset) pair of one sub-layer call (None when its dropout is off)."""
+    return draw_dropout(p.geom, p.kind, x_in, None if p.kind == 'attn' else p.params['w2'].shape[1])
+
+
+def _run_fwd(p, x_in, resid, sign, save, drop=None):
     P = p.params
     if p.kind == 'attn':
         return attn_sublayer_forward(p.geom, x_in, resid, P['ln_w'], P['ln_b'], P['w_qkv'], P['w_out'], P['b_out'], P['scale'], sign,
-                                     p.cos_t, p.sin_t, p.key_mask, save=save)
+                                     p.cos_t, p.sin_t, p.key_mask, save=save, drop=drop)
     return ff_sublayer_forward(p.geom, x_in, resid, P['ln_w'], P['ln_b'], P['w1'], P['b1'], P['w2'], P['b2'], P['scale'], sign,
-                               save=save)
+                               save=save, drop=drop)
 
 
 def _accumulate(param, grad):
@@ -77,34 +82,40 @@ def _accumulate(param, grad):
             r._on_grad(param)
 
 
-def _run_bwd(p, ctx, d_out, sign):
+def _run_bwd(p, ctx, d_out, sign, drop=None):
     """Backward of one sub-layer; parameter gradients are accumulated straight into .grad (as the reference's inner
     torch.autograd.backward calls do, reversible.py:80,93).  Returns the gradient w.r.t. the sub-layer input."""
     P = p.params
     if p.kind == 'attn':
         dx, dln_w, dln_b, dw_qkv, dw_out, db_out, dscale = attn_sublayer_backward(p.geom, ctx, d_out, P['ln_w'], P['scale'], sign,
-                                                                                   p.cos_t, p.sin_t, p.key_mask)
+                                                                                   p.cos_t, p.sin_t, p.key_mask, drop=drop)
         for name, gr in (('ln_w', dln_w), ('ln_b', dln_b), ('w_qkv', dw_qkv), ('w_out', dw_out), ('b_out', db_out), ('scale', dscale)):
             _accumulate(P[name], gr)
     else:
-        dx, dln_w, dln_b, dw1, db1, dw2, db2, dscale = ff_sublayer_backward(p.geom, ctx, d_out, P['ln_w'], P['scale'], sign)
+        dx, dln_w, dln_b, dw1, db1, dw2, db2, dscale = ff_sublayer_backward(p.geom, ctx, d_out, P['ln_w'], P['scale'], sign, drop=drop)
         for name, gr in (('ln_w', dln_w), ('ln_b', dln_b), ('w1', dw1), ('b1', db1), ('w2', dw2), ('b2', db2), ('scale', dscale)):
             _accumulate(P[name], gr)
     return dx
 
 
 class _ReversibleFunction(torch.autograd.Function):
-    """reversible.py:108-124 with the block body replaced by fused kernels.  Only the final (y1, y2) is kept."""
+    """reversible.py:108-124 with the block body replaced by fused kernels.  Only the final (y1, y2) is kept -- plus, when
+    dropout is active, the (seed, offset) pair every sub-layer's mask was drawn with: the recomputation in backward() passes the
+    same pairs, which is this executor's form of Deterministic.record_rng / set_rng (reversible.py:20-50, 64-66, 77, 90)."""
 
     @staticmethod
     def forward(ctx, x, plans):
         x1 = x2 = x                                             # cat([x, x]) then chunk (reversible.py:150, 61)
+        drops = []
         for pf, pg in plans:
             for pl in (pf, pg):
                 _note_use(*[t for t in pl.params.values() if t is not None])
-            x1, _ = _run_fwd(pf, x2, x1, 1.0, save=False)       # y1 = x1 + f(x2)
-            x2, _ = _run_fwd(pg, x1, x2, 1.0, save=False)       # y2 = x2 + g(y1)
-        ctx.plans = plans
+            df = _draw(pf, x2)
+            x1, _ = _run_fwd(pf, x2, x1, 1.0, save=False, drop=df)       # y1 = x1 + f(x2)
+            dg = _draw(pg, x1)
+            x2, _ = _run_fwd(pg, x1, x2, 1.0, save=False, drop=dg)       # y2 = x2 + g(y1)
+            drops.append((df, dg))
+        ctx.plans, ctx.drops = plans, drops
         ctx.y1, ctx.y2 = x1, x2
         return ops.axpby(x1.mul(0.5), x2, 0.5)                  # stack(chunk(out)).mean(0) (reversible.py:157)
 
@@ -113,15 +124,15 @@ class _ReversibleFunction(torch.autograd.Function):
         y1, y2 = ctx.y1, ctx.y2
         dy1 = d_out.contiguous() * 0.5
         dy2 = dy1.clone()
-        for pf, pg in reversed(ctx.plans):
-            # g: recompute g(y1) with activations kept, x2 = y2 - g(y1)          (reversible.py:77-83)
-            x2, gctx = _run_fwd(pg, y1, y2, -1.0, save=True)
-            dg_in = _run_bwd(pg, gctx, dy2, 1.0)                 # gradient of (+g) w.r.t. y1; sign of the recompute is irrelevant
+        for (pf, pg), (df, dg) in zip(reversed(ctx.plans), reversed(ctx.drops)):
+            # g: recompute g(y1) with activations kept (same dropout mask), x2 = y2 - g(y1)          (reversible.py:77-83)
+            x2, gctx = _run_fwd(pg, y1, y2, -1.0, save=True, drop=dg)
+            dg_in = _run_bwd(pg, gctx, dy2, 1.0, drop=dg)        # gradient of (+g) w.r.t. y1; sign of the recompute is irrelevant
             del gctx
             dx1 = ops.axpby(dy1, dg_in, 1.0)                     # dx1 = dy1 + y1.grad       (reversible.py:86)
             # f: recompute f(x2), x1 = y1 - f(x2)                                (reversible.py:90-96)
-            x1, fctx = _run_fwd(pf, x2, y1, -1.0, save=True)
-            df_in = _run_bwd(pf, fctx, dx1, 1.0)
+            x1, fctx = _run_fwd(pf, x2, y1, -1.0, save=True, drop=df)
+            df_in = _run_bwd(pf, fctx, dx1, 1.0, drop=df)
             del fctx
             dx2 = ops.axpby(dy2, df_in, 1.0)                     # dx2 = dy2 + x2.grad       (reversible.py:99)
             y1, y2, dy1, dy2 = x1, x2, dx1, dx2
@@ -139,15 +150,34 @@ class ReversibleBlock(nn.Module):
 
 
 class Deterministic(nn.Module):
-    """reversible.py:20-50 records/replays RNG state for dropout; with dropout = 0 (every benchmark config) there is
-    no RNG to replay, so this is a pure wrapper that keeps the `.net` name."""
+    """reversible.py:20-50: records the RNG state before a call and replays it for the recomputation.  The fused executor
+    above carries the dropout (seed, offset) pairs itself; this module gives the module-by-module path the reference's
+    interface: `record_rng=True` snapshots torch's CPU / CUDA generators, `set_rng=True` runs the wrapped module under those states;
+    the library's dropout kernels draw their Philox offsets from torch's CPU generator (functional.DropoutRNG), so torch dropouts
+    and library dropouts both repeat their masks."""
 
     def __init__(self, net):
         super().__init__()
         self.net = net
+        self.cpu_state = None
+        self.cuda_state = None
 
-    def forward(self, *args, **kwargs):
-        return self.net(*args, **kwargs)
+    def record_rng(self, *args):
+        self.cpu_state = torch.get_rng_state()
+        self.cuda_state = torch.cuda.get_rng_state() if torch.cuda.is_available() and torch.cuda.is_initialized() else None
+
+    def forward(self, *args, record_rng=False, set_rng=False, **kwargs):
+        if record_rng:
+            self.record_rng(*args)
+        if not set_rng:
+            return self.net(*args, **kwargs)
+        assert self.cpu_state is not None, 'set_rng=True before any record_rng=True call'
+        devices = [torch.cuda.current_device()] if self.cuda_state is not None else []
+        with torch.random.fork_rng(devices=devices, enabled=True):
+            torch.set_rng_state(self.cpu_state)
+            if self.cuda_state is not None:
+                torch.cuda.set_rng_state(self.cuda_state)
+            return self.net(*args, **kwargs)
 
 
 class ReversibleSequence(nn.Module):
@@ -163,14 +193,13 @@ class ReversibleSequence(nn.Module):
             pf = blk.f.net.plan(x, **f_args)
             pg = blk.g.net.plan(x, **g_args)
             if pf is None or pg is None:
-                raise NotImplementedError('reversible executor needs fusable sub-layers (no inference cache, no dropout, '
-                                          'no sandwich norm)')
+                raise NotImplementedError('reversible executor needs fusable sub-layers (no inference cache, no sandwich norm)')
             plans.append((pf, pg))
         x = x.float().contiguous()
         if torch.is_grad_enabled():
             return _ReversibleFunction.apply(x, plans)
         x1 = x2 = x
         for pf, pg in plans:
-            x1, _ = _run_fwd(pf, x2, x1, 1.0, save=False)
-            x2, _ = _run_fwd(pg, x1, x2, 1.0, save=False)
+            x1, _ = _run_fwd(pf, x2, x1, 1.0, save=False, drop=_draw(pf, x2))
+            x2, _ = _run_fwd(pg, x1, x2, 1.0, save=False, drop=_draw(pg, x1))
         return ops.axpby(x1.mul(0.5), x2, 0.5)

@@ -20,7 +20,8 @@ import torch.nn.functional as F
 from . import ops, config
 from .attention import (Attention, SparseAttention, SparseConvCausalAttention, SparseAxialCausalAttention, _AttentionBase,
                         rotary_tables, _key_mask_u8)
-from .functional import (SublayerGeom, AttnSublayerFn, FFSublayerFn, LayerNormFn, attn_sublayer_forward, ff_sublayer_forward)
+from .functional import (SublayerGeom, AttnSublayerFn, FFSublayerFn, LayerNormFn, attn_sublayer_forward, ff_sublayer_forward,
+                         draw_dropout)
 from .reversible import ReversibleSequence, SequentialSequence, _Sub
 
 
@@ -96,19 +97,18 @@ class FeedForward(nn.Module):
         return self.training and self.net[2].p > 0
 
     def geom(self, dtype, do_ln=False, do_shift=False, text_len=0, fmap=0):
-        return SublayerGeom(dtype=dtype, text_len=text_len, fmap=fmap, do_ln=do_ln, do_shift=do_shift)
+        return SublayerGeom(dtype=dtype, text_len=text_len, fmap=fmap, do_ln=do_ln, do_shift=do_shift,
+                            p_drop=self.net[2].p if self.dropout_active() else 0.0)
 
     def forward(self, x, cache=None, cache_key=None):
-        if self.dropout_active():
-            raise NotImplementedError('ff_dropout > 0 in training is not supported by the fused GEGLU kernel '
-                                      '(every benchmark configuration uses the reference default 0)')
         dtype = config.compute_dtype()
         x = x.float()
         g = self.geom(dtype)
         w1, b1, w2, b2 = self.net[0].weight, self.net[0].bias, self.net[3].weight, self.net[3].bias
         if torch.is_grad_enabled() and (x.requires_grad or w1.requires_grad):
             return FFSublayerFn.apply(g, False, 1.0, x, None, None, None, w1, b1, w2, b2, None)
-        out, _ = ff_sublayer_forward(g, x, None, None, None, w1, b1, w2, b2, None, 1.0, save=False)
+        out, _ = ff_sublayer_forward(g, x, None, None, None, w1, b1, w2, b2, None, 1.0, save=False,
+                                     drop=draw_dropout(g, 'ff', x, w2.shape[1]))
         return out
 
 
@@ -219,7 +219,8 @@ class LayerScale(nn.Module):
     # ---- fused execution -----------------------------------------------------------------------------
     def plan(self, x, cache=None, mask=None, rotary_pos_emb=None, **kwargs):
         """Resolve LayerScale(PreNorm([CachedAs(PreShiftToken(]CachedAs|NonCached(layer))) into one fused sub-layer, or
-        None when the configuration needs the module-by-module path (inference cache, dropout, sandwich norm)."""
+        None when the configuration needs the module-by-module path (inference cache, sandwich norm).  Active dropout is part of
+        the fused sub-layer (geom.p_drop)."""
         if exists(cache) or kwargs:
             return None
         pre = self.fn
@@ -238,8 +239,6 @@ class LayerScale(nn.Module):
         p = _Sub()
         p.cos_t = p.sin_t = p.key_mask = None
         if isinstance(inner, _AttentionBase):
-            if inner.dropout_active():
-                return None
             p.kind = 'attn'
             p.geom = inner.geom(dtype, do_ln=True, do_shift=do_shift, text_len=text_len, fmap=fmap, n=n)
             p.geom.eps = pre.norm.eps
@@ -248,8 +247,6 @@ class LayerScale(nn.Module):
             p.cos_t, p.sin_t = rotary_tables(rotary_pos_emb, inner.dim_head)
             p.key_mask = _key_mask_u8(mask, n)
         elif isinstance(inner, FeedForward):
-            if inner.dropout_active():
-                return None
             p.kind = 'ff'
             p.geom = inner.geom(dtype, do_ln=True, do_shift=do_shift, text_len=text_len, fmap=fmap)
             p.geom.eps = pre.norm.eps
@@ -272,11 +269,12 @@ class LayerScale(nn.Module):
                 return AttnSublayerFn.apply(p.geom, True, 1.0, p.cos_t, p.sin_t, p.key_mask, x, None, P['ln_w'], P['ln_b'],
                                             P['w_qkv'], P['w_out'], P['b_out'], P['scale'])
             out, _ = attn_sublayer_forward(p.geom, x, x, P['ln_w'], P['ln_b'], P['w_qkv'], P['w_out'], P['b_out'], P['scale'], 1.0,
-                                           p.cos_t, p.sin_t, p.key_mask, save=False)
+                                           p.cos_t, p.sin_t, p.key_mask, save=False, drop=draw_dropout(p.geom, 'attn', x))
             return out
         if grad:
             return FFSublayerFn.apply(p.geom, True, 1.0, x, None, P['ln_w'], P['ln_b'], P['w1'], P['b1'], P['w2'], P['b2'], P['scale'])
-        out, _ = ff_sublayer_forward(p.geom, x, x, P['ln_w'], P['ln_b'], P['w1'], P['b1'], P['w2'], P['b2'], P['scale'], 1.0, save=False)
+        out, _ = ff_sublayer_forward(p.geom, x, x, P['ln_w'], P['ln_b'], P['w1'], P['b1'], P['w2'], P['b2'], P['scale'], 1.0, save=False,
+                                     drop=draw_dropout(p.geom, 'ff', x, P['w2'].shape[1]))
         return out
 
 

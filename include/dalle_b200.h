@@ -245,9 +245,15 @@ int dalle_b200_ce_bwd(void* logits, int dtype, int rows, int vocab, const int64_
  *   concat_rows = 0: src [rows, cols] fp32 -> dst [rows, 6*cols] bf16  (K-major operand: K is the contiguous axis)
  *   concat_rows = 1: src [rows, cols] fp32 -> dst [6*rows, cols] bf16  (MN-major operand: K is the row index) */
 int dalle_b200_split_bf16x3(const float* src, void* dst, int64_t rows, int cols, int concat_rows, int operand, void* stream);
-/* out[r,c] = resid[r,c] + sign * scale[c] * y[r,c]   (fp32; resid / scale optional) -- the LayerScale + residual step of
- * EPI_RESID as a streaming pass (transformer.py:88, reversible.py:139-140), used by the bf16x6 parity mode */
-int dalle_b200_resid_scale(const float* y, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, void* stream);
+/* out[r,c] = resid[r,c] + sign * scale[c] * y[r,c]   (resid / scale optional) -- the LayerScale + residual step of
+ * EPI_RESID as a streaming pass (transformer.py:88, reversible.py:139-140), used by the bf16x6 parity mode and when dropout sits
+ * between the projection and the LayerScale; y is `dtype`, everything else fp32 */
+int dalle_b200_resid_scale(const void* y, int dtype, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, void* stream);
+/* Dropout with a counter-based generator (attention.py:53-56, transformer.py:117): y[i] = keep(i) ? x[i] / (1 - p) : 0 where
+ * keep(i) = word (i & 3) of Philox4x32-10(key = seed, counter = offset + i / 4) <= (1 - p) * 2^32.  In place allowed (y == x).
+ * The mask is a pure function of (seed, offset, i): pass the same pair to the backward pass (on the gradient) and to the
+ * reversible executor's recomputation -- the library's form of Deterministic.record_rng / set_rng (reversible.py:20-50). */
+int dalle_b200_dropout(const void* x, void* y, int dtype, int64_t count, float p, uint64_t seed, uint64_t offset, void* stream);
 /* h[r,j] = u[r,j] * gelu_erf(u[r,hidden+j])   (fp32; transformer.py:106-109) -- the GEGLU step of EPI_GEGLU as a streaming pass */
 int dalle_b200_geglu_fwd(const float* u, float* h, int64_t rows, int hidden, void* stream);
 

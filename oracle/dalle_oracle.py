@@ -260,12 +260,15 @@ def token_shift(x, text_len, fmap):
     return torch.cat([part_a, part_b, x[:, :, half:]], dim=-1)
 
 
-def feed_forward(x, w1, b1, w2, b2):
-    """transformer.py:106-122: Linear(d, 2*mult*d) -> GEGLU (x * gelu_erf(gates)) -> Linear(mult*d, d)."""
+def feed_forward(x, w1, b1, w2, b2, drop_mask=None):
+    """transformer.py:106-122: Linear(d, 2*mult*d) -> GEGLU (x * gelu_erf(gates)) -> Dropout -> Linear(mult*d, d).
+    drop_mask (optional, [b,n,mult*d], entries 0 or 1/(1-p)) is the Dropout of transformer.py:117 with an explicit mask."""
     u = x @ w1.t() + b1
     half = u.shape[-1] // 2
     a, g = u[..., :half], u[..., half:]
     h = a * F.gelu(g)
+    if drop_mask is not None:
+        h = h * drop_mask
     return h @ w2.t() + b2
 
 
@@ -309,28 +312,31 @@ def layer_params(sd, cfg: OracleConfig, i: int, prefix=''):
 # ----------------------------------------------------------------------------------------------
 # transformer stack (reversible.py:126-157, transformer.py:279-300)
 # ----------------------------------------------------------------------------------------------
-def attn_sublayer(x, P, cfg: OracleConfig, kind, angles, allow, key_mask=None):
-    """LayerScale(PreNorm(PreShiftToken(Attention)))   (transformer.py:279-292, 74-102)"""
+def attn_sublayer(x, P, cfg: OracleConfig, kind, angles, allow, key_mask=None, drop_mask=None):
+    """LayerScale(PreNorm(PreShiftToken(Attention)))   (transformer.py:279-292, 74-102).  drop_mask (optional, [b,n,d], entries 0
+    or 1/(1-p)): the Dropout after to_out (attention.py:53-56) with an explicit mask."""
     y = layer_norm(x, P['a_ln_w'], P['a_ln_b'])
     if cfg.shift_tokens:
         y = token_shift(y, cfg.text_len, cfg.fmap)
     y = attention_core(y, P['w_qkv'], P['w_out'], P['b_out'], cfg.heads, angles, allow, cfg.stable, key_mask)
+    if drop_mask is not None:
+        y = y * drop_mask
     if cfg.sandwich_norm:
         y = layer_norm(y, P['a_lno_w'], P['a_lno_b'])
     return y * P['a_scale']
 
 
-def ff_sublayer(x, P, cfg: OracleConfig):
+def ff_sublayer(x, P, cfg: OracleConfig, drop_mask=None):
     y = layer_norm(x, P['f_ln_w'], P['f_ln_b'])
     if cfg.shift_tokens:
         y = token_shift(y, cfg.text_len, cfg.fmap)
-    y = feed_forward(y, P['w1'], P['b1'], P['w2'], P['b2'])
+    y = feed_forward(y, P['w1'], P['b1'], P['w2'], P['b2'], drop_mask)
     if cfg.sandwich_norm:
         y = layer_norm(y, P['f_lno_w'], P['f_lno_b'])
     return y * P['f_scale']
 
 
-def transformer_forward(x, sd, cfg: OracleConfig, prefix='', key_mask=None, causal=True):
+def transformer_forward(x, sd, cfg: OracleConfig, prefix='', key_mask=None, causal=True, dropout_masks=None):
     """x [b,n,d] -> [b,n,d].  Sequential: reversible.py:134-141.  Reversible: :149-157 + :60-68
     (forward values only; gradients of the reversible executor equal autograd through this forward,
     which is what reversible.py:70-106 reconstructs)."""
@@ -351,12 +357,13 @@ def transformer_forward(x, sd, cfg: OracleConfig, prefix='', key_mask=None, caus
         P = layer_params(sd, cfg, i, prefix)
         kind = cfg.attn_type_of_layer(i)
         allow = allow_for(kind)
+        ma, mf = dropout_masks[i] if dropout_masks is not None else (None, None)   # explicit dropout masks (training with p > 0)
         if cfg.reversible:
-            x1 = x1 + attn_sublayer(x2, P, cfg, kind, angles, allow, key_mask)   # y1 = x1 + f(x2)
-            x2 = x2 + ff_sublayer(x1, P, cfg)                                     # y2 = x2 + g(y1)
+            x1 = x1 + attn_sublayer(x2, P, cfg, kind, angles, allow, key_mask, ma)   # y1 = x1 + f(x2)
+            x2 = x2 + ff_sublayer(x1, P, cfg, mf)                                     # y2 = x2 + g(y1)
         else:
-            x = x + attn_sublayer(x, P, cfg, kind, angles, allow, key_mask)
-            x = x + ff_sublayer(x, P, cfg)
+            x = x + attn_sublayer(x, P, cfg, kind, angles, allow, key_mask, ma)
+            x = x + ff_sublayer(x, P, cfg, mf)
     if cfg.reversible:
         return (x1 + x2) / 2                                     # stack(chunk).mean(0) (reversible.py:157)
     return x
@@ -374,7 +381,7 @@ def logits_mask(cfg: OracleConfig, seq_len: int) -> torch.Tensor:
     return m[:seq_len]
 
 
-def dalle_forward(text, image, sd, cfg: OracleConfig, return_loss=False):
+def dalle_forward(text, image, sd, cfg: OracleConfig, return_loss=False, dropout_masks=None):
     """text [b,text_seq_len] int64, image [b, <=fmap^2] int64 token ids (or None).
     Returns logits [b,n,total_tokens] or the scalar loss."""
     assert cfg.rotary_emb, 'oracle restates the rotary_emb=True path (DALLE default, dalle_pytorch.py:372)'
@@ -392,7 +399,7 @@ def dalle_forward(text, image, sd, cfg: OracleConfig, return_loss=False):
     n = tokens.shape[1]
     if cfg.stable:                                                              # :633-635
         tokens = tokens * 0.1 + tokens.detach() * 0.9
-    out = transformer_forward(tokens, sd, cfg)                                  # :639
+    out = transformer_forward(tokens, sd, cfg, dropout_masks=dropout_masks)     # :639
     if cfg.stable:                                                              # :641-642, transformer.py:29-36
         out = out / out.amax(dim=-1, keepdim=True).detach()
     out = layer_norm(out, sd['to_logits.0.weight'], sd['to_logits.0.bias'])     # :644

@@ -507,3 +507,24 @@ def test_gemm_bf16x6_matches_fp64(a_mn, b_mn, M, N, K):
     e1 = float((got1.double() - want).abs().max()) / scale
     assert got6.dtype == torch.float32 and e6 < 4e-6 + 1.5e-8 * K, (e6, e1)
     assert e1 < 5e-6, (e6, e1)
+
+
+# ---- dropout (Philox, counter-based) --------------------------------------------------------------------------------
+def test_dropout_kernel_mask_properties():
+    o = ops()
+    n, p = 1 << 20, 0.3
+    ones = torch.ones(n, device=dev())
+    a = o.dropout_(ones.clone(), p, 1234, 10)
+    kept = a != 0
+    assert abs(float(kept.float().mean()) - (1 - p)) < 5e-3
+    assert torch.allclose(a[kept], torch.full_like(a[kept], 1 / (1 - p)))
+    assert torch.equal(a, o.dropout_(ones.clone(), p, 1234, 10))                       # a pure function of (seed, offset, i)
+    assert not torch.equal(a, o.dropout_(ones.clone(), p, 1235, 10))
+    b = o.dropout_(ones.clone(), p, 1234, 10 + 7)                                      # counter-based: offset k = shift by 4k elements
+    assert torch.equal(a[28:], b[:-28])
+    c = o.dropout_(torch.ones(n, device=dev(), dtype=torch.bfloat16), p, 1234, 10)     # same mask in every dtype
+    assert torch.equal(c != 0, kept)
+    assert torch.equal(o.dropout_(ones.clone(), 0.0, 1, 0), ones) and not o.dropout_(ones.clone(), 1.0, 1, 0).any()
+    x = torch.randn(1003, device=dev())                                                # ragged tail
+    y = o.dropout_(x.clone(), 0.5, 9, 0)
+    assert torch.equal((y != 0), (o.dropout_(torch.ones_like(x), 0.5, 9, 0) != 0)) and torch.allclose(y[y != 0], 2 * x[y != 0])

@@ -428,3 +428,50 @@ def test_graphed_step_matches_eager():
                 if k in gw:
                     report(f'graphed grad {k}', p.grad, gw[k], 1e-3, 1e-3 * float(gw[k].abs().max()) + 1e-7)
         assert ops.launches() == n0, 'a replay must not launch anything from Python'
+
+
+@pytest.mark.parametrize('reversible', [False, True])
+def test_dropout_matches_torch_with_the_same_masks(reversible):
+    """attn_dropout / ff_dropout > 0 (attention.py:53-56, transformer.py:117) on the fused sub-layers, sequential and reversible:
+    the masks are a pure function of the (seed, offset) pairs drawn from torch's generator, so a plain-torch evaluation of the
+    reference math (the oracle's sub-layers with explicit masks) reproduces loss and gradients; the reversible executor must
+    replay the same masks in its recomputation (reference Deterministic, reversible.py:20-50) -- its gradients equal those of
+    autograd through the same two-stream forward."""
+    import dalle_pytorch_b200 as D
+    from dalle_pytorch_b200 import ops, functional
+    cfg = OracleConfig(dim=64, depth=2, heads=2, text_seq_len=8, fmap=4, num_text_tokens=50, num_image_tokens=32,
+                       attn_types=('full', 'axial_row'), reversible=reversible)
+    sd = make_state_dict(cfg, seed=11)
+    pa, pf = 0.25, 0.4
+    vae = D.TokenVAE(image_size=32, num_layers=3, num_tokens=32)
+    m = D.DALLE(dim=64, vae=vae, num_text_tokens=50, text_seq_len=8, depth=2, heads=2, attn_types=cfg.attn_types, reversible=reversible,
+                attn_dropout=pa, ff_dropout=pf)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    text, image = make_inputs(cfg, 2, seed=12)
+    b, n, d, H = 2, cfg.seq_len, 64, 256
+    # the pairs the model will draw: replay torch's generator
+    torch.manual_seed(99)
+    pairs = [functional.DropoutRNG.draw(1) for _ in range(2 * cfg.depth)]
+    masks = []
+    for li in range(cfg.depth):
+        ma = ops.dropout_(torch.ones(b * n * d, device='cuda'), pa, *pairs[2 * li]).view(b, n, d).cpu()
+        mf = ops.dropout_(torch.ones(b * n * H, device='cuda'), pf, *pairs[2 * li + 1]).view(b, n, H).cpu()
+        masks.append((ma, mf))
+    torch.manual_seed(99)
+    with D.compute_dtype_ctx(torch.float32):
+        loss = m(text.cuda(), image.cuda(), return_loss=True)
+        loss.backward()
+    got = {k: p.grad.detach().cpu() for k, p in m.named_parameters() if p.grad is not None}
+    # plain torch evaluation of the same math with the same masks
+    params = {k: v.clone().requires_grad_(k != 'transformer.pos_emb') for k, v in sd.items()}
+    want = dalle_forward(text, image, params, cfg, return_loss=True, dropout_masks=masks)
+    want.backward()
+    report('loss with dropout', loss.detach(), want.detach(), RTOL, ATOL)
+    for k, g in got.items():
+        report(f'grad {k}', g, params[k].grad, RTOL, 2e-5)
+    # a second step draws new masks
+    torch.manual_seed(100)
+    with D.compute_dtype_ctx(torch.float32):
+        loss2 = m(text.cuda(), image.cuda(), return_loss=True)
+    assert abs(float(loss2) - float(loss)) > 1e-6
