@@ -43,6 +43,7 @@ class GemmParams(ctypes.Structure):
                 ('B', c_void_p), ('ldb', c_int64), ('b_mn_major', c_int),
                 ('epilogue', c_int),
                 ('C', c_void_p), ('ldc', c_int64), ('c_dtype', c_int), ('bias', c_void_p), ('split_k_ok', c_int),
+                ('C_multicast', c_void_p), ('c_scale', c_float),
                 ('q', c_void_p), ('k', c_void_p), ('v', c_void_p), ('cos_t', c_void_p), ('sin_t', c_void_p),
                 ('seq_n', c_int), ('heads', c_int), ('dim_head', c_int), ('pos_offset', c_int), ('q_scale', c_float),
                 ('resid', c_void_p), ('scale', c_void_p), ('sign', c_float), ('y_out', c_void_p), ('out', c_void_p),
@@ -113,6 +114,7 @@ def _declare(lib):
     lib.dalle_b200_ce_fwd.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p]
     lib.dalle_b200_ce_bwd.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p]
     lib.dalle_b200_cast_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
+    lib.dalle_b200_mc_add.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_void_p]
     lib.dalle_b200_split_bf16x3.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]
     lib.dalle_b200_resid_scale.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_void_p]
     lib.dalle_b200_dropout.argtypes = [c_void_p, c_void_p, c_int, c_int64, c_float, ctypes.c_uint64, ctypes.c_uint64, c_void_p]
@@ -153,5 +155,5 @@ def check(rc, what=''):
 
 EXPORTED = ['dalle_b200_version', 'dalle_b200_last_error', 'dalle_b200_device_ok', 'dalle_b200_abi_sizes',
             'dalle_b200_ln_shift_fwd', 'dalle_b200_ln_shift_bwd', 'dalle_b200_gemm', 'dalle_b200_gemm_select', 'dalle_b200_attn_fwd',
-            'dalle_b200_attn_bwd', 'dalle_b200_scale_bwd', 'dalle_b200_colsum', 'dalle_b200_qkv_rotary', 'dalle_b200_geglu_bwd', 'dalle_b200_ce_fwd', 'dalle_b200_ce_bwd', 'dalle_b200_cast_bf16', 'dalle_b200_split_bf16x3', 'dalle_b200_resid_scale', 'dalle_b200_dropout', 'dalle_b200_geglu_fwd',
+            'dalle_b200_attn_bwd', 'dalle_b200_scale_bwd', 'dalle_b200_colsum', 'dalle_b200_qkv_rotary', 'dalle_b200_geglu_bwd', 'dalle_b200_ce_fwd', 'dalle_b200_ce_bwd', 'dalle_b200_cast_bf16', 'dalle_b200_mc_add', 'dalle_b200_split_bf16x3', 'dalle_b200_resid_scale', 'dalle_b200_dropout', 'dalle_b200_geglu_fwd',
             'dalle_b200_axpby', 'dalle_b200_embed_fwd', 'dalle_b200_embed_bwd', 'dalle_b200_sumsq', 'dalle_b200_adam', 'dalle_b200_debug_attn_timeline']

@@ -204,28 +204,46 @@ class SparseConvCausalAttention(_AttentionBase):
 
 class SparseAttention(Attention):
     """Block-sparse attention (attention.py:339-398).  The reference delegates to DeepSpeed's
-    VariableSparsityConfig(block=16, global blocks = text blocks, seq_len//block//4 random blocks, unidirectional)
-    + Triton kernels, which are un-vendored and RNG-dependent ("parity unpinned").  Here the same
-    layout family is drawn once at construction into a static block mask and evaluated by the dense-predicate
-    kernel; no DeepSpeed import."""
+    `SparseSelfAttention(VariableSparsityConfig(...))` + Triton kernels, which are un-vendored, unpinned and draw their random
+    blocks from Python's RNG ("parity unpinned").  This class pins the LAYOUT FAMILY with a written spec and
+    evaluates it with the library's attention kernels (static-mask pattern); no DeepSpeed import.
 
-    def __init__(self, *args, block_size=16, text_seq_len=256, num_random_blocks=None, **kwargs):
+    Layout spec (block = `block_size` = 16 tokens, nb = ceil(seq_len / block) block rows / columns; the same layout for every
+    head, as VariableSparsityConfig's default `different_layout_per_head=False`):
+      * global: every block row attends the first ceil(text_seq_len / block) block columns  (`global_block_indices`,
+        attention.py:355) -- the text tokens;
+      * local: block row r attends block column r (VariableSparsityConfig's default `local_window_blocks=[4]` widens this to the
+        window of 4 blocks containing r: columns 4*(r//4) .. r);
+      * random: block row r > 0 additionally attends `num_random_blocks` (default seq_len // block // 4, attention.py:353) block
+        columns drawn uniformly from [0, r] (unidirectional) -- from a generator seeded with `layout_seed` (default 0) so that the
+        layout is reproducible, where DeepSpeed uses the unseeded `random` module;
+      * causal ('unidirectional', attention.py:361): inside the allowed blocks token i attends token j <= i.
+    `block_layout()` returns the [nb, nb] boolean layout; the token-level mask is its Kronecker expansion cropped to seq_len."""
+
+    def __init__(self, *args, block_size=16, text_seq_len=256, num_random_blocks=None, layout_seed=0, **kwargs):
         super().__init__(*args, **kwargs)
         self.block_size = block_size
         num_random_blocks = num_random_blocks if exists(num_random_blocks) else self.seq_len // block_size // 4
+        self.num_random_blocks = num_random_blocks
+        self.num_global_blocks = math.ceil(text_seq_len / block_size)
         nb = math.ceil(self.seq_len / block_size)
-        global_blocks = math.ceil(text_seq_len / block_size)
-        gen = torch.Generator().manual_seed(0)
+        gen = torch.Generator().manual_seed(layout_seed)
         layout = torch.zeros(nb, nb, dtype=torch.bool)
-        layout[:, :global_blocks] = True                       # global attention to the text blocks
+        layout[:, :self.num_global_blocks] = True                  # global attention to the text blocks
         for r in range(nb):
-            layout[r, r] = True                                # local (own block)
+            layout[r, 4 * (r // 4):r + 1] = True                   # local window of 4 blocks, up to the row's own block
             if num_random_blocks > 0 and r > 0:
                 idx = torch.randint(0, r + 1, (num_random_blocks,), generator=gen)
-                layout[r, idx] = True                          # random blocks (unidirectional: at or before the row)
+                layout[r, idx] = True                              # random blocks (unidirectional: at or before the row)
+        if self.causal:
+            layout &= torch.ones(nb, nb, dtype=torch.bool).tril()
+        self._layout = layout
         mask = layout.repeat_interleave(block_size, 0).repeat_interleave(block_size, 1)[:self.seq_len, :self.seq_len]
         self.register_buffer('static_mask', mask, persistent=False)
         self._static_u8 = None
+
+    def block_layout(self):
+        return self._layout.clone()
 
     def forward(self, x, mask=None, rotary_pos_emb=None):
         return self._plain_forward(x, mask, rotary_pos_emb)

@@ -52,6 +52,7 @@ int geglu_bwd_launch(const void* dh, const void* u, void* du, float* dbias, int 
 int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st);
 int split_bf16x3_launch(const float* src, void* dst, int64_t rows, int cols, int concat_rows, int pat, cudaStream_t st);
 int resid_scale_launch(const void* y, int dtype, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, cudaStream_t st);
+int mc_add_launch(const float* src, void* mc_dst, int64_t count, float scale, cudaStream_t st);
 int dropout_launch(const void* x, void* y, int dtype, int64_t count, float p, unsigned long long seed, unsigned long long offset, cudaStream_t st);
 int geglu_fwd_launch(const float* u, float* h, int64_t rows, int hidden, cudaStream_t st);
 int axpby_launch(const float* a, const float* b, float alpha, float* y, int64_t count, cudaStream_t st);
@@ -152,6 +153,9 @@ int dalle_b200_gemm(const db200_gemm_params* p, void* stream) {
   switch (p->epilogue) {
     case DB200_EPI_STORE:
       DB200_CHECK_ARG(p->C && dtype_ok(p->c_dtype) && (p->ldc & 1) == 0, "gemm/STORE: bad C");
+      if (p->C_multicast)
+        DB200_CHECK_ARG(p->c_dtype == DB200_F32 && p->bias == nullptr && aligned16(p->C_multicast) && (p->ldc & 3) == 0 && p->backend != DB200_GEMM_SIMT,
+                        "gemm/STORE: the multicast reduction needs an fp32 result, no bias, 16-byte aligned rows and the tcgen05 kernel");
       break;
     case DB200_EPI_QKV:
       DB200_CHECK_ARG(p->q && p->k && p->v, "gemm/QKV: null q/k/v");
@@ -182,6 +186,8 @@ int dalle_b200_gemm(const db200_gemm_params* p, void* stream) {
       backend = gemm_tcgen05_supported(*p, &why) ? DB200_GEMM_TCGEN05 : DB200_GEMM_SIMT;
     }
   }
+  if (p->C_multicast && backend != DB200_GEMM_TCGEN05)
+    return set_error(DB200_ERR_UNSUPPORTED, "gemm/STORE: the multicast reduction is implemented by the tcgen05 kernel only (shape / alignment did not qualify)");
   if (backend == DB200_GEMM_TCGEN05) {
     const char* why = "";
     if (!gemm_tcgen05_supported(*p, &why)) return set_error(DB200_ERR_UNSUPPORTED, "gemm: tcgen05 backend cannot run this problem: %s", why);
@@ -296,6 +302,11 @@ int dalle_b200_split_bf16x3(const float* src, void* dst, int64_t rows, int cols,
 int dalle_b200_resid_scale(const void* y, int dtype, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, void* stream) {
   DB200_CHECK_ARG(y && out && rows >= 0 && d > 0 && (d & 1) == 0 && dtype_ok(dtype), "resid_scale: bad args (d must be even)");
   return resid_scale_launch(y, dtype, resid, scale, sign, out, rows, d, (cudaStream_t)stream);
+}
+
+int dalle_b200_mc_add(const float* src, void* mc_dst, int64_t count, float scale, void* stream) {
+  DB200_CHECK_ARG(src && mc_dst && count >= 0 && aligned16(src) && aligned16(mc_dst), "mc_add: bad args (16-byte aligned fp32 buffers)");
+  return mc_add_launch(src, mc_dst, count, scale, (cudaStream_t)stream);
 }
 
 int dalle_b200_dropout(const void* x, void* y, int dtype, int64_t count, float p, uint64_t seed, uint64_t offset, void* stream) {

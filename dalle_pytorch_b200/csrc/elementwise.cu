@@ -1322,6 +1322,31 @@ int dropout_launch(const void* x, void* y, int dtype, int64_t count, float p, un
   return DB200_OK;
 }
 
+// mc_dst[i] += scale * src[i] in every GPU's replica (multimem.red through the NVLink multicast address)
+__global__ void __launch_bounds__(256) mc_add_kernel(const float* __restrict__ src, float* mc_dst, long long count, float scale) {
+  pdl_launch();
+  pdl_wait();
+  const long long groups = count >> 2;
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += (long long)gridDim.x * blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(src + 4 * gidx);
+    asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_dst + 4 * gidx), "f"(v.x * scale), "f"(v.y * scale),
+                 "f"(v.z * scale), "f"(v.w * scale)
+                 : "memory");
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (count & 3)) {
+    const long long i = (groups << 2) + threadIdx.x;
+    asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(mc_dst + i), "f"(src[i] * scale) : "memory");
+  }
+}
+
+int mc_add_launch(const float* src, void* mc_dst, int64_t count, float scale, cudaStream_t st) {
+  if (count == 0) return DB200_OK;
+  DB200_CUDA_OK(launch_pdl(mc_add_kernel, dim3(grid_for((count + 3) / 4)), dim3(256), 0, st, src, reinterpret_cast<float*>(mc_dst), (long long)count,
+                           scale));
+  DB200_LAUNCH_OK("mc_add_kernel");
+  return DB200_OK;
+}
+
 int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st) {
   if (count == 0) return DB200_OK;
   int64_t blocks = ceil_div64(count, 256 * 4);

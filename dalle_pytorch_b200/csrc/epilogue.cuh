@@ -9,7 +9,8 @@ namespace db200 {
 struct EpiArgs {
   int M, N;
   // STORE
-  void* C; long long ldc; int c_is_f32; const float* bias; int atomic_c;
+  void* C; long long ldc; int c_is_f32; const float* bias; int atomic_c;      // atomic_c: 0 store, 1 fp32 red.add (split-K), 2 multimem.red
+  float c_scale;                                                             // multiplies the accumulator in the multimem mode
   // QKV
   void* q; void* k; void* v; const float* cos_t; const float* sin_t;
   int seq_n, heads, dim_head, pos_offset; float q_scale;
@@ -22,12 +23,23 @@ struct EpiArgs {
 inline EpiArgs make_epi_args(const db200_gemm_params& p) {
   EpiArgs e;
   e.M = p.M; e.N = p.N;
-  e.C = p.C; e.ldc = p.ldc; e.c_is_f32 = (p.c_dtype == DB200_F32); e.bias = p.bias; e.atomic_c = 0;
+  e.C = p.C; e.ldc = p.ldc; e.c_is_f32 = (p.c_dtype == DB200_F32); e.bias = p.bias; e.atomic_c = 0; e.c_scale = 1.0f;
+  if (p.C_multicast) { e.C = p.C_multicast; e.atomic_c = 2; e.c_scale = p.c_scale; }   // weight gradient reduced across the GPUs in the NVSwitch
   e.q = p.q; e.k = p.k; e.v = p.v; e.cos_t = p.cos_t; e.sin_t = p.sin_t;
   e.seq_n = p.seq_n; e.heads = p.heads; e.dim_head = p.dim_head; e.pos_offset = p.pos_offset; e.q_scale = p.q_scale;
   e.resid = p.resid; e.scale = p.scale; e.sign = p.sign; e.y_out = p.y_out; e.out = p.out;
   e.u_out = p.u_out; e.h_out = p.h_out; e.hidden = p.hidden; e.u_in = p.u_in; e.du_out = p.du_out;
   return e;
+}
+
+// Reduction into the same offset of EVERY GPU's copy of a symmetric buffer through its NVLink multicast address: the NVSwitch adds
+// the value into all replicas (NVLS).  Data-parallel weight gradients are summed across the GPUs by the wgrad GEMM's own
+// epilogue -- no collective kernel, no extra pass over the gradient (distributed.py, multimem mode).
+__device__ __forceinline__ void mc_red_add_v4(float* mc, float a, float b, float c, float d) {
+  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mc_red_add_v2(float* mc, float a, float b) {
+  asm volatile("multimem.red.relaxed.sys.global.add.v2.f32 [%0], {%1, %2};" ::"l"(mc), "f"(a), "f"(b) : "memory");
 }
 
 // EPI_STORE ------------------------------------------------------------------------------------------
@@ -160,7 +172,11 @@ __device__ __forceinline__ void epi_vec8(const EpiArgs& e, int m, int n, float* 
       for (int i = 0; i < 8; ++i) v[i] += bb[i];
     }
     const long long off = (long long)m * e.ldc + n;
-    if (e.atomic_c) {                                  // split-K partial sum (fp32 C, zero-initialised by the caller)
+    if (e.atomic_c == 2) {                             // cross-GPU sum through the multicast address (16-byte aligned granules)
+      float* c = reinterpret_cast<float*>(e.C) + off;
+      mc_red_add_v4(c, v[0] * e.c_scale, v[1] * e.c_scale, v[2] * e.c_scale, v[3] * e.c_scale);
+      mc_red_add_v4(c + 4, v[4] * e.c_scale, v[5] * e.c_scale, v[6] * e.c_scale, v[7] * e.c_scale);
+    } else if (e.atomic_c) {                           // split-K partial sum (fp32 C, zero-initialised by the caller)
       float* c = reinterpret_cast<float*>(e.C) + off;
 #pragma unroll
       for (int i = 0; i < 8; ++i) atomicAdd(c + i, v[i]);
@@ -266,7 +282,8 @@ __device__ __forceinline__ void epi_chunk_cols(const EpiArgs& e, int mbase, int 
       const int m = mbase + 2 * it;
       if (m < M) {
         const long long off = (long long)m * e.ldc + n;
-        if (e.atomic_c) { atomicAdd(reinterpret_cast<float*>(e.C) + off, t[2 * it]); atomicAdd(reinterpret_cast<float*>(e.C) + off + 1, t[2 * it + 1]); }
+        if (e.atomic_c == 2) mc_red_add_v2(reinterpret_cast<float*>(e.C) + off, t[2 * it] * e.c_scale, t[2 * it + 1] * e.c_scale);
+        else if (e.atomic_c) { atomicAdd(reinterpret_cast<float*>(e.C) + off, t[2 * it]); atomicAdd(reinterpret_cast<float*>(e.C) + off + 1, t[2 * it + 1]); }
         else if (e.c_is_f32) store2<float>(reinterpret_cast<float*>(e.C) + off, t[2 * it] + b0, t[2 * it + 1] + b1);
         else store2<T>(reinterpret_cast<T*>(e.C) + off, t[2 * it] + b0, t[2 * it + 1] + b1);
       }

@@ -398,7 +398,7 @@ int launch_cfg_mode(const db200_gemm_params& p, cudaStream_t st) {
   const int num_tiles = num_mn * k_splits;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
   EpiArgs e = make_epi_args(p);
-  e.atomic_c = k_splits > 1;
+  if (e.atomic_c != 2) e.atomic_c = k_splits > 1;      // (multimem reductions are additive already: split-K needs nothing more)
   static const bool static_sched = [] { const char* v = std::getenv("DALLE_B200_SCHED"); return v && !std::strcmp(v, "static"); }();
   const int sched_slot = static_sched ? -1 : static_cast<int>(g_launch_seq.fetch_add(1, std::memory_order_relaxed) % SCHED_SLOTS);
   DB200_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, st, tmA, tmB, p.M, p.N, p.K, k_splits, sched_slot, e));
@@ -421,7 +421,10 @@ inline int epi_mode_env() {
 template <int BLOCK_N, int EPI, bool A_MN, bool B_MN>
 int launch_cfg(const db200_gemm_params& p, cudaStream_t st) {
   const int env = epi_mode_env();
-  const bool cols = env == 2 || (env == 0 && (EPI == DB200_EPI_GEGLU || EPI == DB200_EPI_RESID));   // measured, see profiles/
+  // (multicast reduction: lanes must run along N so that one warp instruction is one contiguous 256-byte run -- NVLink packets of
+  //  16 scattered bytes per lane, the "rows" layout, were measured 10 ms per C2 step slower)
+  const bool cols = env == 2 || (env == 0 && (EPI == DB200_EPI_GEGLU || EPI == DB200_EPI_RESID)) ||
+                    (EPI == DB200_EPI_STORE && p.C_multicast != nullptr);   // measured, see profiles/
   if (cols) return launch_cfg_mode<BLOCK_N, EPI, A_MN, B_MN, true>(p, st);
   return launch_cfg_mode<BLOCK_N, EPI, A_MN, B_MN, false>(p, st);
 }

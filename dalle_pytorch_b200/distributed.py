@@ -15,6 +15,19 @@ bucket is complete, so communication of layer i overlaps the backward kernels of
 the outstanding work and applies 1/world.  NVSwitch gives every GPU full bandwidth to every peer, so buckets are
 sized for launch latency / overlap (default 64 MiB), not for link count.
 
+Multimem mode (NVSwitch boxes, opt-in: `mode='multimem'` / DALLE_B200_DP=multimem): there is NO collective kernel.  The flat buffer is a symmetric allocation (torch.distributed._symmetric_memory) mapped through an NVLink
+multicast address; every weight-gradient GEMM adds `acc / world` into ALL replicas from its own epilogue (`multimem.red`, reduced
+inside the switch: gemm STORE with db200_gemm_params::C_multicast), the remaining gradients (LayerNorm, biases, embeddings, head)
+are pushed the same way by `dalle_b200_mc_add` as they appear, and `finish()` is one device-side barrier.  The gradient bytes cross
+NVLink once per peer, spread over the backward pass, without taking SMs from the GEMMs -- the fused compute + collective form of the
+data-parallel step.  Per step: zero_grad() clears the local replica on a side stream and runs a barrier (nobody may contribute to
+a replica that has not been cleared); the first contribution of the backward pass waits for that event.
+Measured (profiles/r02_summary.md): correct to 5e-7 against the single-process mean (tools/dp_check.py); on 2 x B200 41.70 ms per C2
+step against 41.06 ms with the overlapped NCCL buckets (40.58 ms on one GPU).  `multimem.red` is a PUSH: every replica receives
+one atomic add per contributing GPU, so the NVLink ingress per GPU grows with the world size (8 x 0.96 GB at eight GPUs) where
+NCCL's NVLS all-reduce (pull with multimem.ld_reduce, then multicast store) stays at ~2 x 0.96 GB -- which is why NCCL remains the
+default and this mode is kept for two-GPU boxes and as the template for a fused reduce-scatter.
+
 Validity contract (what makes the reference loop `loss.backward(); clip_grad_norm_(params); opt.step()`,
 train_dalle.py:612-622, safe): the first gradient of a backward pass queues an end-of-backward callback on the
 autograd engine which runs `finish()`, so when `backward()` returns every `.grad` is the reduced mean and no
@@ -128,10 +141,17 @@ class DummyBackend(DistributedBackend):
 class GradAllReducer:
     """Flat-buffer bucketed gradient all-reduce (see module docstring)."""
 
-    def __init__(self, params, process_group=None, bucket_bytes=64 << 20, average=True, auto_finish=True):
+    def __init__(self, params, process_group=None, bucket_bytes=64 << 20, average=True, auto_finish=True, overlap=None, mode=None):
         self.pg = process_group
+        self.mode = mode or os.environ.get('DALLE_B200_DP', 'nccl')           # 'nccl' (default) | 'multimem' | 'auto' (multimem if possible)
+        assert self.mode in ('auto', 'multimem', 'nccl')
+        self.mc = None                                                        # multicast base address of the flat buffer (multimem mode)
+        # overlap=False: nothing is launched during backward; finish() reduces the whole flat buffer with ONE collective (the
+        # collective's CTAs then never compete with the backward GEMMs for SMs / HBM; its time is fully exposed)
+        self.overlap = (os.environ.get('DALLE_B200_DP_OVERLAP', '1') != '0') if overlap is None else bool(overlap)
         self.auto_finish = auto_finish      # finish() runs as an autograd end-of-backward callback
         self._sync, self._finished, self._cb_queued = True, False, False
+        self._direct_pass = set()        # parameters delivered through direct_done() in the running backward pass
         # without an initialised process group this is just the flat gradient buffer of a single process (optim.FusedAdam)
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.average = average
@@ -147,12 +167,25 @@ class GradAllReducer:
         ALIGN = 64
         padded = [(n + ALIGN - 1) // ALIGN * ALIGN for n in sizes]
         total = sum(padded)
-        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat = None
+        if self.world > 1 and self.mode != 'nccl' and dev.type == 'cuda' and dist.get_backend(process_group) == 'nccl':
+            try:
+                self._init_multimem(total, dev)
+            except Exception as ex:
+                if self.mode == 'multimem':
+                    raise
+                self.mc = None
+                import warnings
+                warnings.warn(f'GradAllReducer: NVLink multicast not available ({type(ex).__name__}: {ex}); using NCCL all-reduce')
+        if self.flat is None:
+            self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.views, self.bucket_of, self.buckets = {}, {}, []
         off, b_start, b_params = 0, 0, []
         limit = max(1, bucket_bytes // 4)
         for p, n, n_pad in zip(order, sizes, padded):
             self.views[p] = self.flat[off:off + n].view_as(p)
+            if self.mc is not None:       # what ops.gemm_store / ops.mc_add need to reduce into every replica of this slot
+                self.views[p]._b200_mc = (self.mc + 4 * off, self._mc_scale)
             b_params.append(p)
             off += n_pad
             if off - b_start >= limit:
@@ -173,6 +206,40 @@ class GradAllReducer:
             p._b200_reducer = self
         self.zero_grad()
 
+    # -- multimem mode ---------------------------------------------------------------------------------------------
+    def _init_multimem(self, total, dev):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.pg if self.pg is not None else dist.group.WORLD
+        buf = symm_mem.empty(total, dtype=torch.float32, device=dev)
+        hdl = symm_mem.rendezvous(buf, group.group_name)
+        if not getattr(hdl, 'multicast_ptr', 0):
+            raise RuntimeError('the symmetric allocation has no multicast mapping')
+        buf.zero_()
+        hdl.barrier(channel=0)
+        self.flat, self._hdl, self.mc = buf, hdl, int(hdl.multicast_ptr)
+        self._mc_scale = (1.0 / self.world) if self.average else 1.0
+        self._side = torch.cuda.Stream(device=dev)
+        self._zero_ev, self._dirty = None, False
+
+    def _mc_ready(self):
+        """Before the first contribution of a step: the local replica has been cleared and every peer's has (zero_grad)."""
+        if self._zero_ev is not None:
+            torch.cuda.current_stream().wait_event(self._zero_ev)
+            self._zero_ev = None
+        self._dirty = True
+
+    def _mc_clear(self):
+        if not self._dirty:            # nothing was contributed since the last clear (e.g. zero_grad() called twice): keep the barrier count symmetric
+            return
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)                                  # after whoever consumed the gradients (optimizer step)
+        with torch.cuda.stream(self._side):
+            self.flat.zero_()
+            self._hdl.barrier(channel=0)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        self._zero_ev, self._dirty = ev, False
+
     # -- per-step protocol: zero_grad() -> forward/backward -> finish() -> optimizer.step() ----------------
     def zero_grad(self):
         """Start of a step.  Gradients are NOT pre-zeroed views any more: autograd writes a fresh gradient tensor per
@@ -188,11 +255,17 @@ class GradAllReducer:
             self._launched[bi] = False
         self._works = []
         self._finished = False
+        self._direct_pass = set()
+        if self.mc is not None:
+            self._mc_clear()
 
     @contextlib.contextmanager
     def no_sync(self):
         """Gradient accumulation: backward passes inside this context only accumulate into the flat buffer (no bucket is
         launched, nothing is reduced); the first backward outside it reduces the accumulated sum."""
+        if self.mc is not None:
+            raise NotImplementedError('gradient accumulation (no_sync) needs mode="nccl": in multimem mode every contribution is '
+                                      'reduced across the GPUs as it is produced')
         old, self._sync = self._sync, False
         try:
             yield self
@@ -217,20 +290,28 @@ class GradAllReducer:
 
     def _end_of_backward(self):
         self._cb_queued = False
+        self._direct_pass = set()
         if self._sync:
             self.finish()
 
     def _launch(self, bi):
         s, e, _ = self.buckets[bi]
         self._launched[bi] = True
-        if self.world > 1:
+        if self.world > 1 and self.mc is None:
             # AVG folds the 1/world into the collective (NCCL); gloo (CPU tests) has no AVG -> SUM + scale in finish()
             op = dist.ReduceOp.AVG if (self.average and self._has_avg) else dist.ReduceOp.SUM
             self._works.append(dist.all_reduce(self.flat[s:e], op=op, group=self.pg, async_op=True))
 
     def _adopt(self, p):
         v = self.views[p]
-        if p.grad is None:
+        if self.mc is not None:        # push the local gradient into every replica (nothing to push for a parameter without one)
+            if p.grad is not None:
+                if p.grad.data_ptr() == v.data_ptr():
+                    raise RuntimeError(f'GradAllReducer(multimem): a gradient of shape {tuple(p.shape)} was accumulated in place into its flat-buffer view (seen={p in self._seen}, uses={getattr(p, "_b200_uses", None)})')
+                from . import ops
+                self._mc_ready()
+                ops.mc_add(p.grad.detach().contiguous().view(-1).float(), v._b200_mc[0], v._b200_mc[1])
+        elif p.grad is None:
             v.zero_()
         elif p.grad.data_ptr() != v.data_ptr():
             v.copy_(p.grad)
@@ -243,11 +324,14 @@ class GradAllReducer:
         self._guard()
         if p in self._seen or p not in self.views:
             return None
+        if self.mc is not None:
+            self._mc_ready()
         return self.views[p]
 
     def direct_done(self, p):
         p.grad = self.views[p]
         self._seen.add(p)
+        self._direct_pass.add(p)
         self._count(p)
 
     def _count(self, p):
@@ -256,10 +340,16 @@ class GradAllReducer:
             return
         bi = self.bucket_of[p]
         self._pending[bi] -= 1
-        if self._pending[bi] == 0 and not self._launched[bi]:
+        if self.overlap and self._pending[bi] == 0 and not self._launched[bi]:
             self._launch(bi)
 
     def _on_grad(self, p):
+        # The autograd engine runs the post-accumulate hook of a parameter even when its Function returned None for it (observed
+        # with torch 2.11): a gradient that was delivered through direct_slot()/direct_done() must not be counted a second time
+        # (the bucket would be launched before its other members have arrived).
+        if p in self._direct_pass:
+            self._direct_pass.discard(p)
+            return
         self._guard()
         self._adopt(p)
         self._count(p)
@@ -270,6 +360,24 @@ class GradAllReducer:
         the optimizer's step pre-hook) returns immediately; zero_grad() opens the next step."""
         if self._finished:
             return
+        if self.mc is not None:        # every contribution is already on its way into every replica: adopt the stragglers, one barrier
+            for p in self.params:
+                if p not in self._seen:
+                    self._adopt(p)
+            for bi in range(len(self.buckets)):
+                self._launched[bi] = True
+            self._hdl.barrier(channel=1)
+            self._finished = True
+            return
+        if not self.overlap and not any(self._launched):
+            for p in self.params:
+                if p not in self._seen:
+                    self._adopt(p)
+            for bi in range(len(self.buckets)):
+                self._launched[bi] = True
+            if self.world > 1:
+                op = dist.ReduceOp.AVG if (self.average and self._has_avg) else dist.ReduceOp.SUM
+                self._works.append(dist.all_reduce(self.flat, op=op, group=self.pg, async_op=True))
         for bi, (_, _, ps) in enumerate(self.buckets):
             if not self._launched[bi]:
                 for p in ps:

@@ -129,44 +129,39 @@ class SublayerGeom:
         return self.do_shift and n >= self.text_len
 
 
-# bf16 copies of the fp32 master weights, keyed by the parameter's storage and valid for one value of its version counter:
-# a weight is cast once after each in-place update (optimizer step, load_state_dict) instead of once per use -- 49 cast launches
-# and 1.4 GB of traffic per C2 step otherwise.  `weight_cache_enabled(False)` (used while a training step that UPDATES the weights
-# is captured into a CUDA graph: Python does not run at replay, so a cached copy would go stale) forces the cast at every use.
-_wcache = {}
+# bf16 copies of the fp32 master weights, kept ON the parameter object and valid for one value of its version counter: a weight
+# is cast once after each in-place update (optimizer step, load_state_dict) instead of once per use -- 49 cast launches and 1.4 GB
+# of traffic per C2 step otherwise.  (The copy lives and dies with the parameter: a cache keyed by address would hand a new
+# model the copy of a freed one.)  `weight_cache_enabled(False)` (used while a training step that UPDATES the weights is captured
+# into a CUDA graph: Python does not run at replay, so a cached copy would go stale) forces the cast at every use.
 _wcache_on = True
+_wcache_epoch = 0
 
 
 def weight_cache_enabled(flag):
     global _wcache_on
     old, _wcache_on = _wcache_on, bool(flag)
-    if not flag:
-        _wcache.clear()
     return old
 
 
 def invalidate_weight_cache():
     """For writers that update parameters through raw pointers (FusedAdam's kernel, collectives): torch's version counter does
     not see those writes."""
-    _wcache.clear()
+    global _wcache_epoch
+    _wcache_epoch += 1
 
 
 def _w(weight, dtype):
-    """Weights are stored in fp32 (reference checkpoints); bf16 mode uses a cached bf16 copy (see _wcache)."""
-    weight = weight.detach()
+    """Weights are stored in fp32 (reference checkpoints); bf16 mode uses the bf16 copy cached on the parameter (see above)."""
     if dtype == torch.float32:
-        return weight.contiguous()
-    weight = weight.contiguous()
-    if not _wcache_on:
-        return ops.cast_bf16(weight)
-    key = (weight.data_ptr(), weight.numel(), weight.device.index)
-    hit = _wcache.get(key)
-    if hit is not None and hit[0] == weight._version and hit[1].shape == weight.shape:
+        return weight.detach().contiguous()
+    if not _wcache_on or not weight.is_leaf:
+        return ops.cast_bf16(weight.detach().contiguous())
+    hit = getattr(weight, '_b200_bf16', None)
+    if hit is not None and hit[0] == (weight._version, _wcache_epoch, weight.data_ptr()):
         return hit[1]
-    if len(_wcache) > 4096:
-        _wcache.clear()
-    c = ops.cast_bf16(weight)
-    _wcache[key] = (weight._version, c)
+    c = ops.cast_bf16(weight.detach().contiguous())
+    weight._b200_bf16 = ((weight._version, _wcache_epoch, weight.data_ptr()), c)
     return c
 
 

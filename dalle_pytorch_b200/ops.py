@@ -232,12 +232,16 @@ def gemm_store(A, B, a_mn=False, b_mn=False, out_dtype=None, bias=None, backend=
         C = None
     # weight-gradient shapes (few output tiles, very long K): let the kernel split K; it needs a zeroed fp32 C
     split_ok = out_dtype == torch.float32 and bias is None and A.dtype == torch.bfloat16 and M * N <= 4096 * 1024 and K >= 4096
+    mc = getattr(out, '_b200_mc', None) if out is not None else None      # (multicast address, scale): data-parallel multimem slot
     if C is None:
         C = (torch.zeros if split_ok else torch.empty)(M, N, device=A.device, dtype=out_dtype)
-    elif split_ok:
+    elif split_ok and mc is None:
         C.zero_()
     P = _base(M, N, K, A, A.shape[1], a_mn, B, B.shape[1], b_mn, EPI_STORE, backend)
     P.C, P.ldc, P.c_dtype, P.bias, P.split_k_ok = _p(C), N, dt_code(out_dtype), _p(bias), int(split_ok)
+    if mc is not None:      # the epilogue ADDS scale * acc into every GPU's replica of the (pre-zeroed) flat gradient buffer
+        assert out_dtype == torch.float32 and bias is None
+        P.C_multicast, P.c_scale = ctypes.c_void_p(mc[0]), mc[1]
     _gemm(P)
     return C
 
@@ -478,6 +482,14 @@ def colsum(x):
     _lib.check(_lib.lib().dalle_b200_colsum(_p(_c(x)), dt_code(x.dtype), rows, cols, _p(out), _stream()), 'colsum')
     _count()
     return out
+
+
+def mc_add(src, mc_ptr, scale):
+    """every replica of the symmetric buffer at multicast address mc_ptr += scale * src (fp32, flat)"""
+    src = _c(src)
+    assert src.dtype == torch.float32
+    _lib.check(_lib.lib().dalle_b200_mc_add(_p(src), ctypes.c_void_p(mc_ptr), src.numel(), scale, _stream()), 'mc_add')
+    _count()
 
 
 def cast_bf16(src):

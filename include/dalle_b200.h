@@ -134,6 +134,11 @@ typedef struct {
   /* STORE */
   void* C; int64_t ldc; int c_dtype; const float* bias;   /* bias [N] fp32 optional */
   int split_k_ok;           /* STORE, fp32 C, no bias: C is zero-initialised, the kernel may split K and reduce with fp32 atomics */
+  void* C_multicast;        /* STORE, fp32, no bias, tcgen05 backend: if not NULL, c_scale * acc is ADDED into every GPU's copy of a
+                               symmetric buffer through this NVLink multicast address (multimem.red, reduced in the NVSwitch) instead
+                               of being stored to C -- the data-parallel gradient sum fused into the weight-gradient GEMM.  Same
+                               [M, ldc] indexing as C, 16-byte aligned; the buffers must be zero before the first contribution. */
+  float c_scale;            /* multicast mode only (e.g. 1 / world size) */
   /* QKV: N = 3*heads*dim_head; rows m = b*seq_n + p */
   void* q; void* k; void* v;                 /* [batch, heads, seq_n, dim_head] (dtype)                  */
   const float* cos_t; const float* sin_t;    /* [n_pos, dim_head/2] fp32, (1,0) on pass-through pairs; NULL = no rotary */
@@ -256,6 +261,10 @@ int dalle_b200_resid_scale(const void* y, int dtype, const float* resid, const f
 int dalle_b200_dropout(const void* x, void* y, int dtype, int64_t count, float p, uint64_t seed, uint64_t offset, void* stream);
 /* h[r,j] = u[r,j] * gelu_erf(u[r,hidden+j])   (fp32; transformer.py:106-109) -- the GEGLU step of EPI_GEGLU as a streaming pass */
 int dalle_b200_geglu_fwd(const float* u, float* h, int64_t rows, int hidden, void* stream);
+
+/* mc_dst[i] += scale * src[i] on EVERY GPU's copy of a symmetric buffer (multimem.red through the NVLink multicast address
+ * `mc_dst`, 16-byte aligned): how gradients that are not produced by a weight-gradient GEMM join the data-parallel sum. */
+int dalle_b200_mc_add(const float* src, void* mc_dst, int64_t count, float scale, void* stream);
 
 /* fp32 -> bf16 cast of `count` elements (weights are kept in fp32 and cast once per step) */
 int dalle_b200_cast_bf16(const float* src, void* dst, int64_t count, void* stream);

@@ -151,3 +151,25 @@ def test_patch_dalle_pytorch_rebinds_the_live_reference():
         undo()
     m = ref.DALLE(vae=vae, **kw)
     assert type(m.transformer.layers).__module__ == 'dalle_pytorch.reversible'
+
+
+def test_sparse_attention_layout_spec():
+    """The written layout spec of SparseAttention (attention.py docstring; reference attention.py:339-365): global text blocks,
+    local window, `num_random_blocks` unidirectional random blocks, reproducible from layout_seed."""
+    a = D.SparseAttention(64, 304, causal=True, heads=2, block_size=16, text_seq_len=48)
+    L = a.block_layout()
+    nb = 19
+    assert L.shape == (nb, nb) and a.num_global_blocks == 3 and a.num_random_blocks == 304 // 16 // 4
+    assert not torch.triu(L, 1).any()                                          # unidirectional
+    for r in range(nb):
+        assert L[r, :min(3, r + 1)].all()                                      # global (text) blocks at or before the row
+        assert L[r, 4 * (r // 4):r + 1].all()                                  # local window
+        extra = L[r].clone()
+        extra[:3] = False
+        extra[4 * (r // 4):r + 1] = False
+        assert int(extra.sum()) <= a.num_random_blocks                         # at most num_random_blocks more
+    assert torch.equal(L, D.SparseAttention(64, 304, heads=2, block_size=16, text_seq_len=48).block_layout())      # reproducible
+    assert not torch.equal(L, D.SparseAttention(64, 304, heads=2, block_size=16, text_seq_len=48, layout_seed=1).block_layout())
+    m = a.static_mask
+    assert m.shape == (304, 304) and torch.equal(m, L.repeat_interleave(16, 0).repeat_interleave(16, 1))
+    assert isinstance(a, D.Attention)                                          # transformer.py:279 decides cache support by this

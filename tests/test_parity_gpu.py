@@ -475,3 +475,34 @@ def test_dropout_matches_torch_with_the_same_masks(reversible):
     with D.compute_dtype_ctx(torch.float32):
         loss2 = m(text.cuda(), image.cuda(), return_loss=True)
     assert abs(float(loss2) - float(loss)) > 1e-6
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_sparse_attention_matches_dense_evaluation_of_its_layout(dtype):
+    """SparseAttention (reference attention.py:339-398, DeepSpeed block-sparse): forward and gradients equal a dense torch
+    evaluation of softmax over the documented layout (block_layout() expanded to tokens, intersected with causality), incl. a
+    sequence that is not a multiple of the block size (the reference pads and slices, :369-376, :398)."""
+    import dalle_pytorch_b200 as D
+    from dalle_oracle import attention_core
+    torch.manual_seed(17)
+    dim, heads, seq_len, n = 128, 2, 300, 300
+    a = D.SparseAttention(dim, seq_len, causal=True, heads=heads, block_size=16, text_seq_len=40).cuda()
+    x = torch.randn(2, n, dim, device='cuda', requires_grad=True)
+    ang = rotary_angle_table(41, 16, 64)[:n]
+    with D.compute_dtype_ctx(dtype):
+        out = a(x, rotary_pos_emb=ang.cuda()[None])
+        g = torch.randn_like(out)
+        out.backward(g)
+    allow = a.static_mask.cpu()[:n, :n] & torch.ones(n, n).tril().bool()
+    xr = x.detach().cpu().requires_grad_()
+    P = {k: v.detach().cpu().requires_grad_() for k, v in dict(w_qkv=a.to_qkv.weight, w_out=a.to_out[0].weight, b_out=a.to_out[0].bias).items()}
+    want = attention_core(xr, P['w_qkv'], P['w_out'], P['b_out'], heads, ang, allow, False)
+    want.backward(g.cpu())
+    tol = dict(rtol=RTOL, atol=2e-5) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
+    report('sparse attn out', out, want, **tol)
+    if dtype == torch.float32:
+        report('sparse attn dx', x.grad, xr.grad, RTOL, 2e-5)
+        report('sparse attn dWqkv', a.to_qkv.weight.grad, P['w_qkv'].grad, RTOL, 1e-4)
+        report('sparse attn dWout', a.to_out[0].weight.grad, P['w_out'].grad, RTOL, 1e-4)
+    else:
+        report('sparse attn dx', x.grad, xr.grad, 0.0, 0.05 * float(xr.grad.abs().max()))
