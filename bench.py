@@ -365,7 +365,7 @@ def measure_config(cfg_name, args, ctx, steps, want_e2e=True, want_clocks=True, 
         model = D.DALLE(**kw)
     model = model.to(dev).train()
     reducer = None
-    if backend is not None:
+    if backend is not None and os.environ.get('DALLE_B200_BENCH_NO_ALLREDUCE') != '1':      # (=1: N independent replicas, diagnosis only)
         backend.distribute(model=model)
         reducer = model.grad_reducer
     seq = c['text_seq_len'] + c['fmap'] ** 2

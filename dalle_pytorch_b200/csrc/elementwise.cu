@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(LN_THREADS) ln_shift_bwd_kernel(db200_ln_shift
   float* accg = sm + 2 * d;   // [d] dgamma partial
   float* accb = sm + 3 * d;   // [d] dbeta partial
   for (int c = threadIdx.x; c < d; c += LN_THREADS) { accg[c] = 0.f; accb[c] = 0.f; }
+  __syncthreads();            // the accumulation below uses a different thread <-> channel mapping (compute-sanitizer racecheck, r02)
   const TI* dA = reinterpret_cast<const TI*>(P.d_out);
   const int rows = P.batch * n;
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {

@@ -149,6 +149,10 @@ class GradAllReducer:
         # overlap=False: nothing is launched during backward; finish() reduces the whole flat buffer with ONE collective (the
         # collective's CTAs then never compete with the backward GEMMs for SMs / HBM; its time is fully exposed)
         self.overlap = (os.environ.get('DALLE_B200_DP_OVERLAP', '1') != '0') if overlap is None else bool(overlap)
+        # compress='bf16': the buckets cross NVLink as bf16 (cast -> all-reduce -> cast back into the fp32 buffer): half the bytes,
+        # at the price of rounding every rank's gradient to 8 mantissa bits before the sum (opt-in)
+        self.compress = os.environ.get('DALLE_B200_DP_COMPRESS', '') == 'bf16'
+        self._staged = []
         self.auto_finish = auto_finish      # finish() runs as an autograd end-of-backward callback
         self._sync, self._finished, self._cb_queued = True, False, False
         self._direct_pass = set()        # parameters delivered through direct_done() in the running backward pass
@@ -196,7 +200,10 @@ class GradAllReducer:
         for bi, (_, _, ps) in enumerate(self.buckets):
             for p in ps:
                 self.bucket_of[p] = bi
-        self._has_avg = dist.is_initialized() and dist.get_backend(process_group) == 'nccl'
+        # DALLE_B200_DP_OP=sum: all-reduce SUM and scale afterwards (ncclAvg is a pre-multiplied sum that the in-switch NVLS reduction
+        # does not implement, NCCL then falls back to ring kernels)
+        self._has_avg = (dist.is_initialized() and dist.get_backend(process_group) == 'nccl' and
+                         os.environ.get('DALLE_B200_DP_OP', 'avg') != 'sum')
         self._seen = set()
         self._pending = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
@@ -298,9 +305,16 @@ class GradAllReducer:
         s, e, _ = self.buckets[bi]
         self._launched[bi] = True
         if self.world > 1 and self.mc is None:
-            # AVG folds the 1/world into the collective (NCCL); gloo (CPU tests) has no AVG -> SUM + scale in finish()
-            op = dist.ReduceOp.AVG if (self.average and self._has_avg) else dist.ReduceOp.SUM
-            self._works.append(dist.all_reduce(self.flat[s:e], op=op, group=self.pg, async_op=True))
+            self._reduce_range(s, e)
+
+    def _reduce_range(self, s, e):
+        # AVG folds the 1/world into the collective (NCCL); gloo (CPU tests) has no AVG -> SUM + scale in finish()
+        op = dist.ReduceOp.AVG if (self.average and self._has_avg) else dist.ReduceOp.SUM
+        buf = self.flat[s:e]
+        if self.compress and self._has_avg:
+            buf = buf.to(torch.bfloat16)
+            self._staged.append((buf, s, e))
+        self._works.append(dist.all_reduce(buf, op=op, group=self.pg, async_op=True))
 
     def _adopt(self, p):
         v = self.views[p]
@@ -376,8 +390,7 @@ class GradAllReducer:
             for bi in range(len(self.buckets)):
                 self._launched[bi] = True
             if self.world > 1:
-                op = dist.ReduceOp.AVG if (self.average and self._has_avg) else dist.ReduceOp.SUM
-                self._works.append(dist.all_reduce(self.flat, op=op, group=self.pg, async_op=True))
+                self._reduce_range(0, self.flat.numel())
         for bi, (_, _, ps) in enumerate(self.buckets):
             if not self._launched[bi]:
                 for p in ps:
@@ -387,6 +400,9 @@ class GradAllReducer:
         for w in self._works:
             w.wait()
         self._works = []
+        for buf, s0, e0 in self._staged:
+            self.flat[s0:e0].copy_(buf)
+        self._staged = []
         if self.average and self.world > 1 and not self._has_avg:
             self.flat.mul_(1.0 / self.world)
         self._finished = True

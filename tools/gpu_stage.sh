@@ -28,6 +28,12 @@ for stage in "$@"; do
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph --extra "" > gpurun_out/ncu_list.log 2>&1; tail -3 gpurun_out/ncu_list.log ;;
     ncu_list_c3) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_c3.csv python bench.py --config c3 --steps 1 --warmup 3 --no-cpu-baseline --no-graph --extra '' > gpurun_out/ncu_list_c3.log 2>&1; tail -3 gpurun_out/ncu_list_c3.log ;;
     attn_probe_tc) for pat in full axial_row axial_col; do timeout 120 python tools/attn_probe.py --backend tc --pattern $pat; done 2>&1 | grep "^\[" | tee gpurun_out/attn_probe.log; for pat in axial_row axial_col; do timeout 120 python tools/attn_probe.py --backend tc --pattern $pat --gather 0; done 2>&1 | grep "^\[" | tee -a gpurun_out/attn_probe.log ;;
+    sanitizer) SEL="test_ln_shift_fwd_bwd or (test_gemm_store_all_majors and 96-64-72) or test_gemm_resid_geglu_epilogues or (test_attention_fwd_bwd_patterns and 24-9-4) or (test_axial_gather_kernels and 21-16) or test_dropout_kernel or test_scale_bwd_colsum or test_token_embedding"
+      for tool in memcheck racecheck; do
+        timeout 900 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 1 python -m pytest tests/test_kernels_gpu.py -q --no-header -p no:cacheprovider -x -k "$SEL" > gpurun_out/sanitizer_$tool.log 2>&1
+        echo "$tool rc=$?"; grep -E "ERROR SUMMARY|passed|failed|RACECHECK SUMMARY" gpurun_out/sanitizer_$tool.log | tail -3
+      done ;;
+    ncu_attn_gather) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_.*tc_kernel -s 3 -c 3 -o gpurun_out/prof_attn_gather -f python tools/attn_probe.py --backend tc --pattern axial_col --iters 1 > gpurun_out/ncu_attn_gather.log 2>&1; tail -2 gpurun_out/ncu_attn_gather.log ;;
     ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 44 -c 20 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph --extra "" > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log ;;
     *) echo "unknown stage $stage" ;;
   esac
