@@ -487,6 +487,45 @@ def measure_config(cfg_name, args, ctx, steps, want_e2e=True, want_clocks=True, 
     return res
 
 
+def measure_decode(args, ctx, cfg_name='c2', batch=16):
+    """Autoregressive image generation with the KV cache (generate_images(use_cache=True), dalle_pytorch.py:506-562): image tokens
+    per second on one GPU -- cached attention over the in-place KV cache, library sampling kernel, one token per step."""
+    import gc
+    import torch
+    import dalle_pytorch_b200 as D
+    from dalle_pytorch_b200 import ops
+    dev = ctx['dev']
+    c = CONFIGS[cfg_name]
+    D.set_compute_dtype(torch.bfloat16)
+    torch.manual_seed(0)
+    vae = D.TokenVAE(image_size=8 * c['fmap'], num_layers=3, num_tokens=NUM_IMAGE_TOKENS)
+    model = D.DALLE(dim=c['dim'], vae=vae, num_text_tokens=NUM_TEXT_TOKENS, text_seq_len=c['text_seq_len'], depth=c['depth'], heads=c['heads'],
+                    dim_head=64, attn_types=c['attn_types']).to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    text = torch.randint(1, NUM_TEXT_TOKENS, (batch, c['text_seq_len']), generator=g).to(dev)
+    n_img = c['fmap'] ** 2
+    with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+        model.generate_images(text[:2], use_cache=True)          # warm-up (allocator, caches)
+        torch.cuda.synchronize()
+        n0 = ops.launches()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        img = model.generate_images(text, use_cache=True)
+        e.record()
+        torch.cuda.synchronize()
+    ms = s.elapsed_time(e)
+    assert img.shape == (batch, n_img) and int(img.min()) >= 0 and int(img.max()) < NUM_IMAGE_TOKENS
+    out = {'workload': f'{cfg_name} weights, generate_images(use_cache=True): {n_img} image tokens after {c["text_seq_len"]} text tokens, batch {batch}, '
+                       'filter_thres 0.5, temperature 1, bf16',
+           'value': batch * n_img / (ms / 1e3), 'unit': 'generated image tokens/s', 'ms_per_token_step': ms / n_img, 'total_ms': ms,
+           'library_kernels_per_token_step': (ops.launches() - n0) / n_img, 'n_gpus': 1}
+    log(f"decode: {out['value']:.0f} image tokens/s ({out['ms_per_token_step']:.3f} ms per step of {batch} sequences)")
+    del model
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
 def leg_summary(res, world, peak_tf):
     """Compact per-configuration entry for `extra_configs`."""
     c = res['c']
@@ -544,6 +583,14 @@ def run_gpu_arm(args):
             extra_res.append({'cfg': name, 'error': f'{type(ex).__name__}: {ex}'})
             torch.cuda.empty_cache()
 
+    decode = None
+    if world == 1 and args.extra is None and args.config == 'c2' and not args.batch and not args.dtype:
+        try:
+            decode = measure_decode(args, ctx)
+        except Exception as ex:
+            log(f'decode leg failed: {type(ex).__name__}: {ex}')
+            decode = {'error': f'{type(ex).__name__}: {str(ex)[:200]}'}
+            torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
         if rank != 0:
@@ -628,6 +675,8 @@ def run_gpu_arm(args):
         out['gpu_eager_baseline'] = eager
     if extra_res:
         out['extra_configs'] = {r['cfg']: (leg_summary(r, world, peak_tf) if 'error' not in r else r) for r in extra_res}
+    if decode is not None:
+        out.setdefault('extra_configs', {})['decode_c2'] = decode
     if 'ms_train' in main_res:
         out['train_step'] = {'ms_per_step': main_res['ms_train'] / args.steps, 'tokens_per_s': tokens_per_step * args.steps / (main_res['ms_train'] / 1e3),
                              'optimizer': 'FusedAdam lr=3e-4 betas=(0.9,0.999) clip_grad_norm 0.5 (2 launches over flat fp32 buffers)'}

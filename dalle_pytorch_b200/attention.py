@@ -135,7 +135,10 @@ class Attention(_AttentionBase):
 
     @torch.no_grad()
     def _cached_forward(self, x, mask, rotary_pos_emb, cache, cache_key):
-        """KV-cache decoding (attention.py:61, 71-76, 84-92): queries are the last n positions of the cached keys."""
+        """KV-cache decoding (attention.py:61, 71-76, 84-92): queries are the last n positions of the cached keys.  The cache is
+        IN PLACE: one [b, h, seq_len, dh] buffer pair per layer, allocated at the first call; every step writes its new rows behind
+        the valid ones and the attention kernel is told how many rows are valid (db200_attn_fwd_params::kv_rows) -- the reference
+        re-allocates and copies the whole cache with torch.cat at every token."""
         dtype = config.compute_dtype()
         b, n, d = x.shape
         offset = cache.get('offset', 0)
@@ -143,15 +146,28 @@ class Attention(_AttentionBase):
         a, _, _ = ops.ln_shift_fwd(x.float().contiguous(), None, None, dtype, 0, 1, do_ln=False, do_shift=False)
         wq, wo = _w(self.to_qkv.weight, dtype), _w(self.to_out[0].weight, dtype)        # cached bf16 copies in bf16 mode
         q, k, v = ops.gemm_qkv(a, wq, b, n, self.heads, self.dim_head, cos_t, sin_t, self.scale, pos_offset=offset)
-        if offset > 0:
-            k_top, v_top = cache[cache_key]
-            k = torch.cat([k_top.to(k.dtype), k], dim=-2).contiguous()
-            v = torch.cat([v_top.to(v.dtype), v], dim=-2).contiguous()
-        cache[cache_key] = k, v
-        n_k = k.shape[-2]
-        o, _ = ops.attn_fwd(self.attn_spec(n_k), q, k, v, _key_mask_u8(mask, n_k))
+        n_k = offset + n
+        ent = cache.get(cache_key)
+        cap = max(self.seq_len + 1, n_k)
+        if (not isinstance(ent, _KVCache) or ent.k.shape[0] != b or ent.k.shape[2] < n_k or ent.k.dtype != k.dtype or ent.k.device != k.device
+                or offset == 0):
+            # (zero-filled once: the tensor-core kernels load whole 64-row tiles and multiply the rows behind n_k by exact zeros)
+            ent = _KVCache(torch.zeros(b, self.heads, cap, self.dim_head, device=k.device, dtype=k.dtype),
+                           torch.zeros(b, self.heads, cap, self.dim_head, device=k.device, dtype=k.dtype))
+            cache[cache_key] = ent
+        ent.k[:, :, offset:n_k].copy_(k)
+        ent.v[:, :, offset:n_k].copy_(v)
+        o, _ = ops.attn_fwd(self.attn_spec(n_k), q, ent.k, ent.v, _key_mask_u8(mask, n_k), n_k=n_k)
         out, _ = ops.gemm_resid(o.view(b * n, -1), wo, self.to_out[0].bias.detach(), None, None, 1.0)
         return out.view(b, n, d)
+
+
+class _KVCache:
+    """In-place key/value cache of one attention layer (the `cache[cache_key]` entry of attention.py:71-76)."""
+    __slots__ = ('k', 'v')
+
+    def __init__(self, k, v):
+        self.k, self.v = k, v
 
 
 class SparseAxialCausalAttention(_AttentionBase):

@@ -53,6 +53,8 @@ int cast_bf16_launch(const float* src, void* dst, int64_t count, cudaStream_t st
 int split_bf16x3_launch(const float* src, void* dst, int64_t rows, int cols, int concat_rows, int pat, cudaStream_t st);
 int resid_scale_launch(const void* y, int dtype, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, cudaStream_t st);
 int mc_add_launch(const float* src, void* mc_dst, int64_t count, float scale, cudaStream_t st);
+int sample_topk_gumbel_launch(const void* logits, int dtype, int rows, int vocab, long long ld, int k, float temperature, const float* gumbel,
+                              unsigned long long seed, unsigned long long offset, long long* out, cudaStream_t st);
 int dropout_launch(const void* x, void* y, int dtype, int64_t count, float p, unsigned long long seed, unsigned long long offset, cudaStream_t st);
 int geglu_fwd_launch(const float* u, float* h, int64_t rows, int hidden, cudaStream_t st);
 int axpby_launch(const float* a, const float* b, float alpha, float* y, int64_t count, cudaStream_t st);
@@ -225,6 +227,7 @@ static int check_attn(const db200_attn_fwd_params& f, const char* who) {
   if (f.pattern == DB200_ATTN_AXIAL_ROW || f.pattern == DB200_ATTN_AXIAL_COL || f.pattern == DB200_ATTN_CONV_LIKE)
     DB200_CHECK_ARG(f.fmap > 0 && f.text_len > 0, "%s: sparse pattern needs text_len / fmap", who);
   if (f.pattern == DB200_ATTN_CONV_LIKE) DB200_CHECK_ARG(f.kernel_size > 0 && (f.kernel_size & 1) && f.dilation > 0, "%s: conv_like kernel_size must be odd", who);
+  DB200_CHECK_ARG(f.kv_rows == 0 || (f.kv_rows >= f.n_k && !f.gather), "%s: kv_rows must be >= n_k (and is not combined with gather)", who);
   if (f.gather) {      // the caller has laid q/k/v/lse out for the gathered kernels: there is no other backend to fall back to
     const char* why = nullptr;
     if (!attn_gather_ok(f, &why)) return set_error(DB200_ERR_UNSUPPORTED, "%s: %s", who, why);
@@ -249,6 +252,7 @@ int dalle_b200_attn_bwd(const db200_attn_bwd_params* p, void* stream) {
   DB200_CHECK_ARG(p != nullptr, "attn_bwd: null params");
   const int rc = check_attn(p->f, "attn_bwd");
   if (rc) return rc;
+  DB200_CHECK_ARG(p->f.kv_rows == 0 || p->f.kv_rows == p->f.n_k, "attn_bwd: kv_rows (in-place KV cache) is a forward-only layout");
   DB200_CHECK_ARG(p->f.n_q == p->f.n_k, "attn_bwd: training only (n_q == n_k)");
   DB200_CHECK_ARG(p->d_out && p->delta && p->dqkv, "attn_bwd: null tensor");
   DB200_CHECK_ARG((p->cos_t == nullptr) == (p->sin_t == nullptr), "attn_bwd: cos/sin tables must come together");
@@ -307,6 +311,14 @@ int dalle_b200_resid_scale(const void* y, int dtype, const float* resid, const f
 int dalle_b200_mc_add(const float* src, void* mc_dst, int64_t count, float scale, void* stream) {
   DB200_CHECK_ARG(src && mc_dst && count >= 0 && aligned16(src) && aligned16(mc_dst), "mc_add: bad args (16-byte aligned fp32 buffers)");
   return mc_add_launch(src, mc_dst, count, scale, (cudaStream_t)stream);
+}
+
+int dalle_b200_sample_topk_gumbel(const void* logits, int dtype, int rows, int vocab, int64_t ld, int k, float temperature, const float* gumbel,
+                                  uint64_t seed, uint64_t offset, int64_t* out, void* stream) {
+  DB200_CHECK_ARG(logits && out && rows >= 0 && vocab > 0 && ld >= vocab && dtype_ok(dtype), "sample_topk_gumbel: bad args");
+  DB200_CHECK_ARG(k >= 1 && k <= vocab && temperature > 0.f, "sample_topk_gumbel: need 1 <= k <= vocab and temperature > 0");
+  if ((size_t)vocab * 4 > 200 * 1024) return set_error(DB200_ERR_UNSUPPORTED, "sample_topk_gumbel: vocab=%d does not fit the shared-memory row buffer", vocab);
+  return sample_topk_gumbel_launch(logits, dtype, rows, vocab, ld, k, temperature, gumbel, seed, offset, reinterpret_cast<long long*>(out), (cudaStream_t)stream);
 }
 
 int dalle_b200_dropout(const void* x, void* y, int dtype, int64_t count, float p, uint64_t seed, uint64_t offset, void* stream) {

@@ -13,6 +13,7 @@ struct AttnGeom {
   // coordinates, `col` says the virtual image order is column-major (axis = 1), rows per (b,h) of q/k/v = n_alloc,
   // entries per (b,h) of lse / delta = n_stat, t_pad = text_len rounded up to 64.
   int gather, col, n_alloc, n_stat, t_pad;
+  int kv_rows;                        // rows allocated per (b,h) in k / v (>= n_k: in-place KV cache of the decoding path)
 };
 
 // layout constants of the gathered mode, shared with the host (ops.py mirrors them)
@@ -26,6 +27,7 @@ inline AttnGeom make_geom(const db200_attn_fwd_params& p) {
   g.ksize = p.kernel_size; g.dil = p.dilation > 0 ? p.dilation : 1;
   g.n_q = p.n_q; g.n_k = p.n_k; g.static_mask = p.static_mask; g.static_ld = p.static_ld;
   g.gather = p.gather != 0; g.col = 0; g.n_alloc = p.n_k; g.n_stat = p.n_q; g.t_pad = 0;
+  g.kv_rows = p.kv_rows > p.n_k ? p.kv_rows : p.n_k;
   if (g.gather) {
     g.col = p.pattern == DB200_ATTN_AXIAL_COL;
     g.pattern = DB200_ATTN_AXIAL_ROW;           // column attention IS row attention in the column-major virtual order

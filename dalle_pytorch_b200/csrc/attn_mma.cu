@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(128) attn_fwd_mma_kernel(FwdPtrs P, AttnGeom g
   const int q0 = blockIdx.x * T64;
   const int off = g.n_k - g.n_q;
   const bf16* Q = P.q + (long long)bh * g.n_q * DH;
-  const bf16* K = P.k + (long long)bh * g.n_k * DH;
-  const bf16* V = P.v + (long long)bh * g.n_k * DH;
+  const bf16* K = P.k + (long long)bh * g.kv_rows * DH;      // kv_rows >= n_k rows are allocated per (b,h)
+  const bf16* V = P.v + (long long)bh * g.kv_rows * DH;
   const uint8_t* km = P.key_mask ? P.key_mask + (long long)b * g.n_k : nullptr;
   const uint32_t sq = smem_u32(sQ), sk[2] = {smem_u32(sK[0]), smem_u32(sK[1])}, sv[2] = {smem_u32(sV[0]), smem_u32(sV[1])};
 

@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(256) attn_fwd_simt_kernel(AttnPtrs P, AttnGeom
   const int q0 = blockIdx.x * TQ;
   const int off = g.n_k - g.n_q;                       // absolute position of query 0
   const T* Q = reinterpret_cast<const T*>(P.q) + (long long)bh * g.n_q * DH;     // q: [b,h,n_q,64]
-  const T* K = reinterpret_cast<const T*>(P.k) + (long long)bh * g.n_k * DH;
-  const T* V = reinterpret_cast<const T*>(P.v) + (long long)bh * g.n_k * DH;
+  const T* K = reinterpret_cast<const T*>(P.k) + (long long)bh * g.kv_rows * DH;      // kv_rows >= n_k rows are allocated per (b,h)
+  const T* V = reinterpret_cast<const T*>(P.v) + (long long)bh * g.kv_rows * DH;
   const uint8_t* km = P.key_mask ? P.key_mask + (long long)b * g.n_k : nullptr;
 
   load_rows<T>(Qs, Q, DH, q0, g.n_q);

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
   const int q0 = SQ.origin(qt), q_lim = SQ.limit(qt);       // valid queries of this tile: [q0, q_lim)
   const int off = g.n_k - g.n_q;
   const int q_last = q_lim - 1;
-  const int rows_q = g.gather ? g.n_alloc : g.n_q, rows_k = g.gather ? g.n_alloc : g.n_k;   // rows per (b,h) of q / k,v
+  const int rows_q = g.gather ? g.n_alloc : g.n_q, rows_k = g.gather ? g.n_alloc : g.kv_rows;   // rows per (b,h) of q / k,v
   uint32_t* tlist = reinterpret_cast<uint32_t*>(smem + L::LIST_OFF);
   if (warp == 2) {                              // key tiles of this query tile, once per CTA (geometry only: before pdl_wait)
     const bool no_km = P.key_mask == nullptr;
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(192, FKT == 32 ? 4 : 2) attn_fwd_tc2_kernel(co
   const int q0 = SQ.origin(qt), q_lim = SQ.limit(qt);
   const int off = g.n_k - g.n_q;
   const int q_last = q_lim - 1;
-  const int rows_q = g.gather ? g.n_alloc : g.n_q, rows_k = g.gather ? g.n_alloc : g.n_k;
+  const int rows_q = g.gather ? g.n_alloc : g.n_q, rows_k = g.gather ? g.n_alloc : g.kv_rows;
   uint32_t* tlist = reinterpret_cast<uint32_t*>(smem + L::LIST_OFF);
   if (warp == 2) {                              // key tiles of this query tile, once per CTA (geometry only: before pdl_wait)
     const bool no_km = P.key_mask == nullptr;
@@ -1267,7 +1267,7 @@ int launch_fwd(const db200_attn_fwd_params& p, cudaStream_t st) {
   CUtensorMap tmQ, tmK, tmV;
   const AttnGeom g = make_geom(p);
   const uint64_t bh = (uint64_t)p.batch * p.heads;
-  const uint64_t rows_q = g.gather ? g.n_alloc : p.n_q, rows_k = g.gather ? g.n_alloc : p.n_k;
+  const uint64_t rows_q = g.gather ? g.n_alloc : p.n_q, rows_k = g.gather ? g.n_alloc : g.kv_rows;
   int rc = make_tensor_map_bf16(&tmQ, p.q, DH, bh * rows_q, DH, DH, TQ);
   if (rc) return rc;
   if ((rc = make_tensor_map_bf16(&tmK, p.k, DH, bh * rows_k, DH, DH, FK))) return rc;

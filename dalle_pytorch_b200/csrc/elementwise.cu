@@ -1276,6 +1276,111 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Decoding: top-k filtering + Gumbel-max sampling of one token per row in ONE launch (dalle_pytorch.py:43-58, 533-539:
+// top_k(logits, thres) keeps the k = max(int((1 - thres) * V), 1) largest logits, gumbel_sample draws
+// argmax(logits / temperature + g), g = -log(-log(u))).  One CTA per row: the row is converted to order-preserving integer keys
+// in shared memory, the k-th largest key is found by a 4-pass radix select (8 bits per pass, shared-memory histogram), then the
+// block takes the arg-max of logit / T + g over the keys at or above it.  g comes from Philox4x32-10(seed, offset + element / 4)
+// or, for tests, from an explicit [rows, V] tensor.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int SAMPLE_THREADS = 512;
+__device__ __forceinline__ uint32_t float_key(float v) {            // ascending key order == ascending float order
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SAMPLE_THREADS) sample_topk_gumbel_kernel(const T* __restrict__ logits, int V, long long ld, int k, float inv_temp,
+                                                                           const float* __restrict__ gumbel, unsigned long long seed,
+                                                                           unsigned long long offset, long long* __restrict__ out) {
+  extern __shared__ uint32_t keys[];                                  // [V]
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_prefix, s_remaining;
+  __shared__ float s_val[SAMPLE_THREADS / 32];
+  __shared__ int s_idx[SAMPLE_THREADS / 32];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const T* lrow = logits + (long long)row * ld;
+  for (int i = tid; i < V; i += SAMPLE_THREADS) keys[i] = float_key(to_f32(lrow[i]));
+  if (tid == 0) { s_prefix = 0u; s_remaining = static_cast<uint32_t>(k); }
+  __syncthreads();
+  uint32_t mask = 0u;
+  for (int pass = 3; pass >= 0; --pass) {
+    const int shift = pass * 8;
+    if (tid < 256) hist[tid] = 0u;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    for (int i = tid; i < V; i += SAMPLE_THREADS) {
+      const uint32_t key = keys[i];
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {                                                   // walk the bins from the top: which digit holds the k-th largest
+      uint32_t cum = 0u, rem = s_remaining;
+      int b = 255;
+      for (; b > 0; --b) {
+        if (cum + hist[b] >= rem) break;
+        cum += hist[b];
+      }
+      s_remaining = rem - cum;
+      s_prefix = prefix | (static_cast<uint32_t>(b) << shift);
+    }
+    mask |= 0xffu << shift;
+    __syncthreads();
+  }
+  const uint32_t kth = s_prefix;                                      // key of the k-th largest logit
+  const uint2 pkey = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  for (int i = tid; i < V; i += SAMPLE_THREADS) {
+    if (keys[i] < kth) continue;
+    float g;
+    if (gumbel) g = gumbel[(long long)row * V + i];
+    else {
+      const unsigned long long e = (unsigned long long)row * V + i, c = offset + (e >> 2);
+      const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32), 0u, 0u), pkey);
+      const uint32_t w = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
+      const float u = (static_cast<float>(w >> 8) + 0.5f) * (1.0f / 16777216.0f);        // (0, 1)
+      g = -logf(-logf(u + 1e-20f) + 1e-20f);                         // dalle_pytorch.py:50-52
+    }
+    const float v = to_f32(lrow[i]) * inv_temp + g;
+    if (v > best || (v == best && i < best_i)) { best = v; best_i = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+  }
+  if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = best_i; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < SAMPLE_THREADS / 32; ++w)
+      if (s_val[w] > best || (s_val[w] == best && s_idx[w] < best_i)) { best = s_val[w]; best_i = s_idx[w]; }
+    out[row] = best_i;
+  }
+}
+
+int sample_topk_gumbel_launch(const void* logits, int dtype, int rows, int vocab, long long ld, int k, float temperature, const float* gumbel,
+                              unsigned long long seed, unsigned long long offset, long long* out, cudaStream_t st) {
+  if (rows == 0) return DB200_OK;
+  const size_t smem = (size_t)vocab * 4;
+  static std::atomic<bool> attr_done{false};
+  if (!attr_done.load(std::memory_order_acquire)) {
+    DB200_CUDA_OK(cudaFuncSetAttribute(sample_topk_gumbel_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DB200_CUDA_OK(cudaFuncSetAttribute(sample_topk_gumbel_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done.store(true, std::memory_order_release);
+  }
+  const float inv_temp = 1.0f / temperature;
+  if (dtype == DB200_F32)
+    sample_topk_gumbel_kernel<float><<<rows, SAMPLE_THREADS, smem, st>>>(reinterpret_cast<const float*>(logits), vocab, ld, k, inv_temp, gumbel, seed, offset, out);
+  else
+    sample_topk_gumbel_kernel<__nv_bfloat16><<<rows, SAMPLE_THREADS, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(logits), vocab, ld, k, inv_temp, gumbel,
+                                                                               seed, offset, out);
+  DB200_LAUNCH_OK("sample_topk_gumbel_kernel");
+  return DB200_OK;
+}
+
 static int grid_for(long long work) {
   long long blocks = (work + 255) / 256;
   const long long cap = (long long)sm_count() * 16;

@@ -7,6 +7,8 @@ from torch import nn
 import torch.nn.functional as F
 
 from .transformer import Transformer, DivideMax
+from . import ops
+from .functional import DropoutRNG
 
 
 def exists(val):
@@ -178,8 +180,13 @@ class DALLE(nn.Module):
             text, image = out[:, :text_seq_len], out[:, text_seq_len:]
             logits = self.forward_with_cond_scale(text, image, cond_scale=cond_scale, cache=cache)
             logits = logits[:, -1, :]
-            filtered_logits = top_k(logits, thres=filter_thres)
-            sample = gumbel_sample(filtered_logits, temperature=temperature, dim=-1)
+            if logits.is_cuda and logits.shape[-1] * 4 <= 200 * 1024:
+                # top_k + gumbel_sample (dalle_pytorch.py:533-539) as one library launch; the Philox pair follows torch's generator
+                seed, off = DropoutRNG.draw(logits.numel())
+                sample = ops.sample_topk_gumbel(logits.contiguous(), filter_thres, temperature, seed, off)
+            else:
+                filtered_logits = top_k(logits, thres=filter_thres)
+                sample = gumbel_sample(filtered_logits, temperature=temperature, dim=-1)
             sample -= (num_text_tokens if is_image else 0)
             out = torch.cat((out, sample[:, None]), dim=-1)
 

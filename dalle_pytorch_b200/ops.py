@@ -190,6 +190,18 @@ def resid_scale(y, resid, scale, sign):
     return out
 
 
+def sample_topk_gumbel(logits, thres=0.5, temperature=1.0, seed=0, offset=0, gumbel=None):
+    """logits [B, V] -> int64 [B]: top_k(logits, thres) + gumbel_sample(., temperature) of dalle_pytorch.py:43-58 in one launch."""
+    B, V = logits.shape
+    assert logits.stride(1) == 1
+    k = max(int((1 - thres) * V), 1)
+    out = torch.empty(B, device=logits.device, dtype=torch.int64)
+    _lib.check(_lib.lib().dalle_b200_sample_topk_gumbel(_p(logits), dt_code(logits.dtype), B, V, logits.stride(0), k, float(temperature), _p(gumbel),
+                                                        int(seed) & (2 ** 64 - 1), int(offset), _p(out), _stream()), 'sample_topk_gumbel')
+    _count()
+    return out
+
+
 def dropout_(x, p, seed, offset):
     """In place: x[i] <- keep(i) ? x[i] / (1 - p) : 0 with the Philox mask of (seed, offset) (include/dalle_b200.h)."""
     _lib.check(_lib.lib().dalle_b200_dropout(_p(_c(x)), _p(x), dt_code(x.dtype), x.numel(), float(p), int(seed) & (2 ** 64 - 1), int(offset), _stream()),
@@ -374,29 +386,36 @@ def gather_layout(spec, dtype, n, dim_head=64, key_mask=None):
     return GatherLayout(spec, n)
 
 
-def _attn_params(spec, q, k, v, out, lse, key_mask, lay=None):
+def _attn_params(spec, q, k, v, out, lse, key_mask, lay=None, n_k=None):
     b, h, n_q, dh = q.shape
-    n_k = k.shape[2]
+    kv_rows = 0
+    if n_k is not None:                 # in-place KV cache: k, v are [b, h, capacity, dh] buffers, the first n_k rows valid
+        kv_rows, n_k = k.shape[2], int(n_k)
+        assert n_k <= kv_rows
+    else:
+        n_k = k.shape[2]
     if lay is not None:
         assert n_q == n_k == lay.n_alloc, 'gathered layout: q/k/v must carry n_alloc rows per head'
         n_q = n_k = lay.n
     sm = spec.static_mask
     return _lib.AttnFwdParams(batch=b, heads=h, n_q=n_q, n_k=n_k, dim_head=dh, dtype=dt_code(q.dtype), pattern=spec.pattern,
                               causal=int(spec.causal), stable=int(spec.stable), text_len=spec.text_len, fmap=spec.fmap,
-                              kernel_size=spec.kernel_size, dilation=spec.dilation, gather=int(lay is not None), key_mask=_p(key_mask),
+                              kernel_size=spec.kernel_size, dilation=spec.dilation, gather=int(lay is not None), kv_rows=kv_rows,
+                              key_mask=_p(key_mask),
                               static_mask=_p(sm), static_ld=(sm.shape[1] if sm is not None else 0),
                               q=_p(_c(q)), k=_p(_c(k)), v=_p(_c(v)), out=_p(out), lse=_p(lse))
 
 
-def attn_fwd(spec, q, k, v, key_mask=None, lay=None):
+def attn_fwd(spec, q, k, v, key_mask=None, lay=None, n_k=None):
     """q [b,h,n_q,64], k,v [b,h,n_k,64] -> out [b,n_q,h*64], lse [b,h,n_q]
-    (lay = GatherLayout: q,k,v [b,h,n_alloc,64] -> out [b,n,h*64], lse [b,h,n_stat])"""
+    (lay = GatherLayout: q,k,v [b,h,n_alloc,64] -> out [b,n,h*64], lse [b,h,n_stat];
+     n_k = valid rows of k, v when they are [b,h,capacity,64] in-place KV-cache buffers)"""
     b, h, n_q, dh = q.shape
     if lay is not None:
         n_q = lay.n
     out = torch.empty(b, n_q, h * dh, device=q.device, dtype=q.dtype)
     lse = torch.empty(b, h, lay.n_stat if lay is not None else n_q, device=q.device, dtype=torch.float32)
-    P = _attn_params(spec, q, k, v, out, lse, key_mask, lay)
+    P = _attn_params(spec, q, k, v, out, lse, key_mask, lay, n_k)
     _lib.check(_lib.lib().dalle_b200_attn_fwd(ctypes.byref(P), _stream()), 'attn_fwd')
     _count()
     return out, lse

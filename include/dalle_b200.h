@@ -182,6 +182,10 @@ typedef struct {
   int text_len, fmap;
   int kernel_size, dilation;            /* CONV_LIKE */
   int gather;               /* AXIAL_ROW / AXIAL_COL, bf16, training shapes only: gathered axial tiling, see below */
+  int kv_rows;              /* forward only: rows allocated per (batch, head) in k and v (0 = n_k).  > n_k: an in-place KV cache --
+                               k, v are [batch, heads, kv_rows, 64] buffers of which the first n_k rows are valid (attention.py:71-76
+                               grows the cache with torch.cat instead); the rows behind them must hold finite values (zero-fill
+                               the buffers once) */
   const uint8_t* key_mask;  /* optional [batch, n_k] 1 = keep (attention.py:80-83) */
   const uint8_t* static_mask; int64_t static_ld;   /* STATIC: [n, static_ld] 1 = allowed */
   const void* q; const void* k; const void* v;
@@ -254,6 +258,13 @@ int dalle_b200_split_bf16x3(const float* src, void* dst, int64_t rows, int cols,
  * EPI_RESID as a streaming pass (transformer.py:88, reversible.py:139-140), used by the bf16x6 parity mode and when dropout sits
  * between the projection and the LayerScale; y is `dtype`, everything else fp32 */
 int dalle_b200_resid_scale(const void* y, int dtype, const float* resid, const float* scale, float sign, float* out, int64_t rows, int d, void* stream);
+/* Decoding (generate_images, dalle_pytorch.py:533-539): out[r] = argmax_i(logits[r,i] / temperature + g[r,i]) over the k largest
+ * logits of row r -- top_k(logits, thres) with k = max(int((1 - thres) * vocab), 1) followed by gumbel_sample, in one launch per
+ * step.  g = -log(-log(u)) with u from Philox4x32-10(seed, offset + (r*vocab + i) / 4), or read from `gumbel` [rows, vocab] fp32 when
+ * that pointer is not NULL (tests).  logits: [rows, ld] (dtype), out: int64 [rows]. */
+int dalle_b200_sample_topk_gumbel(const void* logits, int dtype, int rows, int vocab, int64_t ld, int k, float temperature, const float* gumbel,
+                                  uint64_t seed, uint64_t offset, int64_t* out, void* stream);
+
 /* Dropout with a counter-based generator (attention.py:53-56, transformer.py:117): y[i] = keep(i) ? x[i] / (1 - p) : 0 where
  * keep(i) = word (i & 3) of Philox4x32-10(key = seed, counter = offset + i / 4) <= (1 - p) * 2^32.  In place allowed (y == x).
  * The mask is a pure function of (seed, offset, i): pass the same pair to the backward pass (on the gradient) and to the

@@ -528,3 +528,55 @@ def test_dropout_kernel_mask_properties():
     x = torch.randn(1003, device=dev())                                                # ragged tail
     y = o.dropout_(x.clone(), 0.5, 9, 0)
     assert torch.equal((y != 0), (o.dropout_(torch.ones_like(x), 0.5, 9, 0) != 0)) and torch.allclose(y[y != 0], 2 * x[y != 0])
+
+
+# ---- decoding: top-k + Gumbel-max sampling kernel, in-place KV cache ------------------------------------------------
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('V,thres', [(18448, 0.5), (18448, 0.9), (1000, 0.0), (90, 0.99)])
+def test_sample_topk_gumbel_matches_torch(dtype, V, thres):
+    """dalle_b200_sample_topk_gumbel against the reference's top_k + gumbel_sample (dalle_pytorch.py:43-58) fed with the same
+    Gumbel noise; half of the row is masked to -fp32max like the logits of DALLE.forward (:648-652)."""
+    o = ops()
+    torch.manual_seed(41)
+    B = 16
+    logits = (torch.randn(B, V, device=dev()) * 3).to(dtype)
+    logits[:, : V // 2] = torch.finfo(torch.float32).min if dtype == torch.float32 else torch.finfo(torch.bfloat16).min
+    noise = -torch.log(-torch.log(torch.rand(B, V, device=dev()).clamp_min(1e-20)))
+    k = max(int((1 - thres) * V), 1)
+    val, ind = torch.topk(logits.float(), k)
+    filt = torch.full_like(logits.float(), float('-inf')).scatter_(1, ind, val)
+    for temp in (1.0, 0.7):
+        want = (filt / temp + noise).argmax(-1)
+        got = o.sample_topk_gumbel(logits, thres, temp, gumbel=noise)
+        assert torch.equal(got, want), (got, want)
+    # internal Philox noise: deterministic in (seed, offset), inside the top-k set, and distributed like softmax over it
+    a = o.sample_topk_gumbel(logits, thres, 1.0, seed=5, offset=0)
+    assert torch.equal(a, o.sample_topk_gumbel(logits, thres, 1.0, seed=5, offset=0))
+    assert (filt.gather(1, a[:, None]) > float('-inf')).all()
+    if V == 90:
+        row = logits[:1].float().repeat(4096, 1).contiguous().to(dtype)
+        s = o.sample_topk_gumbel(row, 0.9, 1.0, seed=7, offset=123)
+        kk = max(int(0.1 * V), 1)
+        tv, ti = torch.topk(row[0].float(), kk)
+        p = torch.softmax(tv, 0)
+        freq = torch.stack([(s == i).float().mean() for i in ti])
+        assert (freq - p).abs().max() < 0.04, (freq, p)
+
+
+def test_inplace_kv_cache_attention():
+    """Forward attention over an in-place KV cache (kv_rows > n_k) == attention over the compact tensors, all backends."""
+    o = ops()
+    torch.manual_seed(43)
+    b, h, dh, cap = 2, 3, 64, 300
+    for dtype in (torch.float32, torch.bfloat16):
+        for n_k, n_q in ((1, 1), (130, 1), (257, 3)):
+            kbuf = _mk((b, h, cap, dh), dtype)
+            vbuf = _mk((b, h, cap, dh), dtype)
+            kbuf[:, :, n_k:] = 3.0e4                             # rows behind the valid ones must not influence the result (they must be
+            vbuf[:, :, n_k:] = -3.0e4                            # FINITE: the tensor-core kernels multiply them by exact zeros)
+            q = _mk((b, h, n_q, dh), dtype, dh ** -0.5)
+            spec = o.AttnSpec(0, causal=True)
+            a, _ = o.attn_fwd(spec, q, kbuf, vbuf, n_k=n_k)
+            w, _ = o.attn_fwd(spec, q, kbuf[:, :, :n_k].contiguous(), vbuf[:, :, :n_k].contiguous())
+            assert torch.isfinite(a.float()).all()
+            report(f'in-place cache n_k={n_k} {dtype}', a, w, 1e-6, 1e-6)
