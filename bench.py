@@ -530,7 +530,7 @@ def leg_summary(res, world, peak_tf):
     """Compact per-configuration entry for `extra_configs`."""
     c = res['c']
     tokens = res['batch'] * res['seq'] * world * res['steps']
-    graphed = 'ms_dev' in res.get('graph', {})
+    graphed = 'ms_dev' in res.get('graph', {}) and res['graph']['ms_dev'] <= res['ms_dev']     # the faster of the two execution paths
     value = tokens / ((res['graph']['ms_dev'] if graphed else res['ms_dev']) / 1e3)
     fam = res['gemm_stats']['tcgen05']
     flops_tok = model_flops_per_token(c)
@@ -538,6 +538,7 @@ def leg_summary(res, world, peak_tf):
            'ms_per_step': (res['graph']['ms_dev'] if graphed else res['ms_dev']) / res['steps'],
            'execution': 'one CUDA-graph replay per step' if graphed else 'eager launches',
            'eager_ms_per_step': res['ms_dev'] / res['steps'],
+           'graph_ms_per_step': (res['graph']['ms_dev'] / res['steps']) if 'ms_dev' in res.get('graph', {}) else None,
            'steps': res['steps'], 'n_gpus': world, 'gpu_launches': res['launches'], 'peak_mem_gb': res['peak_mem_gb'],
            'mfu_vs_sustained_peak': value / world * flops_tok / 1e12 / peak_tf,
            'gemm_roofline_frac': (fam['flops'] / (fam['ms'] * 1e-3) / 1e12 / peak_tf) if fam['ms'] > 0 else None,
@@ -601,8 +602,8 @@ def run_gpu_arm(args):
     c, batch, seq, dtype = main_res['c'], main_res['batch'], main_res['seq'], main_res['dtype']
     ms_eager, ms_e2e_eager, gemm_stats = main_res['ms_dev'], main_res['ms_e2e'], main_res['gemm_stats']
     gr = main_res.get('graph', {})
-    graphed = 'ms_dev' in gr
-    # headline = the product's execution path: the captured step when the capture succeeded (single process), eager otherwise
+    graphed = 'ms_dev' in gr and gr['ms_dev'] <= ms_eager
+    # headline = the product's execution path: the captured step when the capture succeeded and is not slower, eager otherwise
     ms_dev = gr['ms_dev'] if graphed else ms_eager
     ms_e2e = gr.get('ms_e2e', ms_e2e_eager) if graphed else ms_e2e_eager
     tokens_per_step = batch * seq * world
@@ -665,7 +666,8 @@ def run_gpu_arm(args):
            'execution': ({'mode': 'cuda_graph', 'host_launches_per_step': 1, 'library_kernels_per_step': gr['kernels_per_step'],
                           'eager_ms_per_step': ms_eager / args.steps, 'eager_e2e_ms_per_step': ms_e2e_eager / args.steps}
                          if graphed else {'mode': 'eager', 'library_kernels_per_step': main_res['launches'] / args.steps,
-                                          **({'graph_error': gr['error']} if 'error' in gr else {})}),
+                                          **({'graph_error': gr['error']} if 'error' in gr else {}),
+                                          **({'graph_ms_per_step': gr['ms_dev'] / args.steps} if 'ms_dev' in gr else {})}),
            'model_tflops_per_gpu': value / world * flops_tok / 1e12,
            'mfu_vs_sustained_peak': value / world * flops_tok / 1e12 / peak_tf,
            'clocks': main_res['clocks'], 'roofline': roof}

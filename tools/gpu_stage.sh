@@ -23,7 +23,7 @@ for stage in "$@"; do
     bench_c4) timeout 900 python bench.py --config c4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; tail -3 gpurun_out/bench_c4.err; cat gpurun_out/bench_c4.json ;;
     bench_ref) timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json ;;
     attn_probe) for be in tc mma; do for pat in full axial_row axial_col; do timeout 120 python tools/attn_probe.py --backend $be --pattern $pat; done; done 2>&1 | grep "^\[" | tee gpurun_out/attn_probe.log ;;
-    ncu_attn) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_.*tc_kernel -s 3 -c 3 -o gpurun_out/prof_attn -f python tools/attn_probe.py --backend tc --iters 1 > gpurun_out/ncu_attn.log 2>&1; tail -3 gpurun_out/ncu_attn.log ;;
+    ncu_attn) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_.*tc_kernel -s 3 -c 4 -o gpurun_out/prof_attn -f python tools/attn_probe.py --backend tc --iters 1 > gpurun_out/ncu_attn.log 2>&1; tail -3 gpurun_out/ncu_attn.log ;;
     ncu_ew) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"bwd_tma|scale_bwd_slab|geglu_bwd_kernel" -s 2 -c 4 -o gpurun_out/prof_ew -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph --extra "" > gpurun_out/ncu_ew.log 2>&1; tail -2 gpurun_out/ncu_ew.log ;;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph --extra "" > gpurun_out/ncu_list.log 2>&1; tail -3 gpurun_out/ncu_list.log ;;
     ncu_list_c3) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches_c3.csv python bench.py --config c3 --steps 1 --warmup 3 --no-cpu-baseline --no-graph --extra '' > gpurun_out/ncu_list_c3.log 2>&1; tail -3 gpurun_out/ncu_list_c3.log ;;
@@ -33,7 +33,7 @@ for stage in "$@"; do
         timeout 900 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 1 python -m pytest tests/test_kernels_gpu.py -q --no-header -p no:cacheprovider -x -k "$SEL" > gpurun_out/sanitizer_$tool.log 2>&1
         echo "$tool rc=$?"; grep -E "ERROR SUMMARY|passed|failed|RACECHECK SUMMARY" gpurun_out/sanitizer_$tool.log | tail -3
       done ;;
-    ncu_attn_gather) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_.*tc_kernel -s 3 -c 3 -o gpurun_out/prof_attn_gather -f python tools/attn_probe.py --backend tc --pattern axial_col --iters 1 > gpurun_out/ncu_attn_gather.log 2>&1; tail -2 gpurun_out/ncu_attn_gather.log ;;
+    ncu_attn_gather) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_.*tc_kernel -s 3 -c 4 -o gpurun_out/prof_attn_gather -f python tools/attn_probe.py --backend tc --pattern axial_col --iters 1 > gpurun_out/ncu_attn_gather.log 2>&1; tail -2 gpurun_out/ncu_attn_gather.log ;;
     ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 44 -c 20 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph --extra "" > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log ;;
     *) echo "unknown stage $stage" ;;
   esac
