@@ -580,3 +580,30 @@ def test_inplace_kv_cache_attention():
             w, _ = o.attn_fwd(spec, q, kbuf[:, :, :n_k].contiguous(), vbuf[:, :, :n_k].contiguous())
             assert torch.isfinite(a.float()).all()
             report(f'in-place cache n_k={n_k} {dtype}', a, w, 1e-6, 1e-6)
+
+
+# ---- tcgen05 GEMM at benchmark scale (persistent multi-wave grid, dynamic tile scheduler, split-K, all operand majors) -----------
+@pytest.mark.parametrize('name,M,N,K,a_mn,b_mn,out_f32', [
+    ('fwd FF1-like (store)', 20480, 4096, 1024, False, False, False),
+    ('dgrad FF1 (B read N-major)', 20480, 1024, 8192, False, True, False),
+    ('wgrad FF2 (both MN-major, fp32 out)', 1024, 4096, 20480, True, True, True),
+    ('wgrad out-proj (split-K + fp32 atomics)', 1024, 1024, 20480, True, True, True),
+    ('ragged M / N tails', 20000, 3000, 1032, False, False, False),
+])
+def test_gemm_tcgen05_at_benchmark_scale(name, M, N, K, a_mn, b_mn, out_f32):
+    """The shapes of a C2 step (M = 16 x 1280 rows) through gemm_tcgen05_kernel against torch's fp32 matmul of the same bf16
+    operands: thousands of tiles per launch (multi-wave persistent grid + atomic tile scheduler), the MN-major operand paths and
+    the split-K reduction, which the small-shape tests above do not reach."""
+    o = ops()
+    torch.manual_seed(51)
+    A = _mk((K, M) if a_mn else (M, K), torch.bfloat16)
+    B = _mk((K, N) if b_mn else (N, K), torch.bfloat16)
+    o.gemm_timing(True)
+    got = o.gemm_store(A, B, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32 if out_f32 else None)
+    st = o.gemm_timing(False)
+    assert st['tcgen05']['launches'] == 1 and st['simt']['launches'] == 0, st
+    want = (A.float().t() if a_mn else A.float()) @ (B.float() if b_mn else B.float().t())
+    scale = float(want.abs().max())
+    # fp32 result: the tensor core's truncating fp32 accumulator over K / 16 steps (measured 3e-5 at K = 20480); bf16 result: one rounding
+    tol = (2e-5 + 2e-9 * K) * scale if out_f32 else 8e-3 * scale
+    report(f'gemm {name}', got, want, 0.0, tol)
