@@ -2,6 +2,9 @@
 // Each function consumes one PAIR of adjacent accumulator columns (n even) of one output row m, which is
 // the natural granule for the rotary pair rotation and for packed bf16x2 stores.
 #pragma once
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace db200 {
@@ -11,6 +14,7 @@ struct EpiArgs {
   // STORE
   void* C; long long ldc; int c_is_f32; const float* bias; int atomic_c;      // atomic_c: 0 store, 1 fp32 red.add (split-K), 2 multimem.red
   float c_scale;                                                             // multiplies the accumulator in the multimem mode
+  int tma_store;                                                             // STORE, bf16 C: stage 32 x 64 boxes in smem, cp.async.bulk.tensor store
   // QKV
   void* q; void* k; void* v; const float* cos_t; const float* sin_t;
   int seq_n, heads, dim_head, pos_offset; float q_scale;
@@ -23,8 +27,12 @@ struct EpiArgs {
 inline EpiArgs make_epi_args(const db200_gemm_params& p) {
   EpiArgs e;
   e.M = p.M; e.N = p.N;
-  e.C = p.C; e.ldc = p.ldc; e.c_is_f32 = (p.c_dtype == DB200_F32); e.bias = p.bias; e.atomic_c = 0; e.c_scale = 1.0f;
+  e.C = p.C; e.ldc = p.ldc; e.c_is_f32 = (p.c_dtype == DB200_F32); e.bias = p.bias; e.atomic_c = 0; e.c_scale = 1.0f; e.tma_store = 0;
   if (p.C_multicast) { e.C = p.C_multicast; e.atomic_c = 2; e.c_scale = p.c_scale; }   // weight gradient reduced across the GPUs in the NVSwitch
+  // diagnosis only (tools/gemm_probe.py): DALLE_B200_GEMM_DBG=nostore drops the global stores of the STORE epilogue (3),
+  // =noepi skips the whole epilogue body (4) -- isolates the mainloop from the epilogue in the roofline gap
+  static const int dbg = [] { const char* v = getenv("DALLE_B200_GEMM_DBG"); return !v ? 0 : !strcmp(v, "nostore") ? 3 : !strcmp(v, "noepi") ? 4 : 0; }();
+  if (dbg && p.epilogue == DB200_EPI_STORE && !p.C_multicast) e.atomic_c = dbg;
   e.q = p.q; e.k = p.k; e.v = p.v; e.cos_t = p.cos_t; e.sin_t = p.sin_t;
   e.seq_n = p.seq_n; e.heads = p.heads; e.dim_head = p.dim_head; e.pos_offset = p.pos_offset; e.q_scale = p.q_scale;
   e.resid = p.resid; e.scale = p.scale; e.sign = p.sign; e.y_out = p.y_out; e.out = p.out;
@@ -163,6 +171,55 @@ template <> struct Vec8<float> {
   }
 };
 
+// 32-byte (one full L2 sector) stores: sm_100 has 256-bit global stores (st.global.v8.b32).  The row-mode STORE epilogue writes one
+// sector per lane and instruction instead of two 16-byte halves of it: measured with the stores removed the K = 1024 GEMMs run at
+// 1.55 PFLOP/s against 1.14 with 16-byte stores (tools/gemm_gap.py) -- partial-sector writes to 32 different lines per warp
+// instruction were the whole roofline gap of the short-K shapes.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]),
+               "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+// 16 accumulator columns n .. n+15 of row m (n % 16 == 0) of a plain STORE epilogue without atomics; returns false if the
+// alignment does not allow the 32-byte path (the caller then uses two epi_vec8 granules)
+template <typename T>
+__device__ __forceinline__ bool epi_store16(const EpiArgs& e, int m, int n, const uint32_t* acc) {
+  if (e.atomic_c != 0) return false;
+  const long long off = (long long)m * e.ldc + n;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+  if (e.bias) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + n + i));
+      v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+    }
+  }
+  if (e.c_is_f32) {
+    float* c = reinterpret_cast<float*>(e.C) + off;
+    if (reinterpret_cast<uintptr_t>(c) & 31) return false;
+    uint32_t w[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(v[8 * h + i]);
+      st_global_v8(c + 8 * h, w);
+    }
+  } else {
+    T* c = reinterpret_cast<T*>(e.C) + off;
+    if (reinterpret_cast<uintptr_t>(c) & 31) return false;
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&b2);
+    }
+    st_global_v8(c, w);
+  }
+  return true;
+}
+
 template <int EPI, typename T>
 __device__ __forceinline__ void epi_vec8(const EpiArgs& e, int m, int n, float* v) {
   if constexpr (EPI == DB200_EPI_STORE) {
@@ -172,6 +229,7 @@ __device__ __forceinline__ void epi_vec8(const EpiArgs& e, int m, int n, float* 
       for (int i = 0; i < 8; ++i) v[i] += bb[i];
     }
     const long long off = (long long)m * e.ldc + n;
+    if (e.atomic_c >= 3) return;                       // (diagnosis switch, see make_epi_args)
     if (e.atomic_c == 2) {                             // cross-GPU sum through the multicast address (16-byte aligned granules)
       float* c = reinterpret_cast<float*>(e.C) + off;
       mc_red_add_v4(c, v[0] * e.c_scale, v[1] * e.c_scale, v[2] * e.c_scale, v[3] * e.c_scale);

@@ -87,8 +87,8 @@ static std::atomic<unsigned int> g_launch_seq{0};
 template <int BLOCK_N, int EPI, bool A_MN, bool B_MN, bool EPI_COLS>
 // 320 threads are allocated as 12 warps of registers (4-warp granularity) -> 168 registers per thread at most
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K, int k_splits,
-                    int sched_slot, EpiArgs e) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                    int M, int N, int K, int k_splits, int sched_slot, EpiArgs e) {
   using L = SmemLayout<BLOCK_N>;
   constexpr int STAGES = L::STAGES;
   constexpr int B_STAGE_BYTES = L::B_STAGE_BYTES;
@@ -271,6 +271,51 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(tfull_bar + 8 * as, aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
+      if (e.atomic_c == 4) {
+        // (diagnosis: no epilogue work at all)
+      } else if (EPI == DB200_EPI_STORE && !EPI_COLS && e.tma_store) {
+        // ---- bf16 STORE through TMA: thread = accumulator row packs 32 columns (64 B) per chunk into this warp's 4 KB staging
+        // buffer in the 128B-swizzled layout; two chunks make one [32 rows x 64 columns] box = one cp.async.bulk.tensor store (full
+        // 128-byte lines, issued by one lane, clipped at the M / N edges by the hardware).  The 16-byte stores of the register
+        // path touched 32 different lines per warp instruction and were 27 % of the time of the K = 1024 GEMMs (tools/gemm_gap.py).
+        constexpr int NCH = (BLOCK_N / 2) / 32;
+        const uint32_t stage_u32 = smem_u32(stage);
+        uint32_t r[2][32];
+        tmem_ld32(taddr + half * (BLOCK_N / 2), r[0]);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          tmem_ld_wait();
+          if (ch + 1 < NCH) tmem_ld32(taddr + half * (BLOCK_N / 2) + (ch + 1) * 32, r[(ch + 1) & 1]);
+          const int n = n0 + half * (BLOCK_N / 2) + ch * 32;
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = __uint_as_float(r[ch & 1][2 * i]), b = __uint_as_float(r[ch & 1][2 * i + 1]);
+            if (e.bias && n + 2 * i < N) { const float2 bb = __ldg(reinterpret_cast<const float2*>(e.bias + n + 2 * i)); a += bb.x; b += bb.y; }
+            const __nv_bfloat162 p2 = __floats2bfloat162_rn(a, b);
+            w[i] = *reinterpret_cast<const uint32_t*>(&p2);
+          }
+          if ((ch & 1) == 0) {                                 // the previous box must have been read out of the staging buffer
+            if (lane == 0) bulk_wait_group_read0();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int unit = (ch & 1) * 4 + j;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_u32 + lane * 128 + ((unit ^ (lane & 7)) << 4)), "r"(w[4 * j]),
+                         "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
+                         : "memory");
+          }
+          if (ch & 1) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, stage_u32, n0 + half * (BLOCK_N / 2) + (ch >> 1) * 64, m0 + quarter * 32);
+              bulk_commit_group();
+            }
+          }
+        }
+      } else
       if constexpr (!EPI_COLS) {
         // ---- row mode: thread = accumulator row, 8-column (16-byte) granules straight from registers ----
         const int m = m0 + quarter * 32 + lane;
@@ -309,13 +354,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (ch + 1 < NCH) tmem_ld32(taddr + half * (BLOCK_N / 2) + (ch + 1) * 32, r[(ch + 1) & 1]);
             if (m < M) {
 #pragma unroll
-              for (int o = 0; o < 4; ++o) {
-                const int n = n0 + half * (BLOCK_N / 2) + ch * 32 + o * 8;
-                if (n < N) {
-                  float v[8];
+              for (int o2 = 0; o2 < 2; ++o2) {
+                const int nn = n0 + half * (BLOCK_N / 2) + ch * 32 + o2 * 16;
+                bool done = false;
+                if constexpr (EPI == DB200_EPI_STORE) {          // one 32-byte sector per lane (two for an fp32 result)
+                  if (nn + 16 <= N) done = epi_store16<__nv_bfloat16>(e, m, nn, &r[ch & 1][o2 * 16]);
+                }
+                if (!done) {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[ch & 1][o * 8 + i]);
-                  epi_vec8<EPI, __nv_bfloat16>(e, m, n, v);
+                  for (int o = 2 * o2; o < 2 * o2 + 2; ++o) {
+                    const int n = n0 + half * (BLOCK_N / 2) + ch * 32 + o * 8;
+                    if (n < N) {
+                      float v[8];
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[ch & 1][o * 8 + i]);
+                      epi_vec8<EPI, __nv_bfloat16>(e, m, n, v);
+                    }
+                  }
                 }
               }
             }
@@ -358,6 +413,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_arrive(tempty_bar + 8 * as);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
+    if (EPI == DB200_EPI_STORE && !EPI_COLS && e.tma_store && lane == 0) bulk_wait_group0();   // outstanding tensor stores
   }
 
   tc_fence_before();
@@ -366,6 +422,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+}
+
+inline bool al16(const void* p);
+inline bool tma_store_env() {      // DALLE_B200_GEMM_TMA_STORE=0: register-path stores (A/B timing)
+  static const bool on = [] { const char* v = getenv("DALLE_B200_GEMM_TMA_STORE"); return !(v && !strcmp(v, "0")); }();
+  return on;
 }
 
 template <int BLOCK_N, int EPI, bool A_MN, bool B_MN, bool EPI_COLS>
@@ -379,6 +441,13 @@ int launch_cfg_mode(const db200_gemm_params& p, cudaStream_t st) {
   if (!B_MN) rc = make_tensor_map_bf16(&tmB, p.B, p.K, p.N, p.ldb, BLOCK_K, 128);
   else rc = make_tensor_map_bf16(&tmB, p.B, p.N, p.K, p.ldb, 64, BLOCK_K);
   if (rc) return rc;
+  CUtensorMap tmC = tmA;                                      // placeholder unless the TMA-store epilogue is used
+  EpiArgs e = make_epi_args(p);
+  if (EPI == DB200_EPI_STORE && !EPI_COLS && e.atomic_c == 0 && p.c_dtype == DB200_BF16 && !p.split_k_ok && al16(p.C) && (p.ldc % 8) == 0 &&
+      tma_store_env()) {
+    if ((rc = make_tensor_map_bf16(&tmC, p.C, p.N, p.M, p.ldc, 64, 32))) return rc;
+    e.tma_store = 1;
+  }
   auto kern = gemm_tcgen05_kernel<BLOCK_N, EPI, A_MN, B_MN, EPI_COLS>;
   static std::atomic<bool> attr_done{false};   // idempotent set-up; atomic because forward and autograd threads both launch
   if (!attr_done.load(std::memory_order_acquire)) {
@@ -397,11 +466,10 @@ int launch_cfg_mode(const db200_gemm_params& p, cudaStream_t st) {
   }
   const int num_tiles = num_mn * k_splits;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  EpiArgs e = make_epi_args(p);
-  if (e.atomic_c != 2) e.atomic_c = k_splits > 1;      // (multimem reductions are additive already: split-K needs nothing more)
+  if (e.atomic_c < 2) e.atomic_c = k_splits > 1;      // (multimem reductions are additive already: split-K needs nothing more)
   static const bool static_sched = [] { const char* v = std::getenv("DALLE_B200_SCHED"); return v && !std::strcmp(v, "static"); }();
   const int sched_slot = static_sched ? -1 : static_cast<int>(g_launch_seq.fetch_add(1, std::memory_order_relaxed) % SCHED_SLOTS);
-  DB200_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, st, tmA, tmB, p.M, p.N, p.K, k_splits, sched_slot, e));
+  DB200_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, st, tmA, tmB, tmC, p.M, p.N, p.K, k_splits, sched_slot, e));
   DB200_LAUNCH_OK("gemm_tcgen05_kernel");
   return DB200_OK;
 }

@@ -485,7 +485,7 @@ def test_sparse_attention_matches_dense_evaluation_of_its_layout(dtype):
     import dalle_pytorch_b200 as D
     from dalle_oracle import attention_core
     torch.manual_seed(17)
-    dim, heads, seq_len, n = 128, 2, 300, 300
+    dim, heads, seq_len, n = 128, 2, 297, 297                    # 41 text positions + 16 x 16 image tokens; not a multiple of the block
     a = D.SparseAttention(dim, seq_len, causal=True, heads=heads, block_size=16, text_seq_len=40).cuda()
     x = torch.randn(2, n, dim, device='cuda', requires_grad=True)
     ang = rotary_angle_table(41, 16, 64)[:n]

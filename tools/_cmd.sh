@@ -1,4 +1,3 @@
-run() { echo "=== $*"; env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus 8 --steps 8 --warmup 3 --no-cpu-baseline --extra "" 2>gpurun_out/dp8.err | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'])"; }
-run DALLE_B200_DP_OP=sum DALLE_B200_DP_OVERLAP=1
-run DALLE_B200_DP_OP=sum DALLE_B200_DP_OVERLAP=0 NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=COLL,TUNING
-grep -i "nvls\|algo\|AllReduce" gpurun_out/dp8.err | head -8 | cut -c1-220
+python tools/gemm_gap.py 2>&1 | tail -8
+echo "=== TMA store off"; DALLE_B200_GEMM_TMA_STORE=0 python tools/gemm_gap.py 2>&1 | head -4
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q --no-header -p no:cacheprovider --tb=line -k "gemm" 2>&1 | grep -E "^E  |passed|failed" | cut -c1-250
