@@ -220,6 +220,89 @@ __device__ __forceinline__ bool epi_store16(const EpiArgs& e, int m, int n, cons
   return true;
 }
 
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t* w) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
+// EPI_RESID, row mode with full-sector accesses: 16 accumulator columns n .. n+15 of row m (n % 16 == 0, N % 8 == 0 so that every
+// row of out / resid / y starts on a 32-byte boundary).  Per lane and 16 columns: 2 x 32-byte loads of the residual, 2 x 32-byte
+// stores of out, one 32-byte store of y -- no shared-memory transpose.
+template <typename T>
+__device__ __forceinline__ void epi_resid16(const EpiArgs& e, int m, int n, const uint32_t* acc) {
+  const long long off = (long long)m * e.N + n;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+  if (e.bias) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + n + i));
+      v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+    }
+  }
+  uint32_t rr[16];
+  if (e.resid) { ld_global_v8(e.resid + off, rr); ld_global_v8(e.resid + off + 8, rr + 8); }
+  if (e.y_out) {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&b2);
+    }
+    st_global_v8(reinterpret_cast<T*>(e.y_out) + off, w);
+  }
+  uint32_t o[16];
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (e.scale) sc = __ldg(reinterpret_cast<const float4*>(e.scale + n + i));
+    const float s4[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float r = e.resid ? __uint_as_float(rr[i + k]) : 0.f;
+      o[i + k] = __float_as_uint(r + e.sign * s4[k] * v[i + k]);
+    }
+  }
+  st_global_v8(e.out + off, o);
+  st_global_v8(e.out + off + 8, o + 8);
+}
+
+// EPI_GEGLU, row mode with full-sector stores: hidden indices j .. j+15 of row m (j % 16 == 0, hidden % 16 == 0)
+template <typename T>
+__device__ __forceinline__ void epi_geglu16(const EpiArgs& e, int m, int j, const uint32_t* acc_a, const uint32_t* acc_g) {
+  float a[16], g[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { a[i] = __uint_as_float(acc_a[i]); g[i] = __uint_as_float(acc_g[i]); }
+  if (e.bias) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      const float4 ba = __ldg(reinterpret_cast<const float4*>(e.bias + j + i));
+      const float4 bg = __ldg(reinterpret_cast<const float4*>(e.bias + e.hidden + j + i));
+      a[i] += ba.x; a[i + 1] += ba.y; a[i + 2] += ba.z; a[i + 3] += ba.w;
+      g[i] += bg.x; g[i + 1] += bg.y; g[i + 2] += bg.z; g[i + 3] += bg.w;
+    }
+  }
+  uint32_t w[8];
+  if (e.u_out) {
+    T* u = reinterpret_cast<T*>(e.u_out) + (long long)m * (2 * e.hidden);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const __nv_bfloat162 b2 = __floats2bfloat162_rn(a[2 * i], a[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&b2); }
+    st_global_v8(u + j, w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const __nv_bfloat162 b2 = __floats2bfloat162_rn(g[2 * i], g[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&b2); }
+    st_global_v8(u + e.hidden + j, w);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float2 f, df;
+    gelu_pair2<T>(make_float2(g[2 * i], g[2 * i + 1]), f, df);
+    const __nv_bfloat162 b2 = __floats2bfloat162_rn(a[2 * i] * f.x, a[2 * i + 1] * f.y);
+    w[i] = *reinterpret_cast<const uint32_t*>(&b2);
+  }
+  st_global_v8(reinterpret_cast<T*>(e.h_out) + (long long)m * e.hidden + j, w);
+}
+
 template <int EPI, typename T>
 __device__ __forceinline__ void epi_vec8(const EpiArgs& e, int m, int n, float* v) {
   if constexpr (EPI == DB200_EPI_STORE) {

@@ -332,14 +332,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             const int j0 = (n0 >> 1) + half * 64 + ch * 32;
             if (m < M) {
+              if ((e.hidden & 15) == 0) {                       // full-sector stores of u (a | g) and h
 #pragma unroll
-              for (int o = 0; o < 4; ++o) {
-                const int j = j0 + o * 8;
-                if (j < e.hidden) {
-                  float a[8], g[8];
+                for (int o2 = 0; o2 < 2; ++o2)
+                  if (j0 + o2 * 16 < e.hidden) epi_geglu16<__nv_bfloat16>(e, m, j0 + o2 * 16, &ra[ch][o2 * 16], &rg[ch][o2 * 16]);
+              } else {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(ra[ch][o * 8 + i]); g[i] = __uint_as_float(rg[ch][o * 8 + i]); }
-                  epi_geglu_vec8<__nv_bfloat16>(e, m, j, a, g);
+                for (int o = 0; o < 4; ++o) {
+                  const int j = j0 + o * 8;
+                  if (j < e.hidden) {
+                    float a[8], g[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(ra[ch][o * 8 + i]); g[i] = __uint_as_float(rg[ch][o * 8 + i]); }
+                    epi_geglu_vec8<__nv_bfloat16>(e, m, j, a, g);
+                  }
                 }
               }
             }
@@ -359,6 +365,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 bool done = false;
                 if constexpr (EPI == DB200_EPI_STORE) {          // one 32-byte sector per lane (two for an fp32 result)
                   if (nn + 16 <= N) done = epi_store16<__nv_bfloat16>(e, m, nn, &r[ch & 1][o2 * 16]);
+                }
+                if constexpr (EPI == DB200_EPI_RESID) {          // full-sector residual loads / out, y stores (N % 8 == 0 checked by the launcher)
+                  if (nn + 16 <= N) { epi_resid16<__nv_bfloat16>(e, m, nn, &r[ch & 1][o2 * 16]); done = true; }
                 }
                 if (!done) {
 #pragma unroll
@@ -491,7 +500,9 @@ int launch_cfg(const db200_gemm_params& p, cudaStream_t st) {
   const int env = epi_mode_env();
   // (multicast reduction: lanes must run along N so that one warp instruction is one contiguous 256-byte run -- NVLink packets of
   //  16 scattered bytes per lane, the "rows" layout, were measured 10 ms per C2 step slower)
-  const bool cols = env == 2 || (env == 0 && (EPI == DB200_EPI_GEGLU || EPI == DB200_EPI_RESID)) ||
+  // (r02, tools/gemm_gap.py: with one full 32-byte sector per lane and instruction the row layout beats the transposed one for
+  //  GEGLU-forward, 303 vs 323 us; LayerScale + residual stays faster transposed, 77 vs 83 us)
+  const bool cols = env == 2 || (env == 0 && EPI == DB200_EPI_RESID) ||
                     (EPI == DB200_EPI_STORE && p.C_multicast != nullptr);   // measured, see profiles/
   if (cols) return launch_cfg_mode<BLOCK_N, EPI, A_MN, B_MN, true>(p, st);
   return launch_cfg_mode<BLOCK_N, EPI, A_MN, B_MN, false>(p, st);
