@@ -44,6 +44,14 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
+// one full 32-byte sector per lane and store instruction (sm_100 256-bit global stores): the 16-byte stores of the output rows left
+// half of every sector to a second instruction (see epilogue.cuh::st_global_v8)
+__device__ __forceinline__ void st_global_32B(void* p, uint4 a, uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z),
+               "r"(b.w)
+               : "memory");
+}
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -370,13 +378,17 @@ __global__ void __launch_bounds__(192, 3) attn_fwd_tc_kernel(const __grid_consta
       if (qi < q_lim) {
         bf16* orow = P.out + ((long long)b * g.n_q + attn_nat(g, qi)) * inner + h * DH + c * 32;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u;
-          u.x = pack2(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-          u.y = pack2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-          u.z = pack2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-          u.w = pack2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + 8 * j) = u;
+        for (int j2 = 0; j2 < 2; ++j2) {
+          uint4 u[2];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int j = 2 * j2 + t;
+            u[t].x = pack2(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+            u[t].y = pack2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+            u[t].z = pack2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+            u[t].w = pack2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+          }
+          st_global_32B(orow + 16 * j2, u[0], u[1]);
         }
       }
     }
@@ -636,13 +648,17 @@ __global__ void __launch_bounds__(192, FKT == 32 ? 4 : 2) attn_fwd_tc2_kernel(co
       if (qi < q_lim) {
         bf16* orow = P.out + ((long long)b * g.n_q + attn_nat(g, qi)) * inner + h * DH + c * 32;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u;
-          u.x = pack2(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
-          u.y = pack2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
-          u.z = pack2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
-          u.w = pack2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + 8 * j) = u;
+        for (int j2 = 0; j2 < 2; ++j2) {
+          uint4 u[2];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int j = 2 * j2 + t;
+            u[t].x = pack2(__uint_as_float(r[8 * j]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+            u[t].y = pack2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+            u[t].z = pack2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+            u[t].w = pack2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+          }
+          st_global_32B(orow + 16 * j2, u[0], u[1]);
         }
       }
     }
@@ -738,6 +754,7 @@ __device__ __forceinline__ void store_grad_cols(uint32_t taddr, bf16* dst, const
   tmem_ld32(taddr + c * 32, r);
   tmem_ld_wait();
   if (valid) {
+    uint4 u[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float v[8];
@@ -750,10 +767,10 @@ __device__ __forceinline__ void store_grad_cols(uint32_t taddr, bf16* dst, const
         rotary_adjoint(cc.x, ss.x, v[0], v[1]); rotary_adjoint(cc.y, ss.y, v[2], v[3]);
         rotary_adjoint(cc.z, ss.z, v[4], v[5]); rotary_adjoint(cc.w, ss.w, v[6], v[7]);
       }
-      uint4 u;
-      u.x = pack2(v[0], v[1]); u.y = pack2(v[2], v[3]); u.z = pack2(v[4], v[5]); u.w = pack2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(dst + c * 32 + j * 8) = u;
+      u[j].x = pack2(v[0], v[1]); u[j].y = pack2(v[2], v[3]); u[j].z = pack2(v[4], v[5]); u[j].w = pack2(v[6], v[7]);
     }
+    st_global_32B(dst + c * 32, u[0], u[1]);          // (rows of dqkv start on 128-byte boundaries: heads * 64 bf16 per section)
+    st_global_32B(dst + c * 32 + 16, u[2], u[3]);
   }
 }
 __device__ __forceinline__ void store_grad_row(uint32_t taddr, bf16* dst, const float* cos_row, const float* sin_row, float scale, bool valid) {

@@ -1,2 +1,2 @@
-for m in cols rows; do echo "=== DALLE_B200_EPI=$m"; DALLE_B200_EPI=$m python tools/gemm_gap.py 2>&1 | tail -3; done
-DALLE_B200_EPI=rows timeout 600 python -m pytest tests/test_kernels_gpu.py -q --no-header -p no:cacheprovider --tb=line -k "gemm" 2>&1 | grep -E "^E  |passed|failed" | cut -c1-250
+timeout 900 python -m pytest tests/test_kernels_gpu.py -q --no-header -p no:cacheprovider --tb=line -k "attention or axial_gather or inplace" 2>&1 | grep -E "^E  |passed|failed" | cut -c1-200
+for pat in full axial_col; do python tools/attn_probe.py --pattern $pat | grep "^\["; done
