@@ -782,7 +782,7 @@ __device__ __forceinline__ void store_grad_row(uint32_t taddr, bf16* dst, const 
 // kLseCol: lse/delta vary along the columns (dK/dV kernel, read from smem at ls_addr / dl_addr) instead of being per-row
 // constants (dQ kernel; lse_r already carries the log2(e) factor).  Four packed fp32 instructions + two MUFU + two
 // conversions per element pair.
-template <bool kLseCol, bool kWantP>
+template <bool kLseCol, bool kWantP, bool kNoExp = false>      // kNoExp: diagnosis only (DALLE_B200_ATTN_WAIT bit 3): a multiply instead of ex2
 __device__ __forceinline__ void bwd_softmax16(const uint32_t* rs, const uint32_t* rd, uint32_t mb16, uint32_t ls_addr, uint32_t dl_addr,
                                               float lse_r, float delta_r, uint32_t* pk, uint32_t* dk_) {
   const float2 kLog2e = make_float2(LOG2E, LOG2E), kNegLog2e = make_float2(-LOG2E, -LOG2E), kNegOne = make_float2(-1.f, -1.f);
@@ -803,7 +803,7 @@ __device__ __forceinline__ void bwd_softmax16(const uint32_t* rs, const uint32_t
       const float2 sv = make_float2(__uint_as_float(rs[2 * i]), __uint_as_float(rs[2 * i + 1]));
       const float2 dv = make_float2(__uint_as_float(rd[2 * i]), __uint_as_float(rd[2 * i + 1]));
       const float2 t = fma2(sv, kLog2e, h == 0 ? nl0 : nl1);
-      float2 p = make_float2(ex2(t.x), ex2(t.y));
+      float2 p = kNoExp ? make_float2(t.x * 1e-3f, t.y * 1e-3f) : make_float2(ex2(t.x), ex2(t.y));
       if (mb16 != 0xffffu) { p.x = sel_bit(mb16, 2 * i, p.x, 0.f); p.y = sel_bit(mb16, 2 * i + 1, p.y, 0.f); }
       const float2 e = fma2(h == 0 ? d0 : d1, kNegOne, dv);      // dp - delta
       const float2 ds = mul2(p, e);
@@ -1022,7 +1022,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) attn_bwd_dkv_tc_kernel(const _
           tmem_ld16(tSt + lane_off + col, rs);
           tmem_ld16(tdPt + lane_off + col, rd);
           tmem_ld_wait();
-          bwd_softmax16<true, true>(rs, rd, mb16, smem_u32(s_lse + s * BW + col), smem_u32(s_delta + s * BW + col), 0.f, 0.f, pk, dk_);
+          if (P.wait_mode & 8) bwd_softmax16<true, true, true>(rs, rd, mb16, smem_u32(s_lse + s * BW + col), smem_u32(s_delta + s * BW + col), 0.f, 0.f, pk, dk_);
+          else bwd_softmax16<true, true>(rs, rd, mb16, smem_u32(s_lse + s * BW + col), smem_u32(s_delta + s * BW + col), 0.f, 0.f, pk, dk_);
         }
         tmem_st8(tPt + lane_off + chunk * 32 + sub * 8, pk);
         tmem_st8(tdSt + lane_off + chunk * 32 + sub * 8, dk_);
