@@ -1046,12 +1046,12 @@ int ln_shift_bwd_launch(const db200_ln_shift_bwd_params& P, cudaStream_t st) {
     const int want = ceil_div(rows, LT_R);
     const int grid = want < sm_count() ? want : sm_count();
     if (P.dout_dtype == DB200_F32) {
-      static bool attr = false;
-      if (!attr) { DB200_CUDA_OK(cudaFuncSetAttribute(ln_shift_bwd_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, LnTmaSmem<float>::TOTAL)); attr = true; }
+      static std::atomic<bool> attr{false};   // idempotent set-up; atomic because forward and autograd threads both launch
+      if (!attr.load(std::memory_order_acquire)) { DB200_CUDA_OK(cudaFuncSetAttribute(ln_shift_bwd_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, LnTmaSmem<float>::TOTAL)); attr.store(true, std::memory_order_release); }
       DB200_CUDA_OK(launch_pdl(ln_shift_bwd_tma_kernel<float>, dim3(grid), dim3(LT_THREADS), LnTmaSmem<float>::TOTAL, st, P));
     } else {
-      static bool attr = false;
-      if (!attr) { DB200_CUDA_OK(cudaFuncSetAttribute(ln_shift_bwd_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LnTmaSmem<__nv_bfloat16>::TOTAL)); attr = true; }
+      static std::atomic<bool> attr{false};   // idempotent set-up; atomic because forward and autograd threads both launch
+      if (!attr.load(std::memory_order_acquire)) { DB200_CUDA_OK(cudaFuncSetAttribute(ln_shift_bwd_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, LnTmaSmem<__nv_bfloat16>::TOTAL)); attr.store(true, std::memory_order_release); }
       DB200_CUDA_OK(launch_pdl(ln_shift_bwd_tma_kernel<__nv_bfloat16>, dim3(grid), dim3(LT_THREADS), LnTmaSmem<__nv_bfloat16>::TOTAL, st, P));
     }
     DB200_LAUNCH_OK("ln_shift_bwd_tma_kernel");

@@ -487,11 +487,10 @@ int launch_cfg_mode(const db200_gemm_params& p, cudaStream_t st) {
 // lanes run along N).  Measured on B200 (profiles/): cols wins only for the GEGLU forward epilogue; DALLE_B200_EPI=rows|cols
 // forces one mode for A/B timing.
 inline int epi_mode_env() {
-  static int mode = -1;
-  if (mode < 0) {
+  static const int mode = [] {
     const char* v = getenv("DALLE_B200_EPI");
-    mode = (v && !strcmp(v, "rows")) ? 1 : (v && !strcmp(v, "cols")) ? 2 : 0;
-  }
+    return (v && !strcmp(v, "rows")) ? 1 : (v && !strcmp(v, "cols")) ? 2 : 0;
+  }();
   return mode;
 }
 
