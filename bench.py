@@ -504,22 +504,43 @@ def measure_decode(args, ctx, cfg_name='c2', batch=16):
     g = torch.Generator().manual_seed(5)
     text = torch.randint(1, NUM_TEXT_TOKENS, (batch, c['text_seq_len']), generator=g).to(dev)
     n_img = c['fmap'] ** 2
-    with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
-        model.generate_images(text[:2], use_cache=True)          # warm-up (allocator, caches)
-        torch.cuda.synchronize()
-        n0 = ops.launches()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        img = model.generate_images(text, use_cache=True)
-        e.record()
-        torch.cuda.synchronize()
-    ms = s.elapsed_time(e)
-    assert img.shape == (batch, n_img) and int(img.min()) >= 0 and int(img.max()) < NUM_IMAGE_TOKENS
+    from dalle_pytorch_b200 import decode
+
+    def timed(graph):
+        """One full generate_images call: (ms, library launches per token step)."""
+        was, decode.GRAPH_DEFAULT = decode.GRAPH_DEFAULT, graph
+        try:
+            with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+                model.generate_images(text[:2], use_cache=True)          # warm-up (allocator, caches)
+                torch.cuda.synchronize()
+                n0 = ops.launches()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                img = model.generate_images(text, use_cache=True)
+                e.record()
+                torch.cuda.synchronize()
+        finally:
+            decode.GRAPH_DEFAULT = was
+        assert img.shape == (batch, n_img) and int(img.min()) >= 0 and int(img.max()) < NUM_IMAGE_TOKENS
+        return s.elapsed_time(e), (ops.launches() - n0) / n_img
+
+    ms_host, k_host = timed(False)
+    legs = {'host_indexed': {'value': batch * n_img / (ms_host / 1e3), 'ms_per_token_step': ms_host / n_img,
+                             'library_launches_per_token_step': k_host}}
+    ms = ms_host
+    try:      # decode.py: one CUDA-graph replay per token (position on the device); includes the capture of the call's graph
+        ms_graph, k_graph = timed(True)
+        legs['graph_replay'] = {'value': batch * n_img / (ms_graph / 1e3), 'ms_per_token_step': ms_graph / n_img,
+                                'library_launches_issued_from_python_per_token_step': k_graph}
+        ms = min(ms_host, ms_graph)
+    except Exception as ex:                                              # keep the leg: the host-indexed loop is the fallback path
+        legs['graph_replay'] = {'error': f'{type(ex).__name__}: {ex}'[:300]}
     out = {'workload': f'{cfg_name} weights, generate_images(use_cache=True): {n_img} image tokens after {c["text_seq_len"]} text tokens, batch {batch}, '
                        'filter_thres 0.5, temperature 1, bf16',
            'value': batch * n_img / (ms / 1e3), 'unit': 'generated image tokens/s', 'ms_per_token_step': ms / n_img, 'total_ms': ms,
-           'library_kernels_per_token_step': (ops.launches() - n0) / n_img, 'n_gpus': 1}
-    log(f"decode: {out['value']:.0f} image tokens/s ({out['ms_per_token_step']:.3f} ms per step of {batch} sequences)")
+           'paths': legs, 'default_path': 'graph_replay' if decode.GRAPH_DEFAULT else 'host_indexed', 'n_gpus': 1}
+    log(f"decode: {out['value']:.0f} image tokens/s ({out['ms_per_token_step']:.3f} ms per step of {batch} sequences; "
+        + ', '.join(f"{k} {v['value']:.0f}" if 'value' in v else f'{k} FAILED' for k, v in legs.items()) + ')')
     del model
     gc.collect()
     torch.cuda.empty_cache()

@@ -141,6 +141,20 @@ class Attention(_AttentionBase):
         re-allocates and copies the whole cache with torch.cat at every token."""
         dtype = config.compute_dtype()
         b, n, d = x.shape
+        if cache.get('pos_t') is not None:
+            # device-indexed step (decode.GraphedDecoder, capturable in a CUDA graph): rotary row, cache write position and the
+            # allowed keys are selected on the device; attention runs over the whole buffer with the key mask of this position
+            assert n == 1 and mask is None, 'graph-replayed decoding feeds one token per step and no padding mask'
+            cos_r, sin_r = cache['rot_row']
+            ent = cache[cache_key]
+            a, _, _ = ops.ln_shift_fwd(x.float().contiguous(), None, None, dtype, 0, 1, do_ln=False, do_shift=False)
+            wq, wo = _w(self.to_qkv.weight, dtype), _w(self.to_out[0].weight, dtype)
+            q, k, v = ops.gemm_qkv(a, wq, b, 1, self.heads, self.dim_head, cos_r, sin_r, self.scale, pos_offset=0)
+            ent.k.index_copy_(2, cache['pos_t'], k)
+            ent.v.index_copy_(2, cache['pos_t'], v)
+            o, _ = ops.attn_fwd(ops.AttnSpec(ATTN_FULL, causal=False, stable=self.stable), q, ent.k, ent.v, cache['key_mask'][cache_key])
+            out, _ = ops.gemm_resid(o.view(b, -1), wo, self.to_out[0].bias.detach(), None, None, 1.0)
+            return out.view(b, 1, d)
         offset = cache.get('offset', 0)
         cos_t, sin_t = rotary_tables(rotary_pos_emb, self.dim_head)
         a, _, _ = ops.ln_shift_fwd(x.float().contiguous(), None, None, dtype, 0, 1, do_ln=False, do_shift=False)

@@ -7,7 +7,7 @@ from torch import nn
 import torch.nn.functional as F
 
 from .transformer import Transformer, DivideMax
-from . import ops
+from . import ops, decode
 from .functional import DropoutRNG
 
 
@@ -175,11 +175,19 @@ class DALLE(nn.Module):
             out = torch.cat((out, indices[:, :num_img_tokens]), dim=-1)
 
         cache = {} if use_cache else None
+        # graph-replayed steps (decode.py): after the prompt pass every image token is one CUDA-graph replay + the sampling launch
+        graph_ok = use_cache and decode.GRAPH_DEFAULT and decode.eligible(self, text, cond_scale)
+        stepper, sample = None, None
         for cur_len in range(out.shape[1], total_len):
             is_image = cur_len >= text_seq_len
-            text, image = out[:, :text_seq_len], out[:, text_seq_len:]
-            logits = self.forward_with_cond_scale(text, image, cond_scale=cond_scale, cache=cache)
-            logits = logits[:, -1, :]
+            if graph_ok and stepper is None and cur_len > text_seq_len and cache.get('offset') == cur_len:
+                stepper = decode.GraphedDecoder(self, cache)
+            if stepper is not None:
+                logits = stepper.step(sample)
+            else:
+                text, image = out[:, :text_seq_len], out[:, text_seq_len:]
+                logits = self.forward_with_cond_scale(text, image, cond_scale=cond_scale, cache=cache)
+                logits = logits[:, -1, :]
             if logits.is_cuda and logits.shape[-1] * 4 <= 200 * 1024:
                 # top_k + gumbel_sample (dalle_pytorch.py:533-539) as one library launch; the Philox pair follows torch's generator
                 seed, off = DropoutRNG.draw(logits.numel())

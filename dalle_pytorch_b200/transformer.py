@@ -148,6 +148,19 @@ class PreShiftToken(nn.Module):
 
     def forward(self, x, cache=None, cache_key=None, **kwargs):
         seq_len, image_size, text_len = self.seq_len, self.image_size, self.text_len
+        if exists(cache) and cache_key in cache and cache.get('pos_t') is not None:
+            # device-indexed form of the branch below (decode.GraphedDecoder): the position is a device tensor, the deque a ring
+            ring = cache[cache_key]
+            slot, prev, not_first = cache['shift_idx']
+            x_top, x_left, *x_pass = x[:, -1].chunk(4, dim=-1)
+            top_old = ring.top.index_select(0, slot)[0]                 # the token one row up (fmap steps ago)
+            left_prev = ring.left.index_select(0, prev)[0]              # the previous token
+            ring.top.index_copy_(0, slot, x_top[None])
+            ring.left.index_copy_(0, slot, x_left[None])
+            left_prev = torch.where(not_first, left_prev, torch.zeros_like(left_prev))
+            x = torch.cat((top_old, left_prev, *x_pass), dim=-1)
+            return self.fn(x[:, None], cache=cache, **kwargs)
+
         if exists(cache) and cache_key in cache:
             offset = cache['offset']
             assert offset >= text_len, "cached inference for text is not supported"

@@ -329,6 +329,57 @@ def test_generate_images_cached_and_uncached():
             report(f'cached logits step {cur}', step[live], full[live], 1e-4, 1e-5)
 
 
+@pytest.mark.parametrize('variant', ['full_shift_bf16', 'axial_static_fp32', 'full_noshift_stable_fp32'])
+def test_generate_images_graph_replay(variant, monkeypatch):
+    """decode.GraphedDecoder: after the prompt pass every image token is one CUDA-graph replay whose position is a device tensor
+    (rotary row, KV write, allowed keys, token-shift slot selected on the device).  Same seed -> the same image tokens as the
+    host-indexed cached loop, and teacher-forced logits equal the host-indexed cached step at every position."""
+    import dalle_pytorch_b200 as D
+    from dalle_pytorch_b200 import decode
+    kw = dict(full_shift_bf16=dict(attn_types=('full',), shift_tokens=True),
+              axial_static_fp32=dict(attn_types=('axial_row', 'axial_col'), shift_tokens=True, optimize_for_inference=True),
+              full_noshift_stable_fp32=dict(attn_types=('full',), shift_tokens=False, stable=True))[variant]
+    dtype = torch.bfloat16 if variant.endswith('bf16') else torch.float32
+    torch.manual_seed(21)
+    vae = D.TokenVAE(image_size=64, num_layers=3, num_tokens=40)           # fmap 8: 64 image tokens, 61 graph replays
+    m = D.DALLE(dim=128, vae=vae, num_text_tokens=60, text_seq_len=12, depth=3, heads=2, **kw).cuda().eval()
+    for p in m.parameters():
+        if p.dim() == 3:                                                   # LayerScale 0.1 -> every branch matters
+            torch.nn.init.uniform_(p, 0.5, 1.0)
+    text = torch.randint(1, 60, (3, 12), generator=torch.Generator().manual_seed(22)).cuda()
+    made = []
+
+    class Spy(decode.GraphedDecoder):
+        def __init__(self, *a, **k):
+            made.append(self)
+            super().__init__(*a, **k)
+    monkeypatch.setattr(decode, 'GraphedDecoder', Spy)
+    toks = {}
+    with D.compute_dtype_ctx(dtype):
+        for on in (False, True):
+            monkeypatch.setattr(decode, 'GRAPH_DEFAULT', on)
+            torch.manual_seed(5)
+            toks[on] = m.generate_images(text, use_cache=True, filter_thres=0.9).cpu()
+        assert len(made) == 1 and made[0].graph is not None, 'the second call must have captured and replayed a graph'
+        assert int(made[0].pos_t) == m.total_seq_len and made[0].cache['offset'] == m.total_seq_len
+        assert torch.equal(toks[False], toks[True]), (toks[False], toks[True])
+        # teacher-forced logits, position by position (the decoder is driven by hand: eager warm-up steps, capture, replays)
+        img = toks[False].cuda()
+        host, dev = {}, {}
+        with torch.no_grad():
+            want = [m(text, img[:, :k], cache=host)[:, -1].float() for k in range(img.shape[1])]
+            got = [m(text, img[:, :0], cache=dev)[:, -1].float()]
+            dec = decode.GraphedDecoder(m, dev)
+            for k in range(1, img.shape[1]):
+                got.append(dec.step(img[:, k - 1]).float().clone())
+        assert dec.graph is not None
+    tol = (2e-2, 2e-2) if dtype == torch.bfloat16 else (1e-4, 1e-5)
+    for k, (a, b) in enumerate(zip(want, got)):
+        live = a > -1e30
+        assert torch.equal(live, b > -1e30), k
+        report(f'{variant}: graph-replayed logits step {k}', b[live], a[live], *tol)
+
+
 def test_edge_shapes():
     """Ragged / degenerate shapes through the module API: batch 1, a text-only prefix shorter than text_len (no shift), one
     image token, n not a multiple of any tile."""
