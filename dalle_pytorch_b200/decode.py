@@ -20,7 +20,10 @@ so the whole step (embedding of the previous sample -> transformer -> logits hea
 generator per step (exactly like the eager path, so the same seed gives the same tokens).  The first step (the prompt) and two
 warm-up steps run eagerly through the same code.
 
-`DALLE_B200_DECODE_GRAPH=0|1` switches the path (see GRAPH_DEFAULT); models the path does not cover (reversible executor,
+Measured on B200 (C2 weights, batch 16, 1024 image tokens, bf16; tools/decode_probe.py): 5 734 generated tokens/s = 2.79 ms per
+token step against 3 186 tokens/s = 5.02 ms for the host-indexed loop of the same call.
+
+`DALLE_B200_DECODE_GRAPH=0` restores the host-indexed loop (see GRAPH_DEFAULT); models the path does not cover (reversible executor,
 sparse-pattern layers that re-run the prefix, classifier-free guidance with cond_scale != 1) use the eager loop.
 """
 import os
@@ -28,7 +31,7 @@ from collections import deque
 
 import torch
 
-GRAPH_DEFAULT = os.environ.get('DALLE_B200_DECODE_GRAPH', '0') == '1'
+GRAPH_DEFAULT = os.environ.get('DALLE_B200_DECODE_GRAPH', '1') != '0'
 WARMUP_STEPS = 2
 
 
