@@ -487,7 +487,7 @@ def measure_config(cfg_name, args, ctx, steps, want_e2e=True, want_clocks=True, 
     return res
 
 
-def measure_decode(args, ctx, cfg_name='c2', batch=16):
+def measure_decode(args, ctx, cfg_name='c2', batch=16, host_indexed=True):
     """Autoregressive image generation with the KV cache (generate_images(use_cache=True), dalle_pytorch.py:506-562): image tokens
     per second on one GPU -- cached attention over the in-place KV cache, library sampling kernel, one token per step."""
     import gc
@@ -524,9 +524,11 @@ def measure_decode(args, ctx, cfg_name='c2', batch=16):
         assert img.shape == (batch, n_img) and int(img.min()) >= 0 and int(img.max()) < NUM_IMAGE_TOKENS
         return s.elapsed_time(e), (ops.launches() - n0) / n_img
 
-    ms_host, k_host = timed(False)
-    legs = {'host_indexed': {'value': batch * n_img / (ms_host / 1e3), 'ms_per_token_step': ms_host / n_img,
-                             'library_launches_per_token_step': k_host}}
+    legs, ms_host = {}, float('inf')
+    if host_indexed:
+        ms_host, k_host = timed(False)
+        legs['host_indexed'] = {'value': batch * n_img / (ms_host / 1e3), 'ms_per_token_step': ms_host / n_img,
+                                'library_launches_per_token_step': k_host}
     ms = ms_host
     try:      # decode.py: one CUDA-graph replay per token (position on the device); includes the capture of the call's graph
         ms_graph, k_graph = timed(True)
@@ -535,10 +537,14 @@ def measure_decode(args, ctx, cfg_name='c2', batch=16):
         ms = min(ms_host, ms_graph)
     except Exception as ex:                                              # keep the leg: the host-indexed loop is the fallback path
         legs['graph_replay'] = {'error': f'{type(ex).__name__}: {ex}'[:300]}
+        if not host_indexed:
+            raise
     out = {'workload': f'{cfg_name} weights, generate_images(use_cache=True): {n_img} image tokens after {c["text_seq_len"]} text tokens, batch {batch}, '
                        'filter_thres 0.5, temperature 1, bf16',
            'value': batch * n_img / (ms / 1e3), 'unit': 'generated image tokens/s', 'ms_per_token_step': ms / n_img, 'total_ms': ms,
-           'paths': legs, 'default_path': 'graph_replay' if decode.GRAPH_DEFAULT else 'host_indexed', 'n_gpus': 1}
+           'paths': legs, 'default_path': 'graph_replay' if decode.GRAPH_DEFAULT else 'host_indexed', 'n_gpus': 1,
+           'graph_step': {'flat_layers': decode.FLAT_DEFAULT, 'key_bucket': decode.BUCKET_DEFAULT,
+                          'single_query_attention_kernel': os.environ.get('DALLE_B200_DECODE_ATTN', 'default')}}
     log(f"decode: {out['value']:.0f} image tokens/s ({out['ms_per_token_step']:.3f} ms per step of {batch} sequences; "
         + ', '.join(f"{k} {v['value']:.0f}" if 'value' in v else f'{k} FAILED' for k, v in legs.items()) + ')')
     del model

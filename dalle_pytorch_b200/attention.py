@@ -152,7 +152,8 @@ class Attention(_AttentionBase):
             q, k, v = ops.gemm_qkv(a, wq, b, 1, self.heads, self.dim_head, cos_r, sin_r, self.scale, pos_offset=0)
             ent.k.index_copy_(2, cache['pos_t'], k)
             ent.v.index_copy_(2, cache['pos_t'], v)
-            o, _ = ops.attn_fwd(ops.AttnSpec(ATTN_FULL, causal=False, stable=self.stable), q, ent.k, ent.v, cache['key_mask'][cache_key])
+            o, _ = ops.attn_fwd(ops.AttnSpec(ATTN_FULL, causal=False, stable=self.stable), q, ent.k, ent.v, cache['key_mask'][cache_key],
+                                n_k=cache.get('n_k'))
             out, _ = ops.gemm_resid(o.view(b, -1), wo, self.to_out[0].bias.detach(), None, None, 1.0)
             return out.view(b, 1, d)
         offset = cache.get('offset', 0)

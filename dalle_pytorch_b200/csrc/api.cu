@@ -74,6 +74,12 @@ bool attn_gather_ok(const db200_attn_fwd_params& p, const char** why);
 int attn_fwd_tc_launch(const db200_attn_fwd_params& p, cudaStream_t st);
 int attn_bwd_tc_launch(const db200_attn_bwd_params& p, cudaStream_t st);
 int attn_debug_timeline(long long* out, int count);
+bool attn_decode_supported(const db200_attn_fwd_params& p);
+int attn_decode_launch(const db200_attn_fwd_params& p, cudaStream_t st);
+int decode_shift_launch(const float* h, void* y, int out_dtype, int batch, int d, float* ring_top, float* ring_left, const long long* pos,
+                        int text_len, int fmap, cudaStream_t st);
+int decode_kv_append_launch(const void* k_new, const void* v_new, void* k_cache, void* v_cache, int dtype, int bh, int dh, int kv_rows,
+                            const long long* pos, cudaStream_t st);
 
 static bool dtype_ok(int d) { return d == DB200_F32 || d == DB200_BF16; }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -241,6 +247,8 @@ int dalle_b200_attn_fwd(const db200_attn_fwd_params* p, void* stream) {
   const int rc = check_attn(*p, "attn_fwd");
   if (rc) return rc;
   if (p->batch == 0 || p->n_q == 0) return DB200_OK;
+  // one query per head (KV-cache decoding, bf16): the streaming kernel of decode.cu instead of a 128-query tile
+  if (attn_decode_supported(*p)) return attn_decode_launch(*p, (cudaStream_t)stream);
   // DALLE_B200_ATTN = simt | mma | tc   (default: see attn_default_backend)
   const int be = attn_backend(*p);
   if (be == 2) return attn_fwd_tc_launch(*p, (cudaStream_t)stream);
@@ -319,6 +327,20 @@ int dalle_b200_sample_topk_gumbel(const void* logits, int dtype, int rows, int v
   DB200_CHECK_ARG(k >= 1 && k <= vocab && temperature > 0.f, "sample_topk_gumbel: need 1 <= k <= vocab and temperature > 0");
   if ((size_t)vocab * 4 > 200 * 1024) return set_error(DB200_ERR_UNSUPPORTED, "sample_topk_gumbel: vocab=%d does not fit the shared-memory row buffer", vocab);
   return sample_topk_gumbel_launch(logits, dtype, rows, vocab, ld, k, temperature, gumbel, seed, offset, reinterpret_cast<long long*>(out), (cudaStream_t)stream);
+}
+
+int dalle_b200_decode_shift(const float* h, void* y, int out_dtype, int batch, int d, float* ring_top, float* ring_left, const int64_t* pos,
+                            int text_len, int fmap, void* stream) {
+  DB200_CHECK_ARG(h && y && ring_top && ring_left && pos && dtype_ok(out_dtype), "decode_shift: null tensor / bad dtype");
+  DB200_CHECK_ARG(batch >= 0 && d > 0 && (d & 3) == 0 && fmap > 0 && text_len >= 0, "decode_shift: bad shape (d must be a multiple of 4)");
+  return decode_shift_launch(h, y, out_dtype, batch, d, ring_top, ring_left, reinterpret_cast<const long long*>(pos), text_len, fmap, (cudaStream_t)stream);
+}
+
+int dalle_b200_decode_kv_append(const void* k_new, const void* v_new, void* k_cache, void* v_cache, int dtype, int batch_heads, int dim_head,
+                                int kv_rows, const int64_t* pos, void* stream) {
+  DB200_CHECK_ARG(k_new && v_new && k_cache && v_cache && pos && dtype_ok(dtype), "decode_kv_append: null tensor / bad dtype");
+  DB200_CHECK_ARG(batch_heads >= 0 && dim_head > 0 && kv_rows > 0, "decode_kv_append: bad shape");
+  return decode_kv_append_launch(k_new, v_new, k_cache, v_cache, dtype, batch_heads, dim_head, kv_rows, reinterpret_cast<const long long*>(pos), (cudaStream_t)stream);
 }
 
 int dalle_b200_dropout(const void* x, void* y, int dtype, int64_t count, float p, uint64_t seed, uint64_t offset, void* stream) {

@@ -32,6 +32,13 @@ from collections import deque
 import torch
 
 GRAPH_DEFAULT = os.environ.get('DALLE_B200_DECODE_GRAPH', '1') != '0'
+# flat step: the layers are walked by GraphedDecoder itself with the decode kernels (LayerNorm -> dalle_b200_decode_shift -> QKV ->
+# dalle_b200_decode_kv_append -> attention -> out-projection with the LayerScale + residual in its epilogue): 11 launches per layer
+# instead of the ~30 of the module nest (whose token-shift cache is seven torch index kernels per sub-layer)
+FLAT_DEFAULT = os.environ.get('DALLE_B200_DECODE_FLAT', '0') == '1'
+# attention reads only the first n_k = roundup(position + 1, BUCKET) rows of the cache; one graph is captured per bucket (0 = always
+# the whole buffer, one graph)
+BUCKET_DEFAULT = int(os.environ.get('DALLE_B200_DECODE_BUCKET', '0'))
 WARMUP_STEPS = 2
 
 
@@ -99,6 +106,38 @@ def _attention_layers(model):
     return found
 
 
+class _FlatSub:
+    __slots__ = ('kind', 'ln', 'shift_key', 'mod', 'scale', 'attn_key')
+
+
+def _flat_plan(model):
+    """The sub-layers of the stack resolved to (LayerNorm, token-shift cache key, Attention | FeedForward, LayerScale vector), or
+    None when the flat step does not cover the model (sandwich norm, channel count not a multiple of 4)."""
+    from .attention import Attention
+    from .transformer import CachedAs, PreShiftToken, FeedForward
+    if _attention_layers(model) is None:
+        return None
+    plan = []
+    for pair in model.transformer.layers.layers:
+        for ls in pair:
+            pre = ls.fn
+            if pre.sandwich or pre.norm.weight.shape[0] % 4:
+                return None
+            r = _FlatSub()
+            r.ln, r.scale, r.shift_key, r.attn_key = pre.norm, ls.scale, None, None
+            inner = pre.fn
+            if isinstance(inner, CachedAs) and isinstance(inner.fn, PreShiftToken):
+                r.shift_key = inner.cache_key
+                inner = inner.fn.fn
+            if isinstance(inner, FeedForward):
+                r.kind, r.mod = 'ff', inner
+            else:
+                assert isinstance(inner, CachedAs) and type(inner.fn) is Attention
+                r.kind, r.mod, r.attn_key = 'attn', inner.fn, inner.cache_key
+            plan.append(r)
+    return plan
+
+
 def eligible(model, text, cond_scale):
     return bool(text.is_cuda and cond_scale == 1 and _attention_layers(model) is not None)
 
@@ -147,8 +186,10 @@ class GraphedDecoder:
                 cache[key] = ShiftRing.from_deque(cache[key], pos, *self.shift)
         self.tok = torch.zeros(self.batch, device=dev, dtype=torch.int64)
         self.logits = None
-        self.graph = None
+        self.graph, self.graphs = None, {}
         self.warm = 0
+        self.cap, self.n_k, self.bucket = cap, None, BUCKET_DEFAULT
+        self.plan = _flat_plan(model) if FLAT_DEFAULT else None
         cache['pos_t'] = self.pos_t          # marks the cache as device-indexed for PreShiftToken / Attention
 
     def _step(self):
@@ -156,13 +197,15 @@ class GraphedDecoder:
         if self.shift is not None:
             cache['shift_idx'] = shift_indices(pos, *self.shift)
         cache['rot_row'] = (self.cos.index_select(0, pos), self.sin.index_select(0, pos))
-        km = {tkey: tab.index_select(0, pos).expand(self.batch, -1).contiguous() for tkey, tab in self.allow.items()}
+        nk = self.cap if self.n_k is None else self.n_k
+        km = {tkey: tab.index_select(0, pos)[:, :nk].expand(self.batch, -1).contiguous() for tkey, tab in self.allow.items()}
         cache['key_mask'] = {key: km[tkey] for key, tkey in self.allow_key.items()}
+        cache['n_k'] = self.n_k
         tokens = m.image_emb(self.tok[:, None])
         if m.stable:
             alpha = 0.1
             tokens = tokens * alpha + tokens.detach() * (1 - alpha)
-        out = m.transformer(tokens, cache=cache)
+        out = self._flat_layers(tokens) if self.plan is not None else m.transformer(tokens, cache=cache)
         if m.stable:
             out = m.norm_by_max(out)
         logits = m.to_logits(out)
@@ -172,9 +215,46 @@ class GraphedDecoder:
         self.logits.copy_(logits)
         pos.add_(1)
 
+    def _flat_layers(self, tokens):
+        """The transformer stack for one token per sequence, sub-layer by sub-layer on the library kernels (see FLAT_DEFAULT)."""
+        from . import ops, config
+        from .functional import _w
+        from ._lib import ATTN_FULL
+        cache, b = self.cache, self.batch
+        dtype = config.compute_dtype()
+        x = tokens.reshape(b, -1).float().contiguous()
+        d = x.shape[1]
+        cos_r, sin_r = cache['rot_row']
+        for r in self.plan:
+            ln = r.ln
+            if r.shift_key is not None:
+                h, _, _ = ops.ln_shift_fwd(x.view(1, b, d), ln.weight, ln.bias, torch.float32, 0, 1, do_ln=True, do_shift=False, eps=ln.eps)
+                ring = cache[r.shift_key]
+                a = ops.decode_shift(h, ring.top, ring.left, self.pos_t, self.shift[0], self.shift[1], dtype)
+            else:
+                a, _, _ = ops.ln_shift_fwd(x.view(1, b, d), ln.weight, ln.bias, dtype, 0, 1, do_ln=True, do_shift=False, eps=ln.eps)
+            sc = r.scale.detach().reshape(-1).contiguous()
+            if r.kind == 'attn':
+                m = r.mod
+                ent = cache[r.attn_key]
+                q, k, v = ops.gemm_qkv(a, _w(m.to_qkv.weight, dtype), b, 1, m.heads, m.dim_head, cos_r, sin_r, m.scale, pos_offset=0)
+                ops.decode_kv_append(k, v, ent.k, ent.v, self.pos_t)
+                o, _ = ops.attn_fwd(ops.AttnSpec(ATTN_FULL, causal=False, stable=m.stable), q, ent.k, ent.v, cache['key_mask'][r.attn_key],
+                                    n_k=self.n_k)
+                x, _ = ops.gemm_resid(o.view(b, -1), _w(m.to_out[0].weight, dtype), m.to_out[0].bias.detach(), x, sc, 1.0)
+            else:
+                f = r.mod
+                hh, _ = ops.gemm_geglu(a, _w(f.net[0].weight, dtype), f.net[0].bias.detach(), keep_u=False)
+                x, _ = ops.gemm_resid(hh, _w(f.net[3].weight, dtype), f.net[3].bias.detach(), x, sc, 1.0)
+        return x.view(b, 1, d)
+
     def step(self, sample):
         """sample: [b] image-token ids of the position just generated -> logits [b, total_tokens] of the next position."""
         self.tok.copy_(sample)
+        if self.bucket > 0:                                  # keys this token can see, rounded up to the bucket
+            nk = min(self.cap, -(-(int(self.cache['offset']) + 1) // self.bucket) * self.bucket)
+            if nk != self.n_k:
+                self.n_k, self.graph = nk, self.graphs.get(nk)
         if self.graph is None and self.warm < WARMUP_STEPS:
             self._step()                                     # eager: allocator, weight-copy and autocast caches, cuBLAS handles
             self.warm += 1
@@ -184,7 +264,7 @@ class GraphedDecoder:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._step()
-                self.graph = g
+                self.graph = self.graphs[self.n_k] = g
             self.graph.replay()
         self.cache['offset'] += 1
         return self.logits

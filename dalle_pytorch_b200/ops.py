@@ -202,6 +202,29 @@ def sample_topk_gumbel(logits, thres=0.5, temperature=1.0, seed=0, offset=0, gum
     return out
 
 
+def decode_shift(h, ring_top, ring_left, pos_t, text_len, fmap, out_dtype):
+    """One decoding step of PreShiftToken (include/dalle_b200.h): h [b,d] fp32 (normalised token), rings fp32 [fmap,b,d/4] /
+    [fmap,b,d/2-d/4], pos_t int64 [1] on the device -> y [b,d] out_dtype; the rings are updated in place."""
+    b, d = h.shape
+    assert h.dtype == torch.float32 and ring_top.dtype == torch.float32 and ring_left.dtype == torch.float32 and pos_t.dtype == torch.int64
+    assert ring_top.shape == (fmap, b, d // 4) and ring_left.shape == (fmap, b, d // 2 - d // 4) and d % 4 == 0
+    y = torch.empty(b, d, device=h.device, dtype=out_dtype)
+    _lib.check(_lib.lib().dalle_b200_decode_shift(_p(_c(h)), _p(y), dt_code(out_dtype), b, d, _p(_c(ring_top)), _p(_c(ring_left)), _p(pos_t),
+                                                  int(text_len), int(fmap), _stream()), 'decode_shift')
+    _count()
+    return y
+
+
+def decode_kv_append(k_new, v_new, k_cache, v_cache, pos_t):
+    """k_new, v_new [b,h,1,dh] -> row pos_t (int64 [1] on the device) of the in-place caches [b,h,rows,dh]."""
+    b, h, one, dh = k_new.shape
+    assert one == 1 and v_new.shape == k_new.shape and k_cache.shape == v_cache.shape and k_cache.shape[:2] == (b, h) and k_cache.shape[3] == dh
+    assert k_new.dtype == v_new.dtype == k_cache.dtype == v_cache.dtype and pos_t.dtype == torch.int64
+    _lib.check(_lib.lib().dalle_b200_decode_kv_append(_p(_c(k_new)), _p(_c(v_new)), _p(_c(k_cache)), _p(_c(v_cache)), dt_code(k_cache.dtype), b * h, dh,
+                                                      k_cache.shape[2], _p(pos_t), _stream()), 'decode_kv_append')
+    _count()
+
+
 def dropout_(x, p, seed, offset):
     """In place: x[i] <- keep(i) ? x[i] / (1 - p) : 0 with the Philox mask of (seed, offset) (include/dalle_b200.h)."""
     _lib.check(_lib.lib().dalle_b200_dropout(_p(_c(x)), _p(x), dt_code(x.dtype), x.numel(), float(p), int(seed) & (2 ** 64 - 1), int(offset), _stream()),

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DALLE_B200_VERSION 110
+#define DALLE_B200_VERSION 111
 
 typedef enum {
   DB200_OK = 0,
@@ -264,6 +264,18 @@ int dalle_b200_resid_scale(const void* y, int dtype, const float* resid, const f
  * that pointer is not NULL (tests).  logits: [rows, ld] (dtype), out: int64 [rows]. */
 int dalle_b200_sample_topk_gumbel(const void* logits, int dtype, int rows, int vocab, int64_t ld, int k, float temperature, const float* gumbel,
                                   uint64_t seed, uint64_t offset, int64_t* out, void* stream);
+/* Graph-replayed decoding (dalle_pytorch_b200/decode.py): one new token per sequence, its POSITION read from device memory (`pos`,
+ * one int64) so that one captured launch sequence serves every token.
+ * decode_shift: PreShiftToken's cache branch (reference transformer.py:155-170) for the token at position *pos.  h [batch, d] fp32 =
+ * the token after PreNorm; ring_top [fmap, batch, d/4], ring_left [fmap, batch, d/2 - d/4] fp32 = the first-half channels of the
+ * last `fmap` image tokens, slot = (position - text_len) mod fmap.  y [batch, d] (out_dtype) = [ring_top[slot] | ring_left[slot-1]
+ * (zeros when slot == 0) | h[d/2:]]; the token's own first half replaces ring slot `slot`. */
+int dalle_b200_decode_shift(const float* h, void* y, int out_dtype, int batch, int d, float* ring_top, float* ring_left, const int64_t* pos,
+                            int text_len, int fmap, void* stream);
+/* decode_kv_append: k_new / v_new [batch_heads, dim_head] -> row *pos of the in-place caches k_cache / v_cache
+ * [batch_heads, kv_rows, dim_head] (reference attention.py:71-76 re-allocates the cache with torch.cat instead). */
+int dalle_b200_decode_kv_append(const void* k_new, const void* v_new, void* k_cache, void* v_cache, int dtype, int batch_heads, int dim_head,
+                                int kv_rows, const int64_t* pos, void* stream);
 
 /* Dropout with a counter-based generator (attention.py:53-56, transformer.py:117): y[i] = keep(i) ? x[i] / (1 - p) : 0 where
  * keep(i) = word (i & 3) of Philox4x32-10(key = seed, counter = offset + i / 4) <= (1 - p) * 2^32.  In place allowed (y == x).

@@ -67,8 +67,27 @@ def _gemm_geglu(A, W1, b1, keep_u=True, backend=None):
     return u[:, :H] * F.gelu(u[:, H:]), (u if keep_u else None)
 
 
+def _decode_shift(h, ring_top, ring_left, pos_t, text_len, fmap, out_dtype):
+    slot = (int(pos_t) - text_len) % fmap
+    prev = (slot + fmap - 1) % fmap
+    q, half = h.shape[1] // 4, h.shape[1] // 2
+    y = h.clone()
+    y[:, :q] = ring_top[slot]
+    y[:, q:half] = ring_left[prev] if slot != 0 else 0.
+    ring_top[slot] = h[:, :q]
+    ring_left[slot] = h[:, q:half]
+    return y.to(out_dtype)
+
+
+def _decode_kv_append(k_new, v_new, k_cache, v_cache, pos_t):
+    k_cache[:, :, int(pos_t)] = k_new[:, :, 0]
+    v_cache[:, :, int(pos_t)] = v_new[:, :, 0]
+
+
 @pytest.fixture
 def cpu_kernels(monkeypatch):
+    monkeypatch.setattr(ops, 'decode_shift', _decode_shift)
+    monkeypatch.setattr(ops, 'decode_kv_append', _decode_kv_append)
     monkeypatch.setattr(ops, 'ln_shift_fwd', _ln_shift_fwd)
     monkeypatch.setattr(ops, 'gemm_qkv', _gemm_qkv)
     monkeypatch.setattr(ops, 'attn_fwd', _attn_fwd)
@@ -91,13 +110,18 @@ def _model(attn_types=('full',), shift_tokens=True, stable=False, optimize=False
     return m.eval()
 
 
+@pytest.mark.parametrize('flat,bucket', [(False, 0), (True, 0), (False, 4), (True, 8)])
 @pytest.mark.parametrize('name,kw', [
     ('full_shift', dict()),
     ('full_noshift', dict(shift_tokens=False)),
     ('axial_static_masks', dict(attn_types=('axial_row', 'axial_col'), optimize=True, depth=3)),
     ('stable', dict(stable=True)),
 ])
-def test_device_indexed_step_equals_host_indexed_step(cpu_kernels, name, kw):
+def test_device_indexed_step_equals_host_indexed_step(cpu_kernels, monkeypatch, name, kw, flat, bucket):
+    """flat = GraphedDecoder walks the layers itself (decode kernels + fused LayerScale/residual epilogue) instead of the module
+    nest; bucket = attention reads only the first roundup(position + 1, bucket) cache rows."""
+    monkeypatch.setattr(decode, 'FLAT_DEFAULT', flat)
+    monkeypatch.setattr(decode, 'BUCKET_DEFAULT', bucket)
     m = _model(**kw)
     T, n_img = m.text_seq_len, m.image_seq_len
     g = torch.Generator().manual_seed(1)
@@ -109,11 +133,14 @@ def test_device_indexed_step_equals_host_indexed_step(cpu_kernels, name, kw):
         want = [m(text, img[:, :k], cache=host)[:, -1] for k in range(n_img)]            # host-indexed: one forward per position
         got = [m(text, img[:, :0], cache=dev)[:, -1]]
         dec = decode.GraphedDecoder(m, dev)
+        assert (dec.plan is not None) == flat
         if kw.get('shift_tokens', True):
             assert any(isinstance(v, decode.ShiftRing) for v in dev.values()) and not any(isinstance(v, deque) for v in dev.values())
         for k in range(1, n_img):
             got.append(dec.step(img[:, k - 1]).clone())
     assert dev['offset'] == host['offset'] == T + n_img and int(dec.pos_t) == T + n_img
+    if bucket:
+        assert dec.n_k == min(dec.cap, -(-(T + n_img) // bucket) * bucket)               # the last token sees T + n_img keys
     for k, (a, b) in enumerate(zip(want, got)):
         assert a.shape == b.shape
         live = a > NEG / 2

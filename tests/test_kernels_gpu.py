@@ -582,6 +582,96 @@ def test_inplace_kv_cache_attention():
             report(f'in-place cache n_k={n_k} {dtype}', a, w, 1e-6, 1e-6)
 
 
+# ---- decoding kernels (csrc/decode.cu): position read from device memory ----------------------------------------------------------
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_decode_shift_and_kv_append_kernels(dtype):
+    """dalle_b200_decode_shift == the cache branch of PreShiftToken (transformer.py:155-170) written with torch indexing, over a run of
+    consecutive positions (ring wrap-around, first-of-row zeroing); dalle_b200_decode_kv_append == a row assignment."""
+    o = ops()
+    torch.manual_seed(61)
+    for b, d, fm, text_len in ((3, 128, 4, 9), (2, 1024, 32, 257), (1, 64, 1, 5), (5, 40, 3, 2)):
+        q, half = d // 4, d // 2
+        top = torch.randn(fm, b, q, device='cuda')
+        left = torch.randn(fm, b, half - q, device='cuda')
+        top_w, left_w = top.clone(), left.clone()
+        pos_t = torch.tensor([text_len + 2], device='cuda', dtype=torch.int64)
+        for step in range(2 * fm + 3):
+            h = torch.randn(b, d, device='cuda')
+            pos = int(pos_t)
+            slot = (pos - text_len) % fm
+            prev = (slot + fm - 1) % fm
+            want = h.clone()
+            want[:, :q] = top_w[slot]
+            want[:, q:half] = left_w[prev] if slot != 0 else 0.
+            top_w[slot] = h[:, :q]
+            left_w[slot] = h[:, q:half]
+            got = o.decode_shift(h, top, left, pos_t, text_len, fm, dtype)
+            assert got.dtype == dtype and torch.equal(got, want.to(dtype)), (b, d, fm, step)
+            assert torch.equal(top, top_w) and torch.equal(left, left_w), (b, d, fm, step)
+            pos_t.add_(1)
+    bsz, h_, dh, cap = 2, 3, 64, 37
+    kc, vc = _mk((bsz, h_, cap, dh), dtype), _mk((bsz, h_, cap, dh), dtype)
+    kw, vw = kc.clone(), vc.clone()
+    for pos in (0, 5, 36):
+        kn, vn = _mk((bsz, h_, 1, dh), dtype), _mk((bsz, h_, 1, dh), dtype)
+        o.decode_kv_append(kn, vn, kc, vc, torch.tensor([pos], device='cuda', dtype=torch.int64))
+        kw[:, :, pos], vw[:, :, pos] = kn[:, :, 0], vn[:, :, 0]
+        assert torch.equal(kc, kw) and torch.equal(vc, vw)
+
+
+@pytest.mark.parametrize('n_k,cap', [(1, 1), (7, 40), (64, 64), (513, 600), (1281, 1281), (1500, 1536)])
+def test_single_query_attention_kernel(n_k, cap, monkeypatch):
+    """attn_decode_kernel (one query per head, bf16): against the fp32 softmax of the same operands for the causal, key-masked,
+    static-mask and axial patterns, a fully masked row (uniform attention, as the reference's -fp32max fill gives), and against the
+    general tensor-core kernel (DALLE_B200_DECODE_ATTN=0)."""
+    o = ops()
+    torch.manual_seed(62 + n_k)
+    b, h, dh = 2, 3, 64
+    q = _mk((b, h, 1, dh), torch.bfloat16, dh ** -0.5 * 3)
+    kbuf, vbuf = _mk((b, h, cap, dh), torch.bfloat16), _mk((b, h, cap, dh), torch.bfloat16)
+    kbuf[:, :, n_k:] = 3.0e4
+    vbuf[:, :, n_k:] = -3.0e4
+    s = torch.einsum('bhqd,bhkd->bhqk', q.float(), kbuf[:, :, :n_k].float())[:, :, 0]            # [b, h, n_k]
+    neg = -torch.finfo(torch.float32).max
+
+    def want(allowed):                                                                      # allowed: bool [b, n_k]
+        p = s.masked_fill(~allowed[:, None, :], neg).softmax(dim=-1)
+        return torch.einsum('bhk,bhkd->bhd', p, vbuf[:, :, :n_k].float()).reshape(b, 1, h * dh)
+
+    all_keys = torch.ones(b, n_k, dtype=torch.bool, device='cuda')
+    cases = [('causal', o.AttnSpec(0, causal=True), None, all_keys)]
+    km = torch.rand(b, n_k, device='cuda') > 0.4
+    km[:, 0] = True
+    cases.append(('key mask, non-causal', o.AttnSpec(0, causal=False), km.to(torch.uint8).contiguous(), km))
+    km0 = km.clone()
+    km0[1] = False                                                                          # batch 1: no key allowed -> uniform
+    cases.append(('fully masked row', o.AttnSpec(0, causal=False), km0.to(torch.uint8).contiguous(), km0))
+    sm = torch.rand(n_k, n_k, device='cuda') > 0.5
+    sm[:, 0] = True
+    cases.append(('static mask', o.AttnSpec(4, causal=True, static_mask=sm.to(torch.uint8).contiguous()), None, sm[n_k - 1][None].expand(b, -1)))
+    T, fm = 5, 6
+    if n_k > T + 1:
+        j = torch.arange(n_k, device='cuda')
+        qi = n_k - 1 - T
+        row_ok = (j < T) | (((j - T) // fm == qi // fm) & (j <= n_k - 1))
+        cases.append(('axial row predicate', o.AttnSpec(1, causal=True, text_len=T, fmap=fm), None, row_ok[None].expand(b, -1)))
+    for name, spec, mask, allowed in cases:
+        monkeypatch.setenv('DALLE_B200_DECODE_ATTN', '1')
+        got, lse = o.attn_fwd(spec, q, kbuf, vbuf, mask, n_k=n_k)
+        assert got.shape == (b, 1, h * dh) and torch.isfinite(got.float()).all()
+        w = want(allowed)
+        if name == 'fully masked row':
+            w[1] = vbuf[1, :, :n_k].float().mean(dim=1).reshape(1, h * dh)
+        report(f'single-query attention n_k={n_k} {name}', got, w, 2e-2, 4e-3)
+        w_lse = s.masked_fill(~allowed[:, None, :], neg).logsumexp(dim=-1)
+        if name != 'fully masked row':
+            report(f'single-query lse n_k={n_k} {name}', lse[:, :, 0], w_lse, 1e-3, 1e-3)
+        if name in ('causal', 'key mask, non-causal', 'static mask'):                       # the combinations the decoding paths use
+            monkeypatch.setenv('DALLE_B200_DECODE_ATTN', '0')
+            ref, _ = o.attn_fwd(spec, q, kbuf, vbuf, mask, n_k=n_k)
+            report(f'single-query vs general kernel n_k={n_k} {name}', got, ref, 2e-2, 6e-3)
+
+
 # ---- tcgen05 GEMM at benchmark scale (persistent multi-wave grid, dynamic tile scheduler, split-K, all operand majors) -----------
 @pytest.mark.parametrize('name,M,N,K,a_mn,b_mn,out_f32', [
     ('fwd FF1-like (store)', 20480, 4096, 1024, False, False, False),

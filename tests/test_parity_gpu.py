@@ -329,13 +329,19 @@ def test_generate_images_cached_and_uncached():
             report(f'cached logits step {cur}', step[live], full[live], 1e-4, 1e-5)
 
 
+@pytest.mark.parametrize('mode', ['nest', 'flat', 'flat_bucket'])
 @pytest.mark.parametrize('variant', ['full_shift_bf16', 'axial_static_fp32', 'full_noshift_stable_fp32'])
-def test_generate_images_graph_replay(variant, monkeypatch):
+def test_generate_images_graph_replay(variant, mode, monkeypatch):
     """decode.GraphedDecoder: after the prompt pass every image token is one CUDA-graph replay whose position is a device tensor
     (rotary row, KV write, allowed keys, token-shift slot selected on the device).  Same seed -> the same image tokens as the
-    host-indexed cached loop, and teacher-forced logits equal the host-indexed cached step at every position."""
+    host-indexed cached loop, and teacher-forced logits equal the host-indexed cached step at every position.
+    mode: 'nest' = the captured step walks the module nest; 'flat' = GraphedDecoder walks the layers with the decode kernels
+    (dalle_b200_decode_shift / decode_kv_append, LayerScale + residual in the projection epilogue); 'flat_bucket' = additionally one
+    graph per 16-key bucket of visible cache rows."""
     import dalle_pytorch_b200 as D
     from dalle_pytorch_b200 import decode
+    monkeypatch.setattr(decode, 'FLAT_DEFAULT', mode != 'nest')
+    monkeypatch.setattr(decode, 'BUCKET_DEFAULT', 16 if mode == 'flat_bucket' else 0)
     kw = dict(full_shift_bf16=dict(attn_types=('full',), shift_tokens=True),
               axial_static_fp32=dict(attn_types=('axial_row', 'axial_col'), shift_tokens=True, optimize_for_inference=True),
               full_noshift_stable_fp32=dict(attn_types=('full',), shift_tokens=False, stable=True))[variant]
@@ -361,6 +367,7 @@ def test_generate_images_graph_replay(variant, monkeypatch):
             torch.manual_seed(5)
             toks[on] = m.generate_images(text, use_cache=True, filter_thres=0.9).cpu()
         assert len(made) == 1 and made[0].graph is not None, 'the second call must have captured and replayed a graph'
+        assert (made[0].plan is not None) == (mode != 'nest') and len(made[0].graphs) == (5 if mode == 'flat_bucket' else 1)
         assert int(made[0].pos_t) == m.total_seq_len and made[0].cache['offset'] == m.total_seq_len
         assert torch.equal(toks[False], toks[True]), (toks[False], toks[True])
         # teacher-forced logits, position by position (the decoder is driven by hand: eager warm-up steps, capture, replays)

@@ -14,5 +14,5 @@ if __name__ == '__main__':
 
     class A:
         pass
-    out = bench.measure_decode(A(), {'dev': torch.device('cuda:0')}, batch=batch)
+    out = bench.measure_decode(A(), {'dev': torch.device('cuda:0')}, batch=batch, host_indexed='--graph-only' not in sys.argv)
     print(json.dumps(out))
