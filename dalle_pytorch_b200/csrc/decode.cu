@@ -223,12 +223,12 @@ __global__ void __launch_bounds__(DA_THREADS) attn_decode_kernel(const __nv_bflo
 
 static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// DALLE_B200_DECODE_ATTN=1 routes single-query attention here, 0 / unset to the general kernels (A/B timing, tests)
+// DALLE_B200_DECODE_ATTN=0 sends single-query attention back to the general kernels (A/B timing, tests)
 bool attn_decode_supported(const db200_attn_fwd_params& p) {
   if (!(p.n_q == 1 && p.n_k >= 1 && p.dtype == DB200_BF16 && p.dim_head == DA_DH && !p.gather && al16(p.q) && al16(p.k) && al16(p.v)))
     return false;
   const char* e = getenv("DALLE_B200_DECODE_ATTN");
-  return e && e[0] == '1';
+  return !(e && e[0] == '0');
 }
 
 int attn_decode_launch(const db200_attn_fwd_params& p, cudaStream_t st) {

@@ -20,8 +20,11 @@ so the whole step (embedding of the previous sample -> transformer -> logits hea
 generator per step (exactly like the eager path, so the same seed gives the same tokens).  The first step (the prompt) and two
 warm-up steps run eagerly through the same code.
 
-Measured on B200 (C2 weights, batch 16, 1024 image tokens, bf16; tools/decode_probe.py): 5 734 generated tokens/s = 2.79 ms per
-token step against 3 186 tokens/s = 5.02 ms for the host-indexed loop of the same call.
+Measured on B200 (C2 weights, batch 16, 1024 image tokens, bf16; tools/decode_probe.py, profiles/r02_decode_matrix.txt), generated
+tokens/s of one generate_images call:  host-indexed loop 3 186 (5.02 ms per token step) -> graph replay of the module nest 6 296 ->
+flat step (FLAT_DEFAULT) 7 953 -> + 256-key buckets (BUCKET_DEFAULT) 8 896 -> + the single-query attention kernel of
+csrc/decode.cu 10 444 (1.53 ms per step).  One step of the first graph was 364 kernels / 2.84 ms (profiles/r02_decode_step_launches.txt:
+29 % attention over the whole buffer on 128-query tiles, 28 % the four M = 16 GEMMs per layer, 32 % torch index glue).
 
 `DALLE_B200_DECODE_GRAPH=0` restores the host-indexed loop (see GRAPH_DEFAULT); models the path does not cover (reversible executor,
 sparse-pattern layers that re-run the prefix, classifier-free guidance with cond_scale != 1) use the eager loop.
@@ -35,10 +38,10 @@ GRAPH_DEFAULT = os.environ.get('DALLE_B200_DECODE_GRAPH', '1') != '0'
 # flat step: the layers are walked by GraphedDecoder itself with the decode kernels (LayerNorm -> dalle_b200_decode_shift -> QKV ->
 # dalle_b200_decode_kv_append -> attention -> out-projection with the LayerScale + residual in its epilogue): 11 launches per layer
 # instead of the ~30 of the module nest (whose token-shift cache is seven torch index kernels per sub-layer)
-FLAT_DEFAULT = os.environ.get('DALLE_B200_DECODE_FLAT', '0') == '1'
+FLAT_DEFAULT = os.environ.get('DALLE_B200_DECODE_FLAT', '1') != '0'
 # attention reads only the first n_k = roundup(position + 1, BUCKET) rows of the cache; one graph is captured per bucket (0 = always
 # the whole buffer, one graph)
-BUCKET_DEFAULT = int(os.environ.get('DALLE_B200_DECODE_BUCKET', '0'))
+BUCKET_DEFAULT = int(os.environ.get('DALLE_B200_DECODE_BUCKET', '256'))
 WARMUP_STEPS = 2
 
 
