@@ -18,7 +18,7 @@ c_int, c_float, c_void_p, c_int64 = ctypes.c_int, ctypes.c_float, ctypes.c_void_
 F32, BF16 = 0, 1
 ATTN_FULL, ATTN_AXIAL_ROW, ATTN_AXIAL_COL, ATTN_CONV_LIKE, ATTN_STATIC = 0, 1, 2, 3, 4
 EPI_STORE, EPI_QKV, EPI_RESID, EPI_GEGLU, EPI_GEGLU_BWD = 0, 1, 2, 3, 4
-GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_SMALLM = 0, 1, 2, 3
 
 
 class LnShiftFwdParams(ctypes.Structure):

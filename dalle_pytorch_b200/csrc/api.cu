@@ -64,6 +64,8 @@ int embed_launch(bool bwd, const long long* ids, const float* a, float* o, int b
 int gemm_simt_launch(const db200_gemm_params& p, cudaStream_t st);
 bool gemm_tcgen05_supported(const db200_gemm_params& p, const char** why);
 int gemm_tcgen05_launch(const db200_gemm_params& p, cudaStream_t st);
+bool gemm_smallm_supported(const db200_gemm_params& p, const char** why);
+int gemm_smallm_launch(const db200_gemm_params& p, cudaStream_t st);
 int attn_fwd_simt_launch(const db200_attn_fwd_params& p, cudaStream_t st);
 int attn_bwd_simt_launch(const db200_attn_bwd_params& p, cudaStream_t st);
 bool attn_mma_supported(const db200_attn_fwd_params& p);
@@ -186,6 +188,11 @@ int dalle_b200_gemm(const db200_gemm_params* p, void* stream) {
   }
   if (p->M == 0) return DB200_OK;
   int backend = p->backend;
+  if (backend == DB200_GEMM_SMALLM) {
+    const char* why = "";
+    if (!gemm_smallm_supported(*p, &why)) return set_error(DB200_ERR_UNSUPPORTED, "gemm: the small-M kernel cannot run this problem: %s", why);
+    return gemm_smallm_launch(*p, (cudaStream_t)stream);
+  }
   if (backend == DB200_GEMM_AUTO) {
     const int env = env_choice("DALLE_B200_GEMM", "simt", "tcgen05");
     if (env == 1) backend = DB200_GEMM_SIMT;

@@ -101,10 +101,11 @@ def gemm_timing(enable):
         return None
     ev, _gemm_events = _gemm_events or [], None
     torch.cuda.synchronize()
-    out = {'tcgen05': {'flops': 0.0, 'ms': 0.0, 'launches': 0}, 'simt': {'flops': 0.0, 'ms': 0.0, 'launches': 0}, 'by_shape': {}}
+    out = {'tcgen05': {'flops': 0.0, 'ms': 0.0, 'launches': 0}, 'simt': {'flops': 0.0, 'ms': 0.0, 'launches': 0},
+           'smallm': {'flops': 0.0, 'ms': 0.0, 'launches': 0}, 'by_shape': {}}
     for s, e, flops, backend, key in ev:
         ms = s.elapsed_time(e)
-        fam = out['tcgen05' if backend == _lib.GEMM_TCGEN05 else 'simt']
+        fam = out['tcgen05' if backend == _lib.GEMM_TCGEN05 else 'smallm' if backend == _lib.GEMM_SMALLM else 'simt']
         fam['flops'] += flops
         fam['ms'] += ms
         fam['launches'] += 1
@@ -135,6 +136,15 @@ def _gemm(P):
     _count()
     key = f"{_EPI_NAMES.get(P.epilogue, '?')}:{'M' if P.a_mn_major else 'K'}{'N' if P.b_mn_major else 'K'}:{P.M}x{P.N}x{P.K}"
     _gemm_events.append((s, e, 2.0 * P.M * P.N * P.K, backend, key))
+
+
+SMALL_M = os.environ.get('DALLE_B200_SMALLM', '1') != '0'      # M <= 16 bf16 GEMMs (decoding) on the weight-streaming kernel
+
+
+def _small_m(A, N, a_mn=False, b_mn=False):
+    """A [M, K] bf16 with M <= 16: the problem db200_gemm_backend::DB200_GEMM_SMALLM covers (csrc/gemm_smallm.cu)."""
+    return (SMALL_M and A.dtype == torch.bfloat16 and not a_mn and not b_mn and 1 <= A.shape[0] <= 16 and A.shape[1] % 256 == 0
+            and N % 16 == 0)
 
 
 def _base(M, N, K, A, lda, a_mn, B, ldb, b_mn, epilogue, backend=GEMM_AUTO):
@@ -268,6 +278,8 @@ def gemm_store(A, B, a_mn=False, b_mn=False, out_dtype=None, bias=None, backend=
     # weight-gradient shapes (few output tiles, very long K): let the kernel split K; it needs a zeroed fp32 C
     split_ok = out_dtype == torch.float32 and bias is None and A.dtype == torch.bfloat16 and M * N <= 4096 * 1024 and K >= 4096
     mc = getattr(out, '_b200_mc', None) if out is not None else None      # (multicast address, scale): data-parallel multimem slot
+    if backend == GEMM_AUTO and mc is None and _small_m(A, N, a_mn, b_mn):
+        backend, split_ok = _lib.GEMM_SMALLM, False
     if C is None:
         C = (torch.zeros if split_ok else torch.empty)(M, N, device=A.device, dtype=out_dtype)
     elif split_ok and mc is None:
@@ -294,6 +306,8 @@ def gemm_qkv(A, W, batch, seq_n, heads, dim_head, cos_t, sin_t, q_scale, pos_off
                                                         dim_head, pos_offset, q_scale, seq_n, _stream()), 'qkv_rotary')
             _count()
             return qkv[0], qkv[1], qkv[2]
+    if backend == GEMM_AUTO and _small_m(A, N) and dim_head % 8 == 0:
+        return gemm_qkv_auto(A, W, batch, seq_n, heads, dim_head, cos_t, sin_t, q_scale, pos_offset, n_alloc=seq_n)   # small-M product + head split
     qkv = torch.empty(3, batch, heads, seq_n, dim_head, device=A.device, dtype=A.dtype)
     P = _base(M, N, K, A, K, False, W, K, False, EPI_QKV, backend)
     P.q, P.k, P.v = _p(qkv[0]), _p(qkv[1]), _p(qkv[2])
@@ -332,6 +346,8 @@ def gemm_resid(A, W, bias, resid, scale, sign=1.0, keep_y=False, backend=GEMM_AU
             return resid_scale(y6, resid, scale, sign), (y6 if keep_y else None)
     out = torch.empty(M, N, device=A.device, dtype=torch.float32)
     y = torch.empty(M, N, device=A.device, dtype=A.dtype) if keep_y else None
+    if backend == GEMM_AUTO and _small_m(A, N):
+        backend = _lib.GEMM_SMALLM
     P = _base(M, N, K, A, K, False, W, K, False, EPI_RESID, backend)
     P.bias, P.resid, P.scale, P.sign, P.y_out, P.out = _p(bias), _p(resid), _p(scale), sign, _p(y), _p(out)
     _gemm(P)
@@ -350,6 +366,8 @@ def gemm_geglu(A, W1, b1, keep_u=True, backend=GEMM_AUTO):
             return geglu_fwd(u6), (u6 if keep_u else None)
     h = torch.empty(M, H, device=A.device, dtype=A.dtype)
     u = torch.empty(M, N, device=A.device, dtype=A.dtype) if keep_u else None
+    if backend == GEMM_AUTO and _small_m(A, N):
+        backend = _lib.GEMM_SMALLM
     P = _base(M, N, K, A, K, False, W1, K, False, EPI_GEGLU, backend)
     P.bias, P.u_out, P.h_out, P.hidden = _p(b1), _p(u), _p(h), H
     _gemm(P)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DALLE_B200_VERSION 111
+#define DALLE_B200_VERSION 112
 
 typedef enum {
   DB200_OK = 0,
@@ -57,7 +57,9 @@ typedef enum {
   DB200_EPI_GEGLU_BWD = 4  /* du = [dh*gelu(g) | dh*a*gelu'(g)]                     autograd of the above      */
 } db200_epilogue;
 
-typedef enum { DB200_GEMM_AUTO = 0, DB200_GEMM_SIMT = 1, DB200_GEMM_TCGEN05 = 2 } db200_gemm_backend;
+/* SMALLM: weight-streaming mma.sync kernel for 1 <= M <= 16 rows (decoding), bf16 K-major operands, K % 256 == 0, STORE / RESID / GEGLU;
+ * chosen explicitly by the caller (AUTO never selects it), DB200_ERR_UNSUPPORTED when the problem does not qualify */
+typedef enum { DB200_GEMM_AUTO = 0, DB200_GEMM_SIMT = 1, DB200_GEMM_TCGEN05 = 2, DB200_GEMM_SMALLM = 3 } db200_gemm_backend;
 
 int dalle_b200_version(void);
 const char* dalle_b200_last_error(void);

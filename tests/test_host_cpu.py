@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_loads_and_exports_header_symbols():
     lib = _lib.lib()
-    assert lib.dalle_b200_version() == 111
+    assert lib.dalle_b200_version() == 112
     hdr = open(os.path.join(ROOT, 'include', 'dalle_b200.h')).read()
     declared = set(re.findall(r'\b(dalle_b200_[a-z0-9_]+)\s*\(', hdr))
     assert declared == set(_lib.EXPORTED), declared ^ set(_lib.EXPORTED)

@@ -672,6 +672,41 @@ def test_single_query_attention_kernel(n_k, cap, monkeypatch):
             report(f'single-query vs general kernel n_k={n_k} {name}', got, ref, 2e-2, 6e-3)
 
 
+@pytest.mark.parametrize('M', [1, 3, 16])
+@pytest.mark.parametrize('N,K', [(1024, 1024), (3072, 1024), (1024, 4096), (64, 256), (48, 768)])
+def test_small_m_gemm_kernel(M, N, K):
+    """gemm_smallm_kernel (mma.sync weight streaming for M <= 16, csrc/gemm_smallm.cu) through the same ops entry points the decoding
+    step uses: STORE (+bias, bf16 / fp32 result), RESID (bias, residual, LayerScale vector, sign, kept y), GEGLU (kept u), against
+    torch's fp32 product of the same bf16 operands -- and the launches really went to the small-M backend."""
+    o = ops()
+    torch.manual_seed(71 + M + N)
+    A, W = _mk((M, K), torch.bfloat16), _mk((N, K), torch.bfloat16, K ** -0.5)
+    bias = _mk((N,), torch.float32)
+    acc = A.float() @ W.float().t()
+    o.gemm_timing(True)
+    got = o.gemm_store(A, W)
+    got_b = o.gemm_store(A, W, bias=bias, out_dtype=torch.float32)
+    resid, scale = _mk((M, N), torch.float32), _mk((N,), torch.float32)
+    out, y = o.gemm_resid(A, W, bias, resid, scale, sign=-1.0, keep_y=True)
+    out2, y2 = o.gemm_resid(A, W, bias, None, None, 1.0)
+    H = N // 2
+    h, u = o.gemm_geglu(A, W, bias, keep_u=True)
+    h2, u2 = o.gemm_geglu(A, W, bias, keep_u=False)
+    st = o.gemm_timing(False)
+    assert st['smallm']['launches'] == 6 and st['tcgen05']['launches'] == 0 and st['simt']['launches'] == 0, st
+    report(f'small-M store {M}x{N}x{K}', got, acc, 1e-2, 1e-2)
+    report(f'small-M store+bias fp32 {M}x{N}x{K}', got_b, acc + bias, 1e-4, 1e-4)
+    report(f'small-M resid {M}x{N}x{K}', out, resid - scale * (acc + bias), 1e-4, 1e-4)
+    report(f'small-M resid y {M}x{N}x{K}', y, acc + bias, 1e-2, 1e-2)
+    report(f'small-M plain projection {M}x{N}x{K}', out2, acc + bias, 1e-4, 1e-4)
+    assert y2 is None and u2 is None
+    ub = acc + bias
+    report(f'small-M geglu u {M}x{N}x{K}', u, ub, 1e-2, 1e-2)
+    want_h = ub[:, :H] * torch.nn.functional.gelu(ub[:, H:])
+    report(f'small-M geglu h {M}x{N}x{K}', h, want_h, 1e-2, 1e-2)
+    assert torch.equal(h, h2)
+
+
 # ---- tcgen05 GEMM at benchmark scale (persistent multi-wave grid, dynamic tile scheduler, split-K, all operand majors) -----------
 @pytest.mark.parametrize('name,M,N,K,a_mn,b_mn,out_f32', [
     ('fwd FF1-like (store)', 20480, 4096, 1024, False, False, False),

@@ -348,7 +348,8 @@ def test_generate_images_graph_replay(variant, mode, monkeypatch):
     dtype = torch.bfloat16 if variant.endswith('bf16') else torch.float32
     torch.manual_seed(21)
     vae = D.TokenVAE(image_size=64, num_layers=3, num_tokens=40)           # fmap 8: 64 image tokens, 61 graph replays
-    m = D.DALLE(dim=128, vae=vae, num_text_tokens=60, text_seq_len=12, depth=3, heads=2, **kw).cuda().eval()
+    wide = variant.endswith('bf16')                   # dim 256 / 4 heads: K = 256 and 1024, the shapes the small-M GEMM kernel takes
+    m = D.DALLE(dim=256 if wide else 128, vae=vae, num_text_tokens=60, text_seq_len=12, depth=3, heads=4 if wide else 2, **kw).cuda().eval()
     for p in m.parameters():
         if p.dim() == 3:                                                   # LayerScale 0.1 -> every branch matters
             torch.nn.init.uniform_(p, 0.5, 1.0)
