@@ -23,7 +23,7 @@ warm-up steps run eagerly through the same code.
 Measured on B200 (C2 weights, batch 16, 1024 image tokens, bf16; tools/decode_probe.py, profiles/r02_decode_matrix.txt), generated
 tokens/s of one generate_images call:  host-indexed loop 3 186 (5.02 ms per token step) -> graph replay of the module nest 6 296 ->
 flat step (FLAT_DEFAULT) 7 953 -> + 256-key buckets (BUCKET_DEFAULT) 8 896 -> + the single-query attention kernel of
-csrc/decode.cu 10 444 (1.53 ms per step).  One step of the first graph was 364 kernels / 2.84 ms (profiles/r02_decode_step_launches.txt:
+csrc/decode.cu 10 444 -> + the small-M weight-streaming GEMM (csrc/gemm_smallm.cu) 13 781 (1.16 ms per step).  One step of the first graph was 364 kernels / 2.84 ms (profiles/r02_decode_step_launches.txt:
 29 % attention over the whole buffer on 128-query tiles, 28 % the four M = 16 GEMMs per layer, 32 % torch index glue).
 
 `DALLE_B200_DECODE_GRAPH=0` restores the host-indexed loop (see GRAPH_DEFAULT); models the path does not cover (reversible executor,
