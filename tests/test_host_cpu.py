@@ -173,3 +173,22 @@ def test_sparse_attention_layout_spec():
     m = a.static_mask
     assert m.shape == (304, 304) and torch.equal(m, L.repeat_interleave(16, 0).repeat_interleave(16, 1))
     assert isinstance(a, D.Attention)                                          # transformer.py:279 decides cache support by this
+
+
+def test_small_m_gemm_dispatch_rule():
+    """ops._small_m: which problems the host sends to DB200_GEMM_SMALLM (bf16, K-major, 1 <= M <= 16, K % 256 == 0, N % 16 == 0)."""
+    import torch
+    from dalle_pytorch_b200 import ops, _lib
+    assert _lib.GEMM_SMALLM == 3
+    bf = lambda m, k: torch.empty(m, k, dtype=torch.bfloat16)
+    assert ops._small_m(bf(16, 1024), 3072) and ops._small_m(bf(1, 256), 16)
+    assert not ops._small_m(bf(17, 1024), 3072)                      # more rows than one mma fragment
+    assert not ops._small_m(bf(16, 1000), 3072) and not ops._small_m(bf(16, 128), 3072)
+    assert not ops._small_m(bf(16, 1024), 3080)
+    assert not ops._small_m(torch.empty(16, 1024), 3072)             # fp32 parity mode keeps its own GEMM evaluation
+    assert not ops._small_m(bf(16, 1024), 3072, a_mn=True) and not ops._small_m(bf(16, 1024), 3072, b_mn=True)
+    was, ops.SMALL_M = ops.SMALL_M, False
+    try:
+        assert not ops._small_m(bf(16, 1024), 3072)                  # DALLE_B200_SMALLM=0
+    finally:
+        ops.SMALL_M = was
