@@ -4,7 +4,7 @@
  * This is the drop-in boundary.  Every entry point replaces an op sequence that the
  * reference (lucidrains/DALLE-pytorch, /root/reference/dalle_pytorch/) evaluates with aten calls; the
  * reference file:line each one stands in for is cited next to its declaration.  The host side
- * (dalle_pytorch_b200/*.py) mirrors the reference's module API and calls these functions through ctypes.
+ * (the .py files of dalle_pytorch_b200/) mirrors the reference's module API and calls these functions through ctypes.
  *
  * Conventions
  *   - plain C: POD parameter structs of raw DEVICE pointers, sizes and flags; no torch types.

@@ -192,3 +192,37 @@ def test_small_m_gemm_dispatch_rule():
         assert not ops._small_m(bf(16, 1024), 3072)                  # DALLE_B200_SMALLM=0
     finally:
         ops.SMALL_M = was
+
+
+def test_header_is_plain_c_and_a_c_client_links_against_the_library(tmp_path):
+    """include/dalle_b200.h is the drop-in boundary: it must compile as C (no C++ / CUDA / torch types) and a C program that only
+    knows the header must link against libdalle_b200.so and read the version and struct sizes (no GPU needed: no compute call)."""
+    import os
+    import shutil
+    import subprocess
+    from dalle_pytorch_b200 import _lib
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, 'include')
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-pedantic', '-fsyntax-only', '-x', 'c', os.path.join(hdr, 'dalle_b200.h')],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = tmp_path / 'client.c'
+    src.write_text('#include <stdio.h>\n#include "dalle_b200.h"\n'
+                   'int main(void) {\n'
+                   '  int sizes[8]; int n = dalle_b200_abi_sizes(sizes, 8);\n'
+                   '  db200_gemm_params g; db200_attn_fwd_params a;\n'
+                   '  printf("%d %d %d %d %d\\n", dalle_b200_version(), n, sizes[2] == (int)sizeof g, sizes[3] == (int)sizeof a, DB200_GEMM_SMALLM);\n'
+                   '  return dalle_b200_gemm(0, 0) == DB200_OK;   /* NULL params are rejected with an error code, not a crash */\n'
+                   '}\n')
+    exe = tmp_path / 'client'
+    _lib.lib()                                         # built in-tree
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(['gcc', '-std=c99', '-I', hdr, str(src), '-o', str(exe), '-L', libdir, '-ldalle_b200', '-Wl,-rpath,' + libdir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    ver, n, gemm_ok, attn_ok, smallm = map(int, r.stdout.split())
+    assert ver == 112 and n >= 4 and gemm_ok == 1 and attn_ok == 1 and smallm == 3
