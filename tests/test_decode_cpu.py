@@ -214,3 +214,37 @@ def test_allow_table_and_shift_ring_against_brute_force():
             pos_t.add_(1)
         assert len(fa.seen) == len(fb.seen) == seq_len - n0 + 1
         assert all(torch.equal(u, v) for u, v in zip(fa.seen, fb.seen)), (fm, T, prime)
+
+
+def test_graphed_decoder_drives_a_patched_reference_model(cpu_kernels):
+    """a reference `DALLE` built after `patch_dalle_pytorch()` keeps the reference's own generate loop, but
+    `decode.GraphedDecoder` can take over its cache after the prompt pass -- it only touches attributes both DALLE classes share.
+    Device-indexed steps == the reference DALLE's own host-indexed cached forward, position by position."""
+    import ref_import
+    if not ref_import.reference_available():
+        pytest.skip('reference not present')
+    ref = ref_import.import_reference()
+    undo = D.patch_dalle_pytorch()
+    try:
+        torch.manual_seed(0)
+        vae = ref.DiscreteVAE(image_size=32, num_layers=3, num_tokens=24, codebook_dim=16, hidden_dim=8)       # fmap 4
+        m = ref.DALLE(dim=32, vae=vae, num_text_tokens=30, text_seq_len=6, depth=2, heads=2, dim_head=16, attn_types=('axial_row', 'axial_col'),
+                      shift_tokens=True, optimize_for_inference=True).eval()
+    finally:
+        undo()
+    assert type(m).__module__.startswith('dalle_pytorch.') and decode._attention_layers(m) is not None and decode._flat_plan(m) is not None
+    T, n_img = m.text_seq_len, m.image_seq_len
+    g = torch.Generator().manual_seed(4)
+    text = torch.randint(1, 30, (2, T), generator=g)
+    img = torch.randint(0, 24, (2, n_img), generator=g)
+    with torch.no_grad():
+        host, dev = {}, {}
+        want = [m(text, img[:, :k], cache=host)[:, -1] for k in range(n_img)]
+        got = [m(text, img[:, :0], cache=dev)[:, -1]]
+        dec = decode.GraphedDecoder(m, dev)
+        for k in range(1, n_img):
+            got.append(dec.step(img[:, k - 1]).clone())
+    for k, (a, b) in enumerate(zip(want, got)):
+        live = a > NEG / 2
+        assert torch.equal(live, b > NEG / 2), k
+        assert torch.allclose(a[live], b[live], rtol=1e-5, atol=1e-6), (k, float((a[live] - b[live]).abs().max()))
